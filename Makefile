@@ -1,0 +1,27 @@
+# Builds libmpvss_b200.so (CUDA kernels + C ABI) for sm_100a, the test-only emulator
+# and the oracle's C baseline.  `python -c "import __graft_entry__ as g; g.build()"` runs this.
+NVCC      ?= nvcc
+CXX       ?= g++
+CSRC      := mpvss_rs_b200/csrc
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread
+LIB       := mpvss_rs_b200/libmpvss_b200.so
+CU        := $(CSRC)/api.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu
+OBJ       := $(CU:.cu=.o)
+HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/mpvss_b200.h
+
+all: $(LIB) emu
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) -shared -o $@ $(OBJ) -Xcompiler -pthread
+
+emu: tests/emu/libemu_modp.so
+tests/emu/libemu_modp.so: tests/emu/emu_modp.cpp $(HDR)
+	$(CXX) -std=c++20 -O2 -DMPVSS_SIMT_EMU -shared -fPIC -pthread -o $@ $<
+
+clean:
+	rm -f $(OBJ) $(LIB) tests/emu/*.so
+
+.PHONY: all emu clean

@@ -1,0 +1,185 @@
+// extern "C" surface of libmpvss_b200.so (declared in include/mpvss_b200.h): context
+// management, error reporting and dispatch to the per-group implementations.
+#include "ctx.h"
+
+int mpvss_fail(mpvss_ctx* ctx, int status, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return status;
+}
+int mpvss_cuda_fail(mpvss_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear the sticky flag of non-fatal errors
+  return MPVSS_ERR_CUDA;
+}
+
+void timing_begin(mpvss_ctx* ctx) {
+  ctx->last_launches = 0;
+  ctx->last_ms = 0.f;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  ctx->timing_open = true;
+}
+void timing_launch(mpvss_ctx* ctx, int n) { ctx->last_launches += n; }
+int timing_end(mpvss_ctx* ctx) {
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  MPVSS_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->timing_open = false;
+  return MPVSS_OK;
+}
+
+namespace {
+struct Guard {
+  mpvss_ctx* c;
+  explicit Guard(mpvss_ctx* ctx) : c(ctx) {
+    c->mu.lock();
+    cudaSetDevice(c->device);
+  }
+  ~Guard() { c->mu.unlock(); }
+};
+int unsupported(mpvss_ctx* ctx, const char* fn) {
+  return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, std::string(fn) + ": not available for this group in this build");
+}
+}  // namespace
+
+#define DISPATCH(ctx, fn, ...)                                             \
+  do {                                                                     \
+    if (!(ctx)) return MPVSS_ERR_ARG;                                      \
+    Guard _g(ctx);                                                         \
+    switch ((ctx)->group) {                                                \
+      case MPVSS_GROUP_MODP: return modp_api::fn(ctx, __VA_ARGS__);        \
+      default: return unsupported(ctx, #fn);                               \
+    }                                                                      \
+  } while (0)
+
+extern "C" {
+
+int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
+  if (!out) return MPVSS_ERR_ARG;
+  *out = nullptr;
+  if (group < MPVSS_GROUP_MODP || group > MPVSS_GROUP_RISTRETTO255) return MPVSS_ERR_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return MPVSS_ERR_CUDA;  // no CPU fallback: the hot path exists only on the GPU
+  }
+  mpvss_ctx* ctx = new mpvss_ctx();
+  ctx->group = group;
+  ctx->device = device;
+  auto bail = [&](int s) {
+    mpvss_ctx_destroy(ctx);
+    return s;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
+    return bail(MPVSS_ERR_CUDA);
+  int s = MPVSS_OK;
+  if (group == MPVSS_GROUP_MODP) s = modp_api::init(ctx);
+  if (s != MPVSS_OK) return bail(s);
+  *out = ctx;
+  return MPVSS_OK;
+}
+
+void mpvss_ctx_destroy(mpvss_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  modp_api::destroy(ctx);
+  for (auto& b : ctx->scratch) b.release();
+  for (auto& b : ctx->pinned) b.release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mpvss_last_error(const mpvss_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return MPVSS_ERR_ARG;
+  Guard g(ctx);
+  if (std::string(key) == "modp_tpi") {
+    if (value != 4 && value != 8 && value != 16) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_tpi must be 4, 8 or 16");
+    ctx->modp_tpi = value;
+    return MPVSS_OK;
+  }
+  return mpvss_fail(ctx, MPVSS_ERR_ARG, std::string("unknown tunable: ") + key);
+}
+
+size_t mpvss_element_bytes(const mpvss_ctx* ctx) {
+  if (!ctx) return 0;
+  return ctx->group == MPVSS_GROUP_MODP ? 256 : ctx->group == MPVSS_GROUP_SECP256K1 ? 33 : 32;
+}
+size_t mpvss_scalar_bytes(const mpvss_ctx* ctx) {
+  if (!ctx) return 0;
+  return ctx->group == MPVSS_GROUP_MODP ? 256 : 32;
+}
+float mpvss_last_kernel_ms(const mpvss_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+int mpvss_last_kernel_launches(const mpvss_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int mpvss_batch_exp(mpvss_ctx* ctx, const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n,
+                    uint8_t* out) {
+  DISPATCH(ctx, batch_exp, bases, base_stride, scalars, n, out);
+}
+int mpvss_fixed_base_exp(mpvss_ctx* ctx, int generator, const uint8_t* scalars, size_t n, uint8_t* out) {
+  DISPATCH(ctx, fixed_base_exp, generator, scalars, n, out);
+}
+int mpvss_batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  DISPATCH(ctx, batch_mul, a, b, n, out);
+}
+int mpvss_poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
+                        uint8_t* out) {
+  DISPATCH(ctx, poly_eval_exp, commitments, t, positions, n, out);
+}
+int mpvss_dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2,
+                             const uint8_t* h2, const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n,
+                             uint8_t* a1, uint8_t* a2) {
+  DISPATCH(ctx, dleq_verify_commit, g1, h1, g2, h2, r, c, c_stride, n, a1, a2);
+}
+int mpvss_dleq_prove_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* g2, const uint8_t* w, size_t n,
+                            uint8_t* a1, uint8_t* a2) {
+  DISPATCH(ctx, dleq_prove_commit, g1, g2, w, n, a1, a2);
+}
+int mpvss_multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* out) {
+  DISPATCH(ctx, multi_exp, bases, scalars, n, out);
+}
+int mpvss_verify_distribution_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
+                                    const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,
+                                    const uint8_t* responses, const uint8_t* challenge) {
+  DISPATCH(ctx, verify_stage, n, t, commitments, positions, publickeys, shares, responses, challenge);
+}
+int mpvss_verify_distribution_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out,
+                                  uint8_t* digest_out) {
+  DISPATCH(ctx, verify_run, ok, x_out, a1_out, a2_out, digest_out);
+}
+int mpvss_verify_distribution(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
+                              const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,
+                              const uint8_t* responses, const uint8_t* challenge, int* ok, uint8_t* x_out,
+                              uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
+  int s = mpvss_verify_distribution_stage(ctx, n, t, commitments, positions, publickeys, shares, responses, challenge);
+  if (s != MPVSS_OK) return s;
+  return mpvss_verify_distribution_run(ctx, ok, x_out, a1_out, a2_out, digest_out);
+}
+int mpvss_distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t secret_len,
+                     const uint8_t* coeffs, const uint8_t* witnesses, const uint8_t* publickeys,
+                     uint8_t* commitments_out, uint8_t* shares_out, uint8_t* challenge_out, uint8_t* responses_out,
+                     uint8_t* u_out, uint8_t* x_out) {
+  DISPATCH(ctx, distribute, n, t, secret, secret_len, coeffs, witnesses, publickeys, commitments_out, shares_out,
+           challenge_out, responses_out, u_out, x_out);
+}
+int mpvss_extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const uint8_t* witnesses,
+                         const uint8_t* enc_shares, uint8_t* publickeys_out, uint8_t* shares_out,
+                         uint8_t* challenges_out, uint8_t* responses_out, int* status_out) {
+  DISPATCH(ctx, extract_shares, n, private_keys, witnesses, enc_shares, publickeys_out, shares_out, challenges_out,
+           responses_out, status_out);
+}
+int mpvss_verify_shares(mpvss_ctx* ctx, size_t n, const uint8_t* publickeys, const uint8_t* shares,
+                        const uint8_t* enc_shares, const uint8_t* challenges, const uint8_t* responses, int* ok_out) {
+  DISPATCH(ctx, verify_shares, n, publickeys, shares, enc_shares, challenges, responses, ok_out);
+}
+int mpvss_reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_t* shares, const uint8_t* u,
+                      uint8_t* secret_out, uint8_t* gs_out) {
+  DISPATCH(ctx, reconstruct, k, positions, shares, u, secret_out, gs_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Internal context shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/mpvss_b200.h"
+#include "bigint.h"
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct mpvss_ctx {
+  int group = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  std::string err;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  bool timing_open = false;
+
+  // ---- ModpGroup ----
+  int modp_tpi = 8;
+  big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
+  DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
+  DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
+  std::vector<DevBuf> scratch;  // call-local device buffers, reused across calls
+  std::vector<PinBuf> pinned;   // call-local pinned host buffers
+  // staged verify_distribution state
+  size_t v_n = 0, v_t = 0;
+  uint32_t v_ndigits = 0, v_rwin = 0, v_cwin = 0;
+  std::vector<uint8_t> v_challenge;
+  DevBuf v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+
+  DevBuf& buf(size_t i) {
+    if (scratch.size() <= i) scratch.resize(i + 1);
+    return scratch[i];
+  }
+  PinBuf& pin(size_t i) {
+    if (pinned.size() <= i) pinned.resize(i + 1);
+    return pinned[i];
+  }
+};
+
+int mpvss_fail(mpvss_ctx* ctx, int status, const std::string& msg);
+int mpvss_cuda_fail(mpvss_ctx* ctx, cudaError_t e, const char* what);
+
+#define MPVSS_CUDA(ctx, expr)                                        \
+  do {                                                               \
+    cudaError_t _e = (expr);                                         \
+    if (_e != cudaSuccess) return mpvss_cuda_fail(ctx, _e, #expr);   \
+  } while (0)
+#define MPVSS_TRY(expr)            \
+  do {                             \
+    int _s = (expr);               \
+    if (_s != MPVSS_OK) return _s; \
+  } while (0)
+
+// kernel-time bracket (CUDA events on the library stream)
+void timing_begin(mpvss_ctx* ctx);
+void timing_launch(mpvss_ctx* ctx, int n = 1);
+int timing_end(mpvss_ctx* ctx);
+
+// ---- per-group implementations (modp_api.cu, secp_api.cu, rist_api.cu) ----
+namespace modp_api {
+int init(mpvss_ctx* ctx);
+void destroy(mpvss_ctx* ctx);
+int batch_exp(mpvss_ctx*, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*);
+int fixed_base_exp(mpvss_ctx*, int, const uint8_t*, size_t, uint8_t*);
+int batch_mul(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int poly_eval_exp(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
+int dleq_verify_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                       const uint8_t*, size_t, size_t, uint8_t*, uint8_t*);
+int dleq_prove_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, uint8_t*, uint8_t*);
+int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
+                 const uint8_t*, const uint8_t*);
+int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
+               uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,
+                   uint8_t*, int*);
+int verify_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                  int*);
+int reconstruct(mpvss_ctx*, size_t, const int64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*);
+}  // namespace modp_api

@@ -1,0 +1,83 @@
+// __global__ entry points for the ModpGroup kernels (bodies in modp_kernels.cuh).
+#include <cuda_runtime.h>
+#include "modp_kernels.cuh"
+#include "modp_launch.h"
+
+namespace modp {
+
+constexpr int WARPS_PER_CTA = 4;
+
+template <int TPI>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t w = threadIdx.x >> 5;
+  horner_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>);
+}
+
+template <int TPI>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) exp2_kernel(Exp2Args A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t w = threadIdx.x >> 5;
+  exp2_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * exp2_smem_words<TPI>);
+}
+
+template <int TPI>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) mul_kernel(MulArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t w = threadIdx.x >> 5;
+  mul_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * mul_smem_words<TPI>);
+}
+
+template <int TPI>
+static uint32_t ctas_for(uint32_t n) {
+  uint32_t per_cta = WARPS_PER_CTA * (32 / TPI);
+  return (n + per_cta - 1) / per_cta;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define MODP_DISPATCH(tpi, ...)                            \
+  switch (tpi) {                                           \
+    case 4: { constexpr int T = 4; __VA_ARGS__; break; }   \
+    case 8: { constexpr int T = 8; __VA_ARGS__; break; }   \
+    case 16: { constexpr int T = 16; __VA_ARGS__; break; } \
+    default: return cudaErrorInvalidValue;                 \
+  }
+
+cudaError_t launch_horner(int tpi, const HornerArgs& A, cudaStream_t s) {
+  if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
+  MODP_DISPATCH(tpi, {
+    size_t sm = WARPS_PER_CTA * horner_smem_words<T> * 4;
+    cudaError_t e = set_smem(horner_kernel<T>, sm);
+    if (e != cudaSuccess) return e;
+    horner_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
+  if (A.n == 0 || A.e1_windows == 0 || (A.b2 && A.e2_windows == 0)) return cudaErrorInvalidValue;
+  MODP_DISPATCH(tpi, {
+    size_t sm = WARPS_PER_CTA * exp2_smem_words<T> * 4;
+    cudaError_t e = set_smem(exp2_kernel<T>, sm);
+    if (e != cudaSuccess) return e;
+    exp2_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mul(int tpi, const MulArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  MODP_DISPATCH(tpi, {
+    size_t sm = WARPS_PER_CTA * mul_smem_words<T> * 4;
+    cudaError_t e = set_smem(mul_kernel<T>, sm);
+    if (e != cudaSuccess) return e;
+    mul_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+}  // namespace modp

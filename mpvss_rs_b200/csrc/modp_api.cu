@@ -1,0 +1,706 @@
+// ModpGroup side of the C ABI: host orchestration of the CUDA kernels plus the
+// CPU-resident pieces north_star keeps on the host (Fiat-Shamir SHA-256 over
+// identically serialised values, scalar arithmetic mod q-1 / g).
+//
+// Reference semantics restated here (paths under /root/reference/src):
+//   transcript framing            dleq.rs:58-61, 87-99
+//   challenge = hash_to_scalar(H) participant.rs:251-252, modp.rs:142-148
+//   minimal big-endian bytes      modp.rs:150-152
+//   responses                     participant.rs:255-264, modp.rs:180-192
+//   U mask                        participant.rs:267-272, 512-518
+//   Lagrange exponents            participant.rs:526-561, util.rs:47-64
+#include <thread>
+#include "ctx.h"
+#include "modp_launch.h"
+#include "sha2.h"
+
+namespace {
+
+constexpr size_t EB = 256;  // element / scalar bytes at the boundary
+constexpr size_t EW = 64;   // u32 limbs
+
+const char* RFC3526_2048 =
+    "ffffffffffffffffc90fdaa22168c234c4c6628b80dc1cd129024e088a67cc74"
+    "020bbea63b139b22514a08798e3404ddef9519b3cd3a431b302b0a6df25f1437"
+    "4fe1356d6d51c245e485b576625e7ec6f44c42e9a637ed6b0bff5cb6f406b7ed"
+    "ee386bfb5a899fa5ae9f24117c4b1fe649286651ece45b3dc2007cb8a163bf05"
+    "98da48361c55d39a69163fa8fd24cf5f83655d23dca3ad961c62f356208552bb"
+    "9ed529077096966d670c354e4abc9804f1746c08ca18217c32905e462e36ce3b"
+    "e39e772c180e86039b2783a2ec07a28fb5c55df06f4c52c9de2bcbf695581718"
+    "3995497cea956ae515d2261898fa051015728e5a8aacaa68ffffffffffffffff";
+
+big::Int from_hex(const char* s) {
+  size_t n = strlen(s);
+  std::vector<uint8_t> be((n + 1) / 2, 0);
+  for (size_t i = 0; i < n; ++i) {
+    char c = s[n - 1 - i];
+    uint8_t v = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+    be[be.size() - 1 - i / 2] |= v << (4 * (i % 2));
+  }
+  return big::from_be(be.data(), be.size());
+}
+
+void fill_consts(const big::Int& m, uint32_t* blk) {
+  memset(blk, 0, modp::C_WORDS * 4);
+  big::Int R(65, 0);
+  R[64] = 1;
+  big::Int nq = big::sub(R, m), one = big::mod(R, m), r2 = big::mulmod(one, one, m);
+  auto put = [&](const big::Int& v, int off) {
+    for (size_t i = 0; i < v.size(); ++i) blk[off + i] = v[i];
+  };
+  put(m, modp::C_Q);
+  put(nq, modp::C_NQ);
+  put(one, modp::C_ONE);
+  put(r2, modp::C_R2);
+  uint32_t inv = 1, m0 = m[0];  // Newton: inv = m0^-1 mod 2^32
+  for (int i = 0; i < 5; ++i) inv *= 2u - m0 * inv;
+  blk[modp::C_NP] = 0u - inv;
+}
+
+// minimal-length big-endian bytes of a 256-byte little-endian value (modp.rs:150-152)
+size_t min_be(const uint8_t* le, uint8_t* out) {
+  size_t len = EB;
+  while (len > 1 && le[len - 1] == 0) --len;
+  for (size_t i = 0; i < len; ++i) out[i] = le[len - 1 - i];
+  return len;
+}
+void framed_update(sha2::Sha256& h, const uint8_t* le) {  // dleq.rs:58-61
+  uint8_t tmp[EB], len8[8] = {0};
+  size_t len = min_be(le, tmp);
+  len8[6] = (uint8_t)(len >> 8);
+  len8[7] = (uint8_t)len;
+  h.update(len8, 8);
+  h.update(tmp, len);
+}
+// challenge = int_be(SHA-256(digest)) mod g, as a 256-byte LE scalar (modp.rs:142-148)
+void challenge_from_digest(const mpvss_ctx* ctx, const uint8_t digest[32], uint8_t out[EB]) {
+  uint8_t h2[32];
+  sha2::sha256(digest, 32, h2);
+  big::Int c = big::mod(big::from_be(h2, 32), ctx->g);
+  big::to_le(c, out, EB);
+}
+uint32_t windows_for(const uint8_t* scalars, size_t stride, size_t n) {
+  size_t top = 0;  // highest non-zero byte index + 1 over all scalars
+  for (size_t i = 0; i < n; ++i) {
+    const uint8_t* s = scalars + i * stride;
+    size_t len = EB;
+    while (len > top && s[len - 1] == 0) --len;
+    if (len > top) top = len;
+    if (top == EB) break;
+  }
+  uint32_t w = (uint32_t)(top * 2);
+  return w ? w : 1;
+}
+uint32_t ndigits_for(uint64_t maxpos) {
+  uint32_t d = 1;
+  while (maxpos >> (2 * d)) ++d;
+  return d;
+}
+
+int h2d(mpvss_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+  MPVSS_CUDA(ctx, b.ensure(bytes));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return MPVSS_OK;
+}
+int d2h(mpvss_ctx* ctx, void* dst, const DevBuf& b, size_t bytes) {
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MPVSS_OK;
+}
+int sync(mpvss_ctx* ctx) {
+  MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPVSS_OK;
+}
+
+// device-pointer exponentiation:  out = b1^e1 [* b2^e2]
+int dev_exp2(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
+             uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s,
+             uint32_t e2w, size_t n, uint32_t* out) {
+  modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w};
+  MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, ctx->stream));
+  timing_launch(ctx);
+  return MPVSS_OK;
+}
+int dev_mul(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* a, uint32_t as, const uint32_t* b, uint32_t bs,
+            uint32_t mode, size_t n, uint32_t* out) {
+  modp::MulArgs A{consts, a, b, out, (uint32_t)n, mode, as, bs};
+  MPVSS_CUDA(ctx, modp::launch_mul(ctx->modp_tpi, A, ctx->stream));
+  timing_launch(ctx);
+  return MPVSS_OK;
+}
+
+int check_args(mpvss_ctx* ctx, bool ok, const char* what) {
+  if (!ok) return mpvss_fail(ctx, MPVSS_ERR_ARG, what);
+  return MPVSS_OK;
+}
+
+// P(x) mod (q-1) for x = first..first+count-1 by Horner with lazy reduction.  q-1 has an
+// all-ones top limb, so floor(acc / 2^2048) is the quotient estimate and
+// acc - hi*2^2048 + hi*delta (delta = 2^2048 - (q-1)) keeps acc below 2^2048 + 2^2002.
+// Equals Polynomial::get_value(x) % order (polynomial.rs:50-58, participant.rs:202).
+void poly_eval_range(const uint32_t* coeffs, size_t t, const uint32_t* order, const int64_t* positions, size_t first,
+                     size_t count, uint8_t* out) {
+  uint32_t delta[EW];
+  {
+    uint64_t br = 0;
+    for (size_t i = 0; i < EW; ++i) {  // 2^2048 - order
+      uint64_t d = (uint64_t)0 - order[i] - br;
+      delta[i] = (uint32_t)d;
+      br = (d >> 32) & 1;
+    }
+  }
+  for (size_t idx = first; idx < first + count; ++idx) {
+    uint64_t x = (uint64_t)(positions ? positions[idx] : (int64_t)idx + 1);
+    uint32_t acc[EW + 2] = {0};
+    for (size_t j = t; j-- > 0;) {
+      // acc = acc * x + a_j   (x < 2^32 assumed by the caller)
+      uint64_t c = 0;
+      const uint32_t* a = coeffs + j * EW;
+      for (size_t i = 0; i < EW; ++i) {
+        c += (uint64_t)acc[i] * x + a[i];
+        acc[i] = (uint32_t)c;
+        c >>= 32;
+      }
+      c += (uint64_t)acc[EW] * x;
+      // fold everything at or above 2^2048 back: hi * delta
+      for (int round = 0; round < 2; ++round) {
+        uint64_t hi = c;
+        if (!hi) break;
+        uint64_t cc = 0;
+        for (size_t i = 0; i < EW; ++i) {
+          unsigned __int128 p = (unsigned __int128)hi * delta[i] + acc[i] + cc;
+          acc[i] = (uint32_t)p;
+          cc = (uint64_t)(p >> 32);
+        }
+        c = cc;
+      }
+      acc[EW] = (uint32_t)c;
+    }
+    // final canonical reduction
+    big::Int v(acc, acc + EW + 1);
+    big::trim(v);
+    big::Int m(order, order + EW);
+    big::trim(m);
+    v = big::mod(v, m);
+    big::to_le(v, out + idx * EB, EB);
+  }
+}
+
+}  // namespace
+
+namespace modp_api {
+
+int init(mpvss_ctx* ctx) {
+  ctx->q = from_hex(RFC3526_2048);
+  ctx->qm1 = big::sub(ctx->q, big::from_u64(1));
+  ctx->g = big::shr1(ctx->qm1);
+  std::vector<uint32_t> blk(modp::C_WORDS);
+  fill_consts(ctx->q, blk.data());
+  MPVSS_TRY(h2d(ctx, ctx->consts_q, blk.data(), blk.size() * 4));
+  fill_consts(ctx->g, blk.data());
+  MPVSS_TRY(h2d(ctx, ctx->consts_g, blk.data(), blk.size() * 4));
+  std::vector<uint32_t> gens(128, 0);
+  gens[0] = 2;   // Group::generator()           modp.rs:64
+  gens[64] = 4;  // Group::subgroup_generator()  modp.rs:65-66
+  MPVSS_TRY(h2d(ctx, ctx->gens, gens.data(), gens.size() * 4));
+  return sync(ctx);
+}
+
+void destroy(mpvss_ctx* ctx) {
+  for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2})
+    b->release();
+}
+
+int batch_exp(mpvss_ctx* ctx, const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n,
+              uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, bases && scalars && out && n > 0 && (base_stride == 0 || base_stride == EB),
+                       "batch_exp: bad arguments"));
+  DevBuf &db = ctx->buf(0), &de = ctx->buf(1), &dout = ctx->buf(2);
+  MPVSS_TRY(h2d(ctx, db, bases, base_stride ? n * EB : EB));
+  MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
+  MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), db.as<uint32_t>(), base_stride ? EW : 0, de.as<uint32_t>(), EW,
+                     windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n, dout.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dout, n * EB));
+  return sync(ctx);
+}
+
+int fixed_base_exp(mpvss_ctx* ctx, int generator, const uint8_t* scalars, size_t n, uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, scalars && out && n > 0 && (generator == MPVSS_GEN_MAIN || generator == MPVSS_GEN_SUBGROUP),
+                       "fixed_base_exp: bad arguments"));
+  DevBuf &de = ctx->buf(1), &dout = ctx->buf(2);
+  MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
+  MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), ctx->gens.as<uint32_t>() + (generator ? 64 : 0), 0,
+                     de.as<uint32_t>(), EW, windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n,
+                     dout.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dout, n * EB));
+  return sync(ctx);
+}
+
+int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, a && b && out && n > 0, "batch_mul: bad arguments"));
+  DevBuf &da = ctx->buf(0), &db = ctx->buf(1), &dout = ctx->buf(2);
+  MPVSS_TRY(h2d(ctx, da, a, n * EB));
+  MPVSS_TRY(h2d(ctx, db, b, n * EB));
+  MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), da.as<uint32_t>(), EW, db.as<uint32_t>(), EW, 0, n,
+                    dout.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dout, n * EB));
+  return sync(ctx);
+}
+
+// positions -> u32 array + digit count
+static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, std::vector<uint32_t>& pos,
+                          uint32_t* ndigits) {
+  pos.resize(n);
+  uint64_t mx = 1;
+  for (size_t i = 0; i < n; ++i) {
+    int64_t p = positions ? positions[i] : (int64_t)i + 1;
+    if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
+    pos[i] = (uint32_t)p;
+    if ((uint64_t)p > mx) mx = (uint64_t)p;
+  }
+  *ndigits = ndigits_for(mx);
+  return MPVSS_OK;
+}
+
+// commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
+static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos, size_t n,
+                      uint32_t ndigits, uint32_t* x) {
+  MPVSS_CUDA(ctx, cm.ensure(t * EB));
+  MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
+  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, x, (uint32_t)t, (uint32_t)n, ndigits};
+  MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
+  timing_launch(ctx);
+  return MPVSS_OK;
+}
+
+int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
+                  uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, commitments && out && n > 0 && t > 0, "poly_eval_exp: bad arguments"));
+  std::vector<uint32_t> pos;
+  uint32_t nd;
+  MPVSS_TRY(prep_positions(ctx, positions, n, pos, &nd));
+  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3);
+  MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
+  MPVSS_TRY(h2d(ctx, dp, pos.data(), n * 4));
+  MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), n, nd, dout.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dout, n * EB));
+  return sync(ctx);
+}
+
+int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2, const uint8_t* h2,
+                       const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n, uint8_t* a1, uint8_t* a2) {
+  MPVSS_TRY(check_args(ctx, g1 && h1 && g2 && h2 && r && c && a1 && a2 && n > 0 && (c_stride == 0 || c_stride == EB),
+                       "dleq_verify_commit: bad arguments"));
+  DevBuf &dg1 = ctx->buf(0), &dh1 = ctx->buf(1), &dg2 = ctx->buf(2), &dh2 = ctx->buf(3), &dr = ctx->buf(4),
+         &dc = ctx->buf(5), &da1 = ctx->buf(6), &da2 = ctx->buf(7);
+  MPVSS_TRY(h2d(ctx, dg1, g1, EB));
+  MPVSS_TRY(h2d(ctx, dh1, h1, n * EB));
+  MPVSS_TRY(h2d(ctx, dg2, g2, n * EB));
+  MPVSS_TRY(h2d(ctx, dh2, h2, n * EB));
+  MPVSS_TRY(h2d(ctx, dr, r, n * EB));
+  MPVSS_TRY(h2d(ctx, dc, c, c_stride ? n * EB : EB));
+  MPVSS_CUDA(ctx, da1.ensure(n * EB));
+  MPVSS_CUDA(ctx, da2.ensure(n * EB));
+  uint32_t rw = windows_for(r, EB, n), cw = windows_for(c, EB, c_stride ? n : 1), cs = c_stride ? EW : 0;
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, K, dg1.as<uint32_t>(), 0, dr.as<uint32_t>(), EW, rw, dh1.as<uint32_t>(), EW,
+                     dc.as<uint32_t>(), cs, cw, n, da1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, dg2.as<uint32_t>(), EW, dr.as<uint32_t>(), EW, rw, dh2.as<uint32_t>(), EW,
+                     dc.as<uint32_t>(), cs, cw, n, da2.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
+  MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
+  return sync(ctx);
+}
+
+int dleq_prove_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* g2, const uint8_t* w, size_t n, uint8_t* a1,
+                      uint8_t* a2) {
+  MPVSS_TRY(check_args(ctx, g1 && g2 && w && a1 && a2 && n > 0, "dleq_prove_commit: bad arguments"));
+  DevBuf &dg1 = ctx->buf(0), &dg2 = ctx->buf(2), &dw = ctx->buf(4), &da1 = ctx->buf(6), &da2 = ctx->buf(7);
+  MPVSS_TRY(h2d(ctx, dg1, g1, EB));
+  MPVSS_TRY(h2d(ctx, dg2, g2, n * EB));
+  MPVSS_TRY(h2d(ctx, dw, w, n * EB));
+  MPVSS_CUDA(ctx, da1.ensure(n * EB));
+  MPVSS_CUDA(ctx, da2.ensure(n * EB));
+  uint32_t ww = windows_for(w, EB, n);
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, K, dg1.as<uint32_t>(), 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
+                     da1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, dg2.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
+                     da2.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
+  MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
+  return sync(ctx);
+}
+
+// in-place pairwise product tree over `n` device elements; the result lands in slot 0
+static int dev_product_tree(mpvss_ctx* ctx, uint32_t* v, DevBuf& tmp, size_t n) {
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  MPVSS_CUDA(ctx, tmp.ensure(((n + 1) / 2) * EB));
+  while (n > 1) {
+    size_t half = n / 2;
+    // tmp[i] = v[i] * v[i + half]
+    MPVSS_TRY(dev_mul(ctx, K, v, EW, v + half * EW, EW, 0, half, tmp.as<uint32_t>()));
+    if (n & 1)
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(tmp.as<uint32_t>() + half * EW, v + 2 * half * EW, EB, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+    n = half + (n & 1);
+    MPVSS_CUDA(ctx, cudaMemcpyAsync(v, tmp.p, n * EB, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return MPVSS_OK;
+}
+
+int multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, bases && scalars && out && n > 0, "multi_exp: bad arguments"));
+  DevBuf &db = ctx->buf(0), &de = ctx->buf(1), &dout = ctx->buf(2), &tmp = ctx->buf(3);
+  MPVSS_TRY(h2d(ctx, db, bases, n * EB));
+  MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
+  MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), db.as<uint32_t>(), EW, de.as<uint32_t>(), EW,
+                     windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n, dout.as<uint32_t>()));
+  MPVSS_TRY(dev_product_tree(ctx, dout.as<uint32_t>(), tmp, n));
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dout, EB));
+  return sync(ctx);
+}
+
+// ------------------------------------------------------------------- verify ----
+int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments, const int64_t* positions,
+                 const uint8_t* publickeys, const uint8_t* shares, const uint8_t* responses, const uint8_t* challenge) {
+  MPVSS_TRY(check_args(ctx, n > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
+                       "verify_distribution: bad arguments"));
+  std::vector<uint32_t> pos;
+  MPVSS_TRY(prep_positions(ctx, positions, n, pos, &ctx->v_ndigits));
+  MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
+  MPVSS_TRY(h2d(ctx, ctx->v_pos, pos.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
+  MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
+  MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
+  MPVSS_TRY(h2d(ctx, ctx->v_c, challenge, EB));
+  MPVSS_CUDA(ctx, ctx->v_x.ensure(n * EB));
+  MPVSS_CUDA(ctx, ctx->v_a1.ensure(n * EB));
+  MPVSS_CUDA(ctx, ctx->v_a2.ensure(n * EB));
+  ctx->v_rwin = windows_for(responses, EB, n);
+  ctx->v_cwin = windows_for(challenge, EB, 1);
+  ctx->v_challenge.assign(challenge, challenge + EB);
+  ctx->v_n = n;
+  ctx->v_t = t;
+  return sync(ctx);  // the host buffers may be released by the caller after return
+}
+
+int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
+  MPVSS_TRY(check_args(ctx, ok && ctx->v_n > 0, "verify_distribution_run: nothing staged"));
+  const size_t n = ctx->v_n, t = ctx->v_t;
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  uint32_t* X = ctx->v_x.as<uint32_t>();
+  timing_begin(ctx);
+  // X_i from the commitments (participant.rs:423-434)
+  MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(), n, ctx->v_ndigits, X));
+  // a1 = g^r * X^c ; a2 = y^r * Y^c  (dleq.rs:66-84)
+  MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
+                     ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
+                     ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
+                     ctx->v_a2.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  // results back in index order; Y comes from the staged copy so the hash sees what was verified
+  PinBuf &hx = ctx->pin(0), &ha1 = ctx->pin(1), &ha2 = ctx->pin(2), &hy = ctx->pin(3);
+  MPVSS_CUDA(ctx, hx.ensure(n * EB));
+  MPVSS_CUDA(ctx, ha1.ensure(n * EB));
+  MPVSS_CUDA(ctx, ha2.ensure(n * EB));
+  MPVSS_CUDA(ctx, hy.ensure(n * EB));
+  MPVSS_TRY(d2h(ctx, hx.p, ctx->v_x, n * EB));
+  MPVSS_TRY(d2h(ctx, hy.p, ctx->v_y, n * EB));
+  MPVSS_TRY(d2h(ctx, ha1.p, ctx->v_a1, n * EB));
+  MPVSS_TRY(d2h(ctx, ha2.p, ctx->v_a2, n * EB));
+  MPVSS_TRY(sync(ctx));
+  sha2::Sha256 h;
+  for (size_t i = 0; i < n; ++i) {  // participant.rs:438-447 -> dleq.rs:87-99, order (X, Y, a1, a2)
+    framed_update(h, hx.as<uint8_t>() + i * EB);
+    framed_update(h, hy.as<uint8_t>() + i * EB);
+    framed_update(h, ha1.as<uint8_t>() + i * EB);
+    framed_update(h, ha2.as<uint8_t>() + i * EB);
+  }
+  uint8_t digest[32], c[EB];
+  h.finalize(digest);
+  challenge_from_digest(ctx, digest, c);
+  *ok = memcmp(c, ctx->v_challenge.data(), EB) == 0;  // participant.rs:451-454
+  if (x_out) memcpy(x_out, hx.p, n * EB);
+  if (a1_out) memcpy(a1_out, ha1.p, n * EB);
+  if (a2_out) memcpy(a2_out, ha2.p, n * EB);
+  if (digest_out) memcpy(digest_out, digest, 32);
+  return MPVSS_OK;
+}
+
+// --------------------------------------------------------------- distribute ----
+int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t secret_len, const uint8_t* coeffs,
+               const uint8_t* witnesses, const uint8_t* publickeys, uint8_t* commitments_out, uint8_t* shares_out,
+               uint8_t* challenge_out, uint8_t* responses_out, uint8_t* u_out, uint8_t* x_out) {
+  MPVSS_TRY(check_args(ctx, n > 0 && t > 0 && t <= n && secret && coeffs && witnesses && publickeys &&
+                                commitments_out && shares_out && challenge_out && responses_out && u_out &&
+                                secret_len <= EB,
+                       "distribute: bad arguments (threshold <= n, participant.rs:166)"));
+  std::vector<uint32_t> order(EW, 0);
+  for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
+  // p_i = P(i) mod (q-1) on the host cores (participant.rs:202); index 0 of `pz` is P(0)
+  std::vector<uint8_t> p(n * EB);
+  {
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<std::thread> th;
+    size_t chunk = (n + nt - 1) / nt;
+    for (unsigned k = 0; k < nt; ++k) {
+      size_t first = k * chunk;
+      if (first >= n) break;
+      size_t count = std::min(chunk, n - first);
+      th.emplace_back([&, first, count] {
+        poly_eval_range(reinterpret_cast<const uint32_t*>(coeffs), t, order.data(), nullptr, first, count, p.data());
+      });
+    }
+    for (auto& x : th) x.join();
+  }
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  const uint32_t* G = ctx->gens.as<uint32_t>();
+  DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dw = ctx->buf(2), &dpk = ctx->buf(3), &dC = ctx->buf(4),
+         &dX = ctx->buf(5), &dY = ctx->buf(6), &dA1 = ctx->buf(7), &dA2 = ctx->buf(8), &dGs = ctx->buf(9);
+  // s = P(0) mod (q-1) = a_0 mod (q-1)  (participant.rs:267)
+  uint8_t s_le[EB];
+  big::to_le(big::mod(big::from_le(coeffs, EB), ctx->qm1), s_le, EB);
+  DevBuf& ds = ctx->buf(10);
+  MPVSS_TRY(h2d(ctx, dco, coeffs, t * EB));
+  MPVSS_TRY(h2d(ctx, dp, p.data(), n * EB));
+  MPVSS_TRY(h2d(ctx, dw, witnesses, n * EB));
+  MPVSS_TRY(h2d(ctx, dpk, publickeys, n * EB));
+  MPVSS_TRY(h2d(ctx, ds, s_le, EB));
+  for (DevBuf* b : {&dX, &dY, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
+  MPVSS_CUDA(ctx, dC.ensure(t * EB));
+  MPVSS_CUDA(ctx, dGs.ensure(EB));
+  uint32_t cw = windows_for(coeffs, EB, t), pw = windows_for(p.data(), EB, n), ww = windows_for(witnesses, EB, n);
+  timing_begin(ctx);
+  // C_j = g^a_j (participant.rs:189-193)
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dco.as<uint32_t>(), EW, cw, nullptr, 0, nullptr, 0, 0, t, dC.as<uint32_t>()));
+  // X_i = prod_j C_j^(i^j) = g^P(i): the dealer knows P, one fixed-base exponentiation
+  // gives the same group element as the reference's t-term product (participant.rs:207-215)
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n, dX.as<uint32_t>()));
+  // Y_i = y_i^P(i) (participant.rs:219)
+  MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n,
+                     dY.as<uint32_t>()));
+  // a1 = g^w, a2 = y^w (participant.rs:236-237)
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
+                     dA2.as<uint32_t>()));
+  // G^s (participant.rs:268)
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, ds.as<uint32_t>(), EW, windows_for(s_le, EB, 1), nullptr, 0, nullptr, 0, 0, 1,
+                     dGs.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  std::vector<uint8_t> X(n * EB), A1(n * EB), A2(n * EB);
+  uint8_t gs[EB];
+  MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
+  MPVSS_TRY(d2h(ctx, X.data(), dX, n * EB));
+  MPVSS_TRY(d2h(ctx, shares_out, dY, n * EB));
+  MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
+  MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
+  MPVSS_TRY(d2h(ctx, gs, dGs, EB));
+  MPVSS_TRY(sync(ctx));
+  sha2::Sha256 h;
+  for (size_t i = 0; i < n; ++i) {  // participant.rs:238-245
+    framed_update(h, X.data() + i * EB);
+    framed_update(h, shares_out + i * EB);
+    framed_update(h, A1.data() + i * EB);
+    framed_update(h, A2.data() + i * EB);
+  }
+  uint8_t digest[32];
+  h.finalize(digest);
+  challenge_from_digest(ctx, digest, challenge_out);  // participant.rs:251-252
+  big::Int c = big::from_le(challenge_out, EB);
+  for (size_t i = 0; i < n; ++i) {  // participant.rs:255-264: r = (w - (p*c mod ord)) mod ord
+    big::Int alpha_c = big::mulmod(big::from_le(p.data() + i * EB, EB), c, ctx->qm1);
+    big::Int w = big::from_le(witnesses + i * EB, EB);
+    // scalar_sub (modp.rs:184-192): negative -> add the order once, else reduce
+    big::Int r = big::cmp(w, alpha_c) >= 0 ? big::mod(big::sub(w, alpha_c), ctx->qm1)
+                                           : big::mod(big::sub(big::add(w, ctx->qm1), alpha_c), ctx->qm1);
+    big::to_le(r, responses_out + i * EB, EB);
+  }
+  // U = secret XOR (int(SHA-256(bytes(G^s))) mod q)  (participant.rs:269-272)
+  uint8_t tmp[EB], hs[32];
+  size_t len = min_be(gs, tmp);
+  sha2::sha256(tmp, len, hs);
+  big::Int mask = big::mod(big::from_be(hs, 32), ctx->q);
+  big::Int u = big::bxor(big::from_be(secret, secret_len), mask);
+  big::to_be(u, u_out, EB);
+  if (x_out) memcpy(x_out, X.data(), n * EB);
+  return MPVSS_OK;
+}
+
+// ------------------------------------------------------------------ extract ----
+int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const uint8_t* witnesses,
+                   const uint8_t* enc_shares, uint8_t* publickeys_out, uint8_t* shares_out, uint8_t* challenges_out,
+                   uint8_t* responses_out, int* status_out) {
+  MPVSS_TRY(check_args(ctx, n > 0 && private_keys && witnesses && enc_shares && publickeys_out && shares_out &&
+                                challenges_out && responses_out,
+                       "extract_shares: bad arguments"));
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  const uint32_t* Kg = ctx->consts_g.as<uint32_t>();
+  const uint32_t* G = ctx->gens.as<uint32_t>();
+  // sk^-1 mod (q-1), q-1 = 2g (util.rs:33-41 via participant.rs:314): by CRT it is the odd
+  // representative of sk^(g-2) mod g; it exists iff sk is odd and not a multiple of g.
+  std::vector<uint8_t> skg(n * EB), e(EB);
+  std::vector<int> st(n, MPVSS_OK);
+  for (size_t i = 0; i < n; ++i) {
+    big::Int sk = big::mod(big::from_le(private_keys + i * EB, EB), ctx->qm1);
+    big::Int r = big::mod(sk, ctx->g);
+    if (!big::is_odd(sk) || big::is_zero(r)) st[i] = MPVSS_ERR_NOT_INVERTIBLE;
+    big::to_le(r, skg.data() + i * EB, EB);
+  }
+  big::to_le(big::sub(ctx->g, big::from_u64(2)), e.data(), EB);
+  DevBuf &dsk = ctx->buf(0), &dskg = ctx->buf(1), &de = ctx->buf(2), &dinv = ctx->buf(3), &dw = ctx->buf(4),
+         &dY = ctx->buf(5), &dpk = ctx->buf(6), &dS = ctx->buf(7), &dA1 = ctx->buf(8), &dA2 = ctx->buf(9);
+  MPVSS_TRY(h2d(ctx, dsk, private_keys, n * EB));
+  MPVSS_TRY(h2d(ctx, dskg, skg.data(), n * EB));
+  MPVSS_TRY(h2d(ctx, de, e.data(), EB));
+  MPVSS_TRY(h2d(ctx, dw, witnesses, n * EB));
+  MPVSS_TRY(h2d(ctx, dY, enc_shares, n * EB));
+  for (DevBuf* b : {&dinv, &dpk, &dS, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
+  timing_begin(ctx);
+  MPVSS_TRY(dev_exp2(ctx, Kg, dskg.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(e.data(), EB, 1), nullptr, 0,
+                     nullptr, 0, 0, n, dinv.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  std::vector<uint8_t> inv(n * EB);
+  MPVSS_TRY(d2h(ctx, inv.data(), dinv, n * EB));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < n; ++i) {
+    big::Int x = big::from_le(inv.data() + i * EB, EB);
+    if (!big::is_odd(x)) x = big::add(x, ctx->g);
+    big::to_le(x, inv.data() + i * EB, EB);
+  }
+  MPVSS_TRY(h2d(ctx, dinv, inv.data(), n * EB));
+  uint32_t skw = windows_for(private_keys, EB, n), ww = windows_for(witnesses, EB, n);
+  float ms0 = ctx->last_ms;
+  int l0 = ctx->last_launches;
+  timing_begin(ctx);
+  // pk = G^sk (participant.rs:306), S = Y^(1/sk) (:316), a1 = G^w, a2 = S^w (:331-332)
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dsk.as<uint32_t>(), EW, skw, nullptr, 0, nullptr, 0, 0, n, dpk.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, dY.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 512, nullptr, 0, nullptr, 0, 0, n,
+                     dS.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, dS.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
+                     dA2.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  ctx->last_ms += ms0;
+  ctx->last_launches += l0;
+  std::vector<uint8_t> A1(n * EB), A2(n * EB);
+  MPVSS_TRY(d2h(ctx, publickeys_out, dpk, n * EB));
+  MPVSS_TRY(d2h(ctx, shares_out, dS, n * EB));
+  MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
+  MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < n; ++i) {
+    sha2::Sha256 h;  // participant.rs:330-340: (pk, Y, a1, a2)
+    framed_update(h, publickeys_out + i * EB);
+    framed_update(h, enc_shares + i * EB);
+    framed_update(h, A1.data() + i * EB);
+    framed_update(h, A2.data() + i * EB);
+    uint8_t digest[32];
+    h.finalize(digest);
+    uint8_t* c_le = challenges_out + i * EB;
+    challenge_from_digest(ctx, digest, c_le);
+    // r = w - sk*c (dleq.rs:42-50 with modp.rs:180-192)
+    big::Int c = big::from_le(c_le, EB);
+    big::Int alpha_c = big::mulmod(big::from_le(private_keys + i * EB, EB), c, ctx->qm1);
+    big::Int w = big::from_le(witnesses + i * EB, EB);
+    big::Int r = big::cmp(w, alpha_c) >= 0 ? big::mod(big::sub(w, alpha_c), ctx->qm1)
+                                           : big::sub(big::add(w, ctx->qm1), alpha_c);
+    big::to_le(r, responses_out + i * EB, EB);
+  }
+  if (status_out) memcpy(status_out, st.data(), n * sizeof(int));
+  return MPVSS_OK;
+}
+
+// ------------------------------------------------------------- verify_share ----
+int verify_shares(mpvss_ctx* ctx, size_t n, const uint8_t* publickeys, const uint8_t* shares,
+                  const uint8_t* enc_shares, const uint8_t* challenges, const uint8_t* responses, int* ok_out) {
+  MPVSS_TRY(check_args(ctx, n > 0 && publickeys && shares && enc_shares && challenges && responses && ok_out,
+                       "verify_shares: bad arguments"));
+  std::vector<uint8_t> a1(n * EB), a2(n * EB), gen(EB, 0);
+  gen[0] = 2;  // DLEQ(G, pk, S, Y)  participant.rs:378-385
+  MPVSS_TRY(dleq_verify_commit(ctx, gen.data(), publickeys, shares, enc_shares, responses, challenges, EB, n,
+                               a1.data(), a2.data()));
+  for (size_t i = 0; i < n; ++i) {
+    sha2::Sha256 h;  // dleq.rs:275-302: (h1, h2, a1, a2) = (pk, Y, a1, a2)
+    framed_update(h, publickeys + i * EB);
+    framed_update(h, enc_shares + i * EB);
+    framed_update(h, a1.data() + i * EB);
+    framed_update(h, a2.data() + i * EB);
+    uint8_t digest[32], c[EB];
+    h.finalize(digest);
+    challenge_from_digest(ctx, digest, c);
+    ok_out[i] = memcmp(c, challenges + i * EB, EB) == 0;
+  }
+  return MPVSS_OK;
+}
+
+// -------------------------------------------------------------- reconstruct ----
+int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_t* shares, const uint8_t* u,
+                uint8_t* secret_out, uint8_t* gs_out) {
+  MPVSS_TRY(check_args(ctx, k > 0 && positions && shares && u && secret_out, "reconstruct: bad arguments"));
+  for (size_t i = 0; i < k; ++i)
+    if (positions[i] < 1 || positions[i] > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range");
+  // lambda_i = prod_{j != i} j / (j - i) mod g with the sign folded into the exponent:
+  // S^(-lambda) = S^((q-1) - lambda)  (participant.rs:535-558, element_inverse modp.rs:138-140)
+  const big::Int& g = ctx->g;
+  std::vector<big::Int> num(k), den(k);
+  std::vector<bool> neg(k);
+  for (size_t i = 0; i < k; ++i) {
+    big::Int nu = big::from_u64(1), de = big::from_u64(1);
+    bool sg = false;
+    for (size_t j = 0; j < k; ++j) {
+      if (j == i) continue;
+      if (positions[j] == positions[i]) return mpvss_fail(ctx, MPVSS_ERR_ARG, "duplicate position");
+      int64_t d = positions[j] - positions[i];
+      if (d < 0) { sg = !sg; d = -d; }
+      nu = big::mod(big::mul(nu, big::from_u64((uint64_t)positions[j])), g);
+      de = big::mod(big::mul(de, big::from_u64((uint64_t)d)), g);
+    }
+    num[i] = nu; den[i] = de; neg[i] = sg;
+  }
+  // one inversion for all denominators (Montgomery's trick)
+  std::vector<big::Int> pre(k + 1);
+  pre[0] = big::from_u64(1);
+  for (size_t i = 0; i < k; ++i) pre[i + 1] = big::mulmod(pre[i], den[i], g);
+  big::Int inv_all;
+  if (!big::modinv(pre[k], g, &inv_all)) return mpvss_fail(ctx, MPVSS_ERR_NOT_INVERTIBLE, "Lagrange denominator");
+  std::vector<uint8_t> lam(k * EB);
+  for (size_t i = k; i-- > 0;) {
+    big::Int di = big::mulmod(inv_all, pre[i], g);
+    inv_all = big::mulmod(inv_all, den[i], g);
+    big::Int l = big::mulmod(num[i], di, g);
+    if (neg[i] && !big::is_zero(l)) l = big::sub(ctx->qm1, l);
+    big::to_le(l, lam.data() + i * EB, EB);
+  }
+  uint8_t gs[EB];
+  MPVSS_TRY(multi_exp(ctx, shares, lam.data(), k, gs));
+  uint8_t tmp[EB], hs[32];
+  size_t len = min_be(gs, tmp);
+  sha2::sha256(tmp, len, hs);
+  big::Int mask = big::mod(big::from_be(hs, 32), ctx->q);  // participant.rs:512-518
+  big::to_be(big::bxor(mask, big::from_be(u, EB)), secret_out, EB);
+  if (gs_out) memcpy(gs_out, gs, EB);
+  return MPVSS_OK;
+}
+
+}  // namespace modp_api

@@ -1,0 +1,253 @@
+// Cooperative 2048-bit Montgomery arithmetic for ModpGroup (replaces
+// num-bigint's BigInt::modpow / `*` / `%` behind groups/modp.rs:122-132 of the
+// reference).
+//
+// Layout: one 2048-bit value = 64 little-endian u32 limbs, spread over a *group*
+// of TPI lanes of one warp (TPI in {4, 8, 16}); lane k of the group keeps limbs
+// [k*L, k*L+L), L = 64/TPI, in registers.  A warp holds 32/TPI independent values.
+//
+// mont_mul is a fused operand-scanning Montgomery product, one 32-bit digit of b
+// per iteration (64 iterations):
+//     W <- (W + a_k * b_j + q_k * m_j) / 2^32        (per lane, on its own window)
+// Each lane's window W is kept as two interleaved accumulators (`even`/`odd`
+// 64-bit aligned column pairs) so that every 32x32->64 multiply-accumulate is one
+// IMAD.WIDE.U32 with the carry chained through a predicate (mad.lo.cc/madc.hi.cc).
+// Per iteration the group exchanges exactly two words by warp shuffle: the
+// Montgomery digit m_j (from lane 0 of the group) and the limb each lane shifts
+// out at the bottom of its window (to lane k-1).  b_j is read from shared memory
+// (broadcast LDS.128 every 4 iterations).  Windows carry at most ~2 bits above
+// their L limbs (bounds in DESIGN.md §modp), so no carry crosses lanes until the
+// single carry-resolve at the end (ballot + add trick).
+//
+// Values are kept in [0, 2^2048) ("almost Montgomery"): the final conditional
+// subtraction only fires on overflow of 2^2048; canonical reduction below q
+// happens once, when results leave the kernel.
+#pragma once
+#include "simt.h"
+
+namespace modp {
+
+template <int TPI>
+struct Cfg {
+  static_assert(TPI == 4 || TPI == 8 || TPI == 16, "TPI must be 4, 8 or 16");
+  static constexpr int L = 64 / TPI;
+};
+
+// Per-lane slice of the modulus constants.
+template <int L>
+struct Mod {
+  uint32_t q[L];   // limbs [k*L, k*L+L) of q
+  uint32_t nq[L];  // same slice of 2^2048 - q
+  uint32_t np;     // -q^{-1} mod 2^32
+};
+
+// Identity of a lane inside its group.
+struct Lane {
+  int k;          // lane index inside the group, 0..TPI-1
+  int lane0;      // warp lane of the group's lane 0
+  int shift;      // == lane0 (bit position of the group in a ballot)
+  uint32_t gmask; // (1 << TPI) - 1
+};
+
+template <int TPI>
+MP_DEV Lane make_lane() {
+  Lane ln;
+  int wl = (int)simt::lane_id();
+  ln.k = wl & (TPI - 1);
+  ln.lane0 = wl - ln.k;
+  ln.shift = ln.lane0;
+  ln.gmask = (TPI == 32) ? 0xffffffffu : ((1u << TPI) - 1u);
+  return ln;
+}
+
+// Resolve a carry (or borrow) chain across the lanes of a group.
+//   gen  : this lane produced a carry out of its L limbs
+//   prop : this lane's limbs are all ones (all zeros for borrows)
+// returns carry-in for this lane; *cout = carry out of the whole group.
+template <int TPI>
+MP_DEV uint32_t resolve(const Lane& ln, bool gen, bool prop, uint32_t* cout) {
+  uint32_t G = (simt::ballot(gen) >> ln.shift) & ln.gmask;
+  uint32_t P = (simt::ballot(prop) >> ln.shift) & ln.gmask;
+  uint32_t C = ((G | P) + G) ^ P;  // bit i = carry into lane i, bit TPI = carry out
+  *cout = (C >> TPI) & 1u;
+  return (C >> ln.k) & 1u;
+}
+
+template <int L>
+MP_DEV bool all_ones(const uint32_t (&r)[L]) {
+  uint32_t x = r[0];
+#pragma unroll
+  for (int i = 1; i < L; ++i) x &= r[i];
+  return x == 0xffffffffu;
+}
+
+// r += addend (per-lane slices of a 2048-bit value), carries resolved across the
+// group; returns the carry out of bit 2048.
+template <int TPI>
+MP_DEV uint32_t add_resolve(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&x)[Cfg<TPI>::L], uint32_t mask,
+                            const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  r[0] = simt::add_cc(r[0], x[0] & mask);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], x[i] & mask);
+  uint32_t c = simt::addc(0, 0);
+  uint32_t cout;
+  uint32_t cin = resolve<TPI>(ln, c != 0, all_ones<L>(r), &cout);
+  r[0] = simt::add_cc(r[0], cin);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
+  return cout;
+}
+
+// One digit of the fused Montgomery product.  P is the accumulator whose column
+// pairs are aligned with the current lowest limb ("even" role); S holds the other
+// accumulator ("odd" role; for FIRST == false it arrives as the previous
+// iteration's even accumulator and is shifted down one column pair in place).
+template <int TPI, bool FIRST>
+MP_DEV void mm_digit(uint32_t (&P)[Cfg<TPI>::L + 2], uint32_t (&S)[Cfg<TPI>::L + 2],
+                     const uint32_t (&a)[Cfg<TPI>::L], uint32_t b, const Mod<Cfg<TPI>::L>& M, const Lane& ln,
+                     uint32_t& in) {
+  constexpr int L = Cfg<TPI>::L;
+  if (FIRST) {
+#pragma unroll
+    for (int i = 0; i < L; i += 2) {
+      P[i] = simt::mul_lo(a[i], b);
+      P[i + 1] = simt::mul_hi(a[i], b);
+      S[i] = simt::mul_lo(a[i + 1], b);
+      S[i + 1] = simt::mul_hi(a[i + 1], b);
+    }
+    P[L] = P[L + 1] = 0;
+    S[L] = S[L + 1] = 0;
+  } else {
+    // limb shifted in from lane k+1 lands on (new) column L-1 = S[L] before the shift
+    S[L] = simt::add_cc(S[L], in);
+    S[L + 1] = simt::addc(S[L + 1], 0);
+    // stray high half of the dropped pair -> column 0; its carry feeds the odd chain
+    P[0] = simt::add_cc(P[0], S[1]);
+#pragma unroll
+    for (int x = 0; x < L; x += 2) {
+      S[x] = simt::madc_lo_cc(a[x + 1], b, S[x + 2]);
+      S[x + 1] = simt::madc_hi_cc(a[x + 1], b, S[x + 3]);
+    }
+    S[L] = simt::addc(0, 0);
+    S[L + 1] = 0;
+    P[0] = simt::mad_lo_cc(a[0], b, P[0]);
+    P[1] = simt::madc_hi_cc(a[0], b, P[1]);
+#pragma unroll
+    for (int i = 2; i < L; i += 2) {
+      P[i] = simt::madc_lo_cc(a[i], b, P[i]);
+      P[i + 1] = simt::madc_hi_cc(a[i], b, P[i + 1]);
+    }
+    P[L] = simt::addc(P[L], 0);
+  }
+  // Montgomery digit from the lowest limb of the whole value (group lane 0)
+  uint32_t m = simt::shfl(simt::mul_lo(P[0], M.np), ln.lane0);
+  S[0] = simt::mad_lo_cc(M.q[1], m, S[0]);
+  S[1] = simt::madc_hi_cc(M.q[1], m, S[1]);
+#pragma unroll
+  for (int i = 3; i < L; i += 2) {
+    S[i - 1] = simt::madc_lo_cc(M.q[i], m, S[i - 1]);
+    S[i] = simt::madc_hi_cc(M.q[i], m, S[i]);
+  }
+  S[L] = simt::addc(S[L], 0);
+  P[0] = simt::mad_lo_cc(M.q[0], m, P[0]);
+  P[1] = simt::madc_hi_cc(M.q[0], m, P[1]);
+#pragma unroll
+  for (int i = 2; i < L; i += 2) {
+    P[i] = simt::madc_lo_cc(M.q[i], m, P[i]);
+    P[i + 1] = simt::madc_hi_cc(M.q[i], m, P[i + 1]);
+  }
+  P[L] = simt::addc(P[L], 0);
+  // P[0] is now the limb that leaves this lane's window (zero on group lane 0)
+  uint32_t out = simt::shfl(P[0], (int)simt::lane_id() + 1);
+  in = (ln.k == TPI - 1) ? 0u : out;
+}
+
+// r = a * b * 2^-2048 mod q, result in [0, 2^2048).  `bs` points at the 64 limbs of
+// b (shared memory, visible to the whole group).  r may alias a.
+template <int TPI>
+MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* bs,
+                     const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t A0[L + 2], A1[L + 2];
+  uint32_t in = 0;
+  const uint4* b4 = reinterpret_cast<const uint4*>(bs);
+  {
+    uint4 bw = b4[0];
+    mm_digit<TPI, true>(A0, A1, a, bw.x, M, ln, in);
+    mm_digit<TPI, false>(A1, A0, a, bw.y, M, ln, in);
+    mm_digit<TPI, false>(A0, A1, a, bw.z, M, ln, in);
+    mm_digit<TPI, false>(A1, A0, a, bw.w, M, ln, in);
+  }
+#pragma unroll 1
+  for (int j = 1; j < 16; ++j) {
+    uint4 bw = b4[j];
+    mm_digit<TPI, false>(A0, A1, a, bw.x, M, ln, in);
+    mm_digit<TPI, false>(A1, A0, a, bw.y, M, ln, in);
+    mm_digit<TPI, false>(A0, A1, a, bw.z, M, ln, in);
+    mm_digit<TPI, false>(A1, A0, a, bw.w, M, ln, in);
+  }
+  // last call had P = A1, S = A0:  value = S + (P >> 32) + in * 2^(32(L-1))
+  r[0] = simt::add_cc(A0[0], A1[1]);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(A0[i], A1[i + 1]);
+  uint32_t ov = simt::addc(A0[L], A1[L + 1]);
+  r[L - 1] = simt::add_cc(r[L - 1], in);
+  ov = simt::addc(ov, 0);
+  // hand the (<= 2 bit) overflow of each window to the next lane, resolve carries
+  uint32_t ovin = simt::shfl(ov, (int)simt::lane_id() - 1);
+  uint32_t ovtop = simt::shfl(ov, ln.lane0 + TPI - 1);
+  if (ln.k == 0) ovin = 0;
+  r[0] = simt::add_cc(r[0], ovin);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
+  uint32_t c = simt::addc(0, 0);
+  uint32_t cout;
+  uint32_t cin = resolve<TPI>(ln, c != 0, all_ones<L>(r), &cout);
+  r[0] = simt::add_cc(r[0], cin);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
+  // value >= 2^2048  ->  subtract q once (add 2^2048 - q, drop the carry)
+  uint32_t over = ovtop + cout;
+  (void)add_resolve<TPI>(r, M.nq, 0u - over, ln);
+}
+
+// Bring a value of [0, 2^2048) into [0, q): canonical representative.
+template <int TPI>
+MP_DEV void canonical(uint32_t (&r)[Cfg<TPI>::L], const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  // 2^2048 < 2q for every 2048-bit modulus, so one conditional subtraction suffices.
+  uint32_t t[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) t[i] = r[i];
+  uint32_t ge = add_resolve<TPI>(t, M.nq, 0xffffffffu, ln);  // carry <=> r >= q
+  if (ge) {
+#pragma unroll
+    for (int i = 0; i < L; ++i) r[i] = t[i];
+  }
+}
+
+// Shared-memory staging of a group's value so that every lane can read all 64 limbs.
+template <int TPI>
+MP_DEV void stage(uint32_t* dst64, const uint32_t (&v)[Cfg<TPI>::L], const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint4* d = reinterpret_cast<uint4*>(dst64 + ln.k * L);
+#pragma unroll
+  for (int i = 0; i < L; i += 4) d[i / 4] = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+
+template <int TPI>
+MP_DEV void load_slice(uint32_t (&v)[Cfg<TPI>::L], const uint32_t* src64, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  const uint4* s = reinterpret_cast<const uint4*>(src64 + ln.k * L);
+#pragma unroll
+  for (int i = 0; i < L; i += 4) {
+    uint4 w = s[i / 4];
+    v[i] = w.x;
+    v[i + 1] = w.y;
+    v[i + 2] = w.z;
+    v[i + 3] = w.w;
+  }
+}
+
+}  // namespace modp

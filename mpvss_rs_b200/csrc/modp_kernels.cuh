@@ -1,0 +1,240 @@
+// Kernel bodies for the ModpGroup hot path.  Each body is written against simt.h so
+// that the CUDA build (modp.cu) and the lane-per-thread emulator (tests/emu) run
+// the same source.  A body is executed by whole warps; `wg` is the global warp
+// index and `wsm` the warp's private slice of dynamic shared memory.  No block
+// barrier is used anywhere (warps are independent), only warp shuffles/barriers.
+//
+// Reference call sites replaced (paths under /root/reference/src):
+//   horner_body  : X_i = prod_j C_j^(i^j)  participant.rs:207-215, 423-434; mpvss.rs:114-123
+//   exp2_body    : group.exp / DLEQ commitments  modp.rs:122-128, dleq.rs:37-39, 66-84,
+//                  participant.rs:219, 236-237, 316, 331-332, 553
+//   mul_body     : group.mul  modp.rs:130-132
+#pragma once
+#include "modp_arith.cuh"
+
+namespace modp {
+
+// Layout of the constant block (device global memory, u32 limbs):
+//   [0,64) q   [64,128) 2^2048-q   [128,192) R mod q (Montgomery one)
+//   [192,256) R^2 mod q   [256] -q^-1 mod 2^32
+enum { C_Q = 0, C_NQ = 64, C_ONE = 128, C_R2 = 192, C_NP = 256, C_WORDS = 260 };
+
+template <int TPI>
+MP_DEV void load_mod(Mod<Cfg<TPI>::L>& M, const uint32_t* consts, const Lane& ln) {
+  load_slice<TPI>(M.q, consts + C_Q, ln);
+  load_slice<TPI>(M.nq, consts + C_NQ, ln);
+  M.np = consts[C_NP];
+}
+
+// copy 64 limbs global -> this warp's shared buffer (lane l moves limbs 2l, 2l+1)
+MP_DEV void warp_copy64(uint32_t* dst, const uint32_t* src) {
+  uint32_t l = simt::lane_id();
+  dst[2 * l] = src[2 * l];
+  dst[2 * l + 1] = src[2 * l + 1];
+}
+
+template <int TPI>
+MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  stage<TPI>(sq, acc, ln);
+  simt::syncwarp();
+  mont_mul<TPI>(acc, acc, sq, M, ln);
+}
+
+// Leave Montgomery form (multiply by 1), reduce below q, store 64 limbs.
+template <int TPI>
+MP_DEV void finish_store(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, uint32_t* dst64, bool live,
+                         const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t one[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) one[i] = 0;
+  if (ln.k == 0) one[0] = 1;
+  stage<TPI>(sq, one, ln);
+  simt::syncwarp();
+  mont_mul<TPI>(acc, acc, sq, M, ln);
+  canonical<TPI>(acc, M, ln);
+  if (live) stage<TPI>(dst64, acc, ln);
+}
+
+// ---------------------------------------------------------------- Horner ----
+struct HornerArgs {
+  const uint32_t* consts;  // constant block
+  const uint32_t* cm;      // t commitments, Montgomery form, 64 limbs each
+  const uint32_t* pos;     // n positions (1-based, < 2^(2*ndigits))
+  uint32_t* out;           // n results, canonical, 64 limbs each
+  uint32_t t, n, ndigits;  // ndigits = base-4 digits of the largest position
+};
+
+template <int TPI>
+constexpr int horner_smem_words = 128 + (32 / TPI) * 256;
+
+// X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
+// integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
+template <int TPI>
+MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t inst = wg * GPW + gi;
+  const bool live = inst < A.n;
+  if (!live) inst = A.n - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* cbuf = wsm;
+  uint32_t* one = wsm + 64;
+  uint32_t* tbl = wsm + 128 + gi * 256;  // tbl[0..2] = X, X^2, X^3 ; tbl + 192 = squaring stage
+  uint32_t* sq = tbl + 192;
+  warp_copy64(one, A.consts + C_ONE);
+  const uint32_t pos = A.pos[inst];
+  uint32_t acc[L];
+  load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
+  simt::syncwarp();
+  for (int j = (int)A.t - 2; j >= 0; --j) {
+    warp_copy64(cbuf, A.cm + (size_t)j * 64);
+    // window table X, X^2, X^3
+    stage<TPI>(tbl, acc, ln);
+    simt::syncwarp();
+    uint32_t x[L];
+    mont_mul<TPI>(x, acc, tbl, M, ln);
+    stage<TPI>(tbl + 64, x, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(x, x, tbl, M, ln);
+    stage<TPI>(tbl + 128, x, ln);
+    simt::syncwarp();
+    uint32_t d = (pos >> (2 * (A.ndigits - 1))) & 3u;
+    load_slice<TPI>(acc, d ? tbl + (d - 1) * 64 : one, ln);
+    for (int s = (int)A.ndigits - 2; s >= 0; --s) {
+      sqr_inplace<TPI>(acc, sq, M, ln);
+      sqr_inplace<TPI>(acc, sq, M, ln);
+      d = (pos >> (2 * s)) & 3u;
+      mont_mul<TPI>(acc, acc, d ? tbl + (d - 1) * 64 : one, M, ln);
+    }
+    mont_mul<TPI>(acc, acc, cbuf, M, ln);
+  }
+  finish_store<TPI>(acc, sq, A.out + (size_t)inst * 64, live, M, ln);
+}
+
+// ------------------------------------------------- (double) exponentiation ----
+struct Exp2Args {
+  const uint32_t* consts;
+  const uint32_t* b1;   // bases, normal form; stride b1_stride limbs (0 = one shared base)
+  const uint32_t* e1;   // exponents, little-endian limbs, stride e1_stride
+  const uint32_t* b2;   // optional second base (nullptr: single exponentiation)
+  const uint32_t* e2;
+  uint32_t* out;        // n results, canonical
+  uint32_t n;
+  uint32_t b1_stride, e1_stride, e1_windows;  // windows of 4 bits, counted from bit 0
+  uint32_t b2_stride, e2_stride, e2_windows;
+};
+
+template <int TPI>
+constexpr int exp2_smem_words = 64 + (32 / TPI) * (16 * 64 + 64);
+
+template <int TPI>
+MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, const uint32_t* e, uint32_t windows,
+                        uint32_t* tbl, uint32_t* sq, const uint32_t* r2, const uint32_t* consts,
+                        const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t x[L];
+  // tbl[0] = one, tbl[1] = base in Montgomery form, tbl[i] = tbl[i-1] * base
+  load_slice<TPI>(x, consts + C_ONE, ln);
+  stage<TPI>(tbl, x, ln);
+  load_slice<TPI>(x, base64, ln);
+  mont_mul<TPI>(x, x, r2, M, ln);
+  stage<TPI>(tbl + 64, x, ln);
+  simt::syncwarp();
+  for (int i = 2; i < 16; ++i) {
+    mont_mul<TPI>(x, x, tbl + 64, M, ln);
+    stage<TPI>(tbl + i * 64, x, ln);
+    simt::syncwarp();
+  }
+  uint32_t wi = windows - 1;
+  uint32_t d = (e[wi >> 3] >> ((wi & 7u) * 4)) & 15u;
+  load_slice<TPI>(acc, tbl + d * 64, ln);
+  while (wi-- > 0) {
+    sqr_inplace<TPI>(acc, sq, M, ln);
+    sqr_inplace<TPI>(acc, sq, M, ln);
+    sqr_inplace<TPI>(acc, sq, M, ln);
+    sqr_inplace<TPI>(acc, sq, M, ln);
+    d = (e[wi >> 3] >> ((wi & 7u) * 4)) & 15u;
+    mont_mul<TPI>(acc, acc, tbl + d * 64, M, ln);
+  }
+}
+
+// out_i = b1_i^e1_i [* b2_i^e2_i]  (fixed 4-bit windows; the window count is a launch
+// parameter, so every group of every warp runs the same schedule).
+template <int TPI>
+MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t inst = wg * GPW + gi;
+  const bool live = inst < A.n;
+  if (!live) inst = A.n - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* r2 = wsm;
+  uint32_t* tbl = wsm + 64 + gi * (16 * 64 + 64);
+  uint32_t* sq = tbl + 16 * 64;
+  warp_copy64(r2, A.consts + C_R2);
+  simt::syncwarp();
+  uint32_t acc[L];
+  exp_window4<TPI>(acc, A.b1 + (size_t)inst * A.b1_stride, A.e1 + (size_t)inst * A.e1_stride, A.e1_windows, tbl, sq,
+                   r2, A.consts, M, ln);
+  if (A.b2 != nullptr) {
+    uint32_t acc2[L];
+    exp_window4<TPI>(acc2, A.b2 + (size_t)inst * A.b2_stride, A.e2 + (size_t)inst * A.e2_stride, A.e2_windows, tbl,
+                     sq, r2, A.consts, M, ln);
+    stage<TPI>(sq, acc2, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, sq, M, ln);
+  }
+  finish_store<TPI>(acc, sq, A.out + (size_t)inst * 64, live, M, ln);
+}
+
+// ------------------------------------------------------- element-wise mul ----
+struct MulArgs {
+  const uint32_t* consts;
+  const uint32_t* a;   // n values
+  const uint32_t* b;   // n values, or nullptr
+  uint32_t* out;
+  uint32_t n;
+  uint32_t mode;       // 0: out = a*b mod q (canonical)   1: out = a*R mod q (to Montgomery form)
+  uint32_t a_stride, b_stride;
+};
+
+template <int TPI>
+constexpr int mul_smem_words = 64 + (32 / TPI) * 64;
+
+template <int TPI>
+MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t inst = wg * GPW + gi;
+  const bool live = inst < A.n;
+  if (!live) inst = A.n - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* r2 = wsm;
+  uint32_t* sq = wsm + 64 + gi * 64;
+  warp_copy64(r2, A.consts + C_R2);
+  simt::syncwarp();
+  uint32_t acc[L];
+  load_slice<TPI>(acc, A.a + (size_t)inst * A.a_stride, ln);
+  mont_mul<TPI>(acc, acc, r2, M, ln);  // a*R
+  if (A.mode == 0) {
+    uint32_t y[L];
+    load_slice<TPI>(y, A.b + (size_t)inst * A.b_stride, ln);
+    stage<TPI>(sq, y, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, sq, M, ln);  // a*R*b/R = a*b
+  }
+  canonical<TPI>(acc, M, ln);
+  if (live) stage<TPI>(A.out + (size_t)inst * 64, acc, ln);
+}
+
+}  // namespace modp

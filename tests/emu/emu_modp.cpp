@@ -1,0 +1,62 @@
+// Lane-per-thread emulator harness for the ModpGroup kernel bodies (tests only).
+// Builds mpvss_rs_b200/csrc/modp_kernels.cuh with g++ (-DMPVSS_SIMT_EMU) so the
+// GPU-less container can execute the exact kernel source against the oracle.
+#include <thread>
+#include <vector>
+#include <cstdlib>
+#include "../../mpvss_rs_b200/csrc/modp_kernels.cuh"
+
+namespace {
+template <typename F>
+void run_warps(uint32_t nwarps, size_t smem_words, F body) {
+  for (uint32_t w = 0; w < nwarps; ++w) {
+    simt::EmuWarp warp;
+    std::vector<uint32_t> smem_raw(smem_words + 4, 0);
+    uint32_t* smem = smem_raw.data();
+    while (reinterpret_cast<uintptr_t>(smem) & 15) ++smem;
+    std::vector<std::thread> lanes;
+    for (uint32_t l = 0; l < 32; ++l)
+      lanes.emplace_back([&, l] {
+        simt::g_lane.warp = &warp;
+        simt::g_lane.lane = l;
+        simt::g_cf = 0;
+        body(w, smem);
+      });
+    for (auto& t : lanes) t.join();
+  }
+}
+template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / (32 / TPI); }
+}  // namespace
+
+#define DISPATCH(tpi, CALL)        \
+  switch (tpi) {                   \
+    case 4: { constexpr int T = 4; CALL; break; }   \
+    case 8: { constexpr int T = 8; CALL; break; }   \
+    case 16: { constexpr int T = 16; CALL; break; } \
+    default: return -1;            \
+  }
+
+extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
+                               uint32_t n, uint32_t ndigits, uint32_t* out) {
+  modp::HornerArgs A{consts, cm, pos, out, t, n, ndigits};
+  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
+                          [&](uint32_t w, uint32_t* s) { modp::horner_body<T>(A, w, s); }));
+  return 0;
+}
+
+extern "C" int emu_modp_exp2(int tpi, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
+                             uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2,
+                             uint32_t e2s, uint32_t e2w, uint32_t n, uint32_t* out) {
+  modp::Exp2Args A{consts, b1, e1, b2, e2, out, n, b1s, e1s, e1w, b2s, e2s, e2w};
+  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::exp2_smem_words<T>,
+                          [&](uint32_t w, uint32_t* s) { modp::exp2_body<T>(A, w, s); }));
+  return 0;
+}
+
+extern "C" int emu_modp_mul(int tpi, const uint32_t* consts, const uint32_t* a, uint32_t as, const uint32_t* b,
+                            uint32_t bs, uint32_t n, uint32_t mode, uint32_t* out) {
+  modp::MulArgs A{consts, a, b, out, n, mode, as, bs};
+  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::mul_smem_words<T>,
+                          [&](uint32_t w, uint32_t* s) { modp::mul_body<T>(A, w, s); }));
+  return 0;
+}

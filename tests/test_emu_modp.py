@@ -1,0 +1,92 @@
+"""CPU execution of the *CUDA kernel bodies* for ModpGroup through the lane-per-thread
+emulator (tests/emu): the same modp_arith.cuh / modp_kernels.cuh source that nvcc compiles,
+checked bit-exactly against Python integers / the oracle."""
+import random
+
+import numpy as np
+import pytest
+
+import emu_util as eu
+from oracle import pvss
+from oracle.groups import ModpGroup
+
+G = ModpGroup()
+Q = G.q
+R = 1 << 2048
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return eu.build()
+
+
+def _struct(rng):
+    if rng.random() < 0.3:
+        return rng.randrange(R)
+    limbs = [rng.choice([0, 0xFFFFFFFF, 1, 0xFFFFFFFE, rng.getrandbits(32)]) for _ in range(64)]
+    return sum(l << (32 * i) for i, l in enumerate(limbs))
+
+
+@pytest.mark.parametrize("tpi", [4, 8, 16])
+@pytest.mark.parametrize("modulus", ["q", "g"])
+def test_mont_mul_edge_patterns(lib, tpi, modulus):
+    m = Q if modulus == "q" else G.g
+    C = eu.consts_block(m)
+    rng = random.Random(tpi * 3 + len(modulus))
+    n = 48
+    A = [_struct(rng) for _ in range(n)]
+    B = [_struct(rng) for _ in range(n)]
+    A[:5] = [R - 1, 0, m - 1, m, m + 5]
+    B[:5] = [R - 1, 7, m - 1, m, 1]
+    a = np.concatenate([eu.to_limbs(x) for x in A])
+    b = np.concatenate([eu.to_limbs(x) for x in B])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, eu.P(b), 64, n, 0, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * B[i] % m, (tpi, i)
+    # mode 1: Montgomery form a * 2^2048 mod m, canonical
+    assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, None, 0, n, 1, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * R % m, (tpi, i)
+
+
+@pytest.mark.parametrize("tpi", [4, 8, 16])
+def test_horner_kernel_equals_reference_schedule(lib, tpi):
+    C = eu.consts_block(Q)
+    rng = random.Random(tpi)
+    t = 5
+    comm = [pow(4, rng.randrange(Q - 1), Q) for _ in range(t)]
+    cm = np.concatenate([eu.to_limbs(c * R % Q) for c in comm])
+    positions = [1, 2, 3, 5, 11, 14, 15, 64, 255][: 9 if tpi != 4 else 9]
+    nd = 4
+    pos = np.array(positions, dtype=np.uint32)
+    n = len(positions)
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, nd, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
+
+
+@pytest.mark.parametrize("tpi", [8, 16])
+def test_exp2_kernel(lib, tpi):
+    C = eu.consts_block(Q)
+    rng = random.Random(40 + tpi)
+    n = 6
+    b1 = [rng.randrange(Q) for _ in range(n)]
+    e1 = [rng.getrandbits(96) for _ in range(n)]
+    b2 = [rng.randrange(Q) for _ in range(n)]
+    e2 = [rng.getrandbits(40) for _ in range(n)]
+    e1[0], e2[1], b1[2] = 0, 0, 1
+    B1 = np.concatenate([eu.to_limbs(x) for x in b1])
+    E1 = np.concatenate([eu.to_limbs(x) for x in e1])
+    B2 = np.concatenate([eu.to_limbs(x) for x in b2])
+    E2 = np.concatenate([eu.to_limbs(x, 8) for x in e2])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(B1), 64, eu.P(E1), 64, 24, eu.P(B2), 64, eu.P(E2), 8, 10, n,
+                             eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(b1[i], e1[i], Q) * pow(b2[i], e2[i], Q) % Q
+    # single exponentiation with one shared base (stride 0)
+    assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(B1), 0, eu.P(E1), 64, 24, None, 0, None, 0, 0, n, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(b1[0], e1[i], Q)
