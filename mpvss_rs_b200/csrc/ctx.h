@@ -74,14 +74,10 @@ struct mpvss_ctx {
   std::vector<uint8_t> v_challenge;
   DevBuf v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
 
-  DevBuf& buf(size_t i) {
-    if (scratch.size() <= i) scratch.resize(i + 1);
-    return scratch[i];
-  }
-  PinBuf& pin(size_t i) {
-    if (pinned.size() <= i) pinned.resize(i + 1);
-    return pinned[i];
-  }
+  // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call
+  mpvss_ctx() : scratch(24), pinned(8) {}
+  DevBuf& buf(size_t i) { return scratch.at(i); }
+  PinBuf& pin(size_t i) { return pinned.at(i); }
 };
 
 int mpvss_fail(mpvss_ctx* ctx, int status, const std::string& msg);
