@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- verified DLEQ shares/sec on B200 (BASELINE.json metric).
+
+A "step" is one pass of Participant::verify_distribution_shares (participant.rs:399-455)
+over one synthetic DistributionSharesBox: for every participant recompute
+X_i = prod_j C_j^(i^j) from the t commitments, a1 = g^r X^c, a2 = y^r Y^c, then hash the
+framed transcript on the host and compare the challenge.  Workload at N=1: the headline
+configuration of the metric, ModpGroup n=4096 t=2731.  With N GPUs every rank verifies a
+contiguous slice of n participants of one box of N*n participants (weak scaling, t fixed);
+the X/a1/a2 rows are combined with one NCCL all-gather and rank 0 hashes them.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N] [--t T]
+
+`--impl reference` times the reference's CPU schedule (oracle/cpu_baseline.c, an OpenSSL
+proxy for num-bigint since the Rust reference cannot be built here) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "verified DLEQ shares/sec (MODP n=4096 t=2731, verify_distribution_shares)"
+SQR_MACS, MUL_MACS = 6240, 8256          # 2048-bit Montgomery sqr / mul, 32x32->64 MACs
+Q = None
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def le256(x):
+    return int(x).to_bytes(256, "little")
+
+
+# ------------------------------------------------------------------ clocks ----
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        load = [x for x in sm if x > 200]
+        return {"sm_mhz": statistics.median(load) if load else (statistics.median(sm) if sm else None),
+                "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------- workload ----
+def build_box(group, n_total, t, seed):
+    """Synthetic DistributionSharesBox made with the library's own dealer path.
+    Returns flat little-endian arrays in publickeys order."""
+    from mpvss_rs_b200 import synth
+    from mpvss_rs_b200.lib import buf, ptr
+    from mpvss_rs_b200.participant import RFC3526_2048 as q
+    c = group.codec
+    sks = synth.private_keys(seed, n_total, "modp", q - 1, q)
+    coeffs = synth.coefficients(seed, t, q - 1)
+    ws = synth.witnesses(seed, n_total, q)
+    pks = group.fixed_base_exp(sks)
+    pk_b = c.enc_elems(pks)
+    comm, shares = buf(size=t * 256), buf(size=n_total * 256)
+    chal, resp, u, x = buf(size=256), buf(size=n_total * 256), buf(size=256), buf(size=n_total * 256)
+    secret = b"Hello MPVSS Example."
+    group.ctx.check(group.ctx.lib.mpvss_distribute(
+        group.ctx.h, n_total, t, ptr(buf(secret)), len(secret), ptr(buf(c.enc_scalars(coeffs))),
+        ptr(buf(c.enc_scalars(ws))), ptr(buf(pk_b)), ptr(comm), ptr(shares), ptr(chal), ptr(resp), ptr(u), ptr(x)))
+    return {"commitments": bytes(comm), "publickeys": pk_b, "shares": bytes(shares), "responses": bytes(resp),
+            "challenge": bytes(chal), "x_dealer": bytes(x), "n": n_total, "t": t}
+
+
+def horner_macs(n0, n, t):
+    """Algorithmic MACs of the X_i kernel for positions n0+1..n0+n: per Horner step the executed
+    fixed 2-bit-window schedule is (2(d-1)+1) squarings and (d-1)+2 multiplications, d = base-4
+    digits of the position."""
+    total = 0
+    for p in range(n0 + 1, n0 + n + 1):
+        d = 1
+        while p >> (2 * d):
+            d += 1
+        total += (t - 1) * ((2 * (d - 1) + 1) * SQR_MACS + ((d - 1) + 2) * MUL_MACS)
+    return total
+
+
+def dleq_macs(n, rwin=512, cwin=64):
+    """Algorithmic MACs of the two DLEQ commitment launches (4-bit fixed windows)."""
+    def exp(w):
+        return 4 * (w - 1) * SQR_MACS + (15 + (w - 1)) * MUL_MACS  # 14 table mults + to-Montgomery
+    return 2 * n * (exp(rwin) + exp(cwin) + 2 * MUL_MACS)
+
+
+def measure_imad_peak():
+    """Measured 32-bit integer multiply-add issue peak of this GPU (tools/imad_peak.cu)."""
+    exe = os.path.join(ROOT, "tools", "imad_peak")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        j = json.loads(out)
+        lo = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_lo_"))
+        wide = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_wide"))
+        return lo, wide, "measured live (tools/imad_peak)"
+    except Exception:
+        try:
+            j = json.load(open(os.path.join(ROOT, "profiles", "imad_peak_r01.json")))
+            lo = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_lo_"))
+            wide = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_wide"))
+            return lo, wide, "profiles/imad_peak_r01.json (measured on this pool)"
+        except Exception:
+            return 18.4, 7.7, "fallback constant (round-1 measurement)"
+
+
+# ------------------------------------------------------------ CPU baseline ----
+def cpu_reference_step(box, sample_idx, threads, schedule=0):
+    """One bounded sample of the workload on the host cores; returns seconds."""
+    from oracle import cpu_baseline
+    from mpvss_rs_b200.participant import RFC3526_2048 as q
+    lib = cpu_baseline.load()
+    be = lambda b: bytes(reversed(b))
+    s = len(sample_idx)
+    t = box["t"]
+    comm = b"".join(be(box["commitments"][j * 256:(j + 1) * 256]) for j in range(t))
+    sel = lambda key: b"".join(be(box[key][i * 256:(i + 1) * 256]) for i in sample_idx)
+    xo, a1o, a2o = (ctypes.create_string_buffer(256 * s) for _ in range(3))
+    pos = (ctypes.c_int64 * s)(*[i + 1 for i in sample_idx])
+    t0 = time.perf_counter()
+    lib.cpu_modp_verify(q.to_bytes(256, "big"), comm, t, pos, sel("publickeys"), sel("shares"), sel("responses"),
+                        be(box["challenge"]), s, threads, schedule, xo, a1o, a2o)
+    dt = time.perf_counter() - t0
+    xs = [xo.raw[i * 256:(i + 1) * 256] for i in range(s)]
+    return dt, xs
+
+
+def spread_sample(n, s):
+    return sorted({min(n - 1, (k * n) // s + (n // (2 * s))) for k in range(s)})
+
+
+# ------------------------------------------------------------------- main ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096, help="participants per GPU")
+    ap.add_argument("--t", type=int, default=0, help="threshold (default ceil(2n/3))")
+    ap.add_argument("--tpi", type=int, default=0, help="override lanes per 2048-bit value")
+    ap.add_argument("--seed", type=int, default=0x6D70767373)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    n = args.n
+    t = args.t or -(-2 * n // 3)
+    n_total = n * world
+    cores = os.cpu_count() or 1
+
+    import torch
+    if args.impl == "reference" and rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mpvss_rs_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1 and args.impl == "ours":
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import mpvss_rs_b200 as m
+    from mpvss_rs_b200.lib import buf, ptr
+    group = m.Group("modp", device=local)
+    if args.tpi:
+        group.ctx.set_int("modp_tpi", args.tpi)
+    lib, h = group.ctx.lib, group.ctx.h
+    box = build_box(group, n_total, t, args.seed)
+    config = {"workload": f"ModpGroup verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
+              "group": "modp-rfc3526-2048", "n_per_gpu": n, "n_total": n_total, "t": t,
+              "x_schedule": "Horner in the exponent, fixed 2-bit windows (DESIGN.md)",
+              "l2": "flushed between timed steps (256 MiB write)", "sharding": f"participants/{world}"}
+
+    # ---------------------------------------------------------- reference arm ----
+    if args.impl == "reference":
+        sample = spread_sample(n_total, min(cores, n_total))
+        for _ in range(args.warmup):
+            cpu_reference_step(box, sample[: max(1, len(sample) // 4)], cores)
+        times = [cpu_reference_step(box, sample, cores)[0] for _ in range(args.steps)]
+        per = statistics.mean(times)
+        val = len(sample) / per
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "shares/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (2048-bit integers)",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "shares/s", "cores": cores, "kind": "port",
+                                 "sample": f"{len(sample)} participants per step at positions spread over "
+                                           f"1..{n_total}, full t={t}, reference schedule (t+4 exponentiations per "
+                                           "share, participant.rs:423-447) on OpenSSL BN_mod_exp_mont"},
+                "e2e": {"value": val, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # --------------------------------------------------------------- our arm ----
+    lo, hi = rank * n, (rank + 1) * n
+    sl = lambda key: box[key][lo * 256:hi * 256]
+    positions = (ctypes.c_int64 * n)(*range(lo + 1, hi + 1))
+    pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
+    host = {k: pin(v) for k, v in (("commitments", box["commitments"]), ("publickeys", sl("publickeys")),
+                                   ("shares", sl("shares")), ("responses", sl("responses")),
+                                   ("challenge", box["challenge"]))}
+    P = lambda tns: ctypes.cast(tns.data_ptr(), ctypes.POINTER(ctypes.c_uint8))
+    ok = ctypes.c_int(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out_local = torch.empty((3, n, 256), dtype=torch.uint8, device="cuda")
+    out_all = torch.empty((world, 3, n, 256), dtype=torch.uint8, device="cuda") if world > 1 else None
+    out_host = torch.empty((world, 3, n, 256), dtype=torch.uint8).pin_memory() if world > 1 else None
+    x_chk = buf(size=n * 256)
+
+    def stage():
+        group.ctx.check(lib.mpvss_verify_distribution_stage(
+            h, n, t, P(host["commitments"]), positions, P(host["publickeys"]), P(host["shares"]),
+            P(host["responses"]), P(host["challenge"])))
+
+    def run_resident(want_x=False):
+        """one step with the box resident in HBM; returns (ok, kernel_ms, phase0_ms)"""
+        if world == 1:
+            group.ctx.check(lib.mpvss_verify_distribution_run(h, ctypes.byref(ok), ptr(x_chk) if want_x else None,
+                                                              None, None, None))
+            return ok.value, group.ctx.last_kernel_ms, group.ctx.last_phase_ms(0)
+        group.ctx.check(lib.mpvss_verify_distribution_compute(
+            h, out_local[0].data_ptr(), out_local[1].data_ptr(), out_local[2].data_ptr()))
+        kms, p0 = group.ctx.last_kernel_ms, group.ctx.last_phase_ms(0)
+        dist.all_gather_into_tensor(out_all, out_local)          # one NCCL all-gather per phase
+        res = 1
+        if rank == 0:
+            out_host.copy_(out_all, non_blocking=False)
+            g = out_host.numpy()
+            cat = lambda k: g[:, k].reshape(-1).tobytes()
+            group.ctx.check(lib.mpvss_transcript_check(h, n_total, ptr(buf(cat(0))), ptr(buf(box["shares"])),
+                                                       ptr(buf(cat(1))), ptr(buf(cat(2))), ptr(buf(box["challenge"])),
+                                                       ctypes.byref(ok), None))
+            res = ok.value
+        return res, kms, p0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    stage()
+    # correctness gate before timing: the box verifies and the verifier's X equals the dealer's g^P(i)
+    okv, _, _ = run_resident(want_x=(world == 1))
+    if rank == 0 and okv != 1:
+        raise SystemExit("verification of the synthetic box failed -- refusing to report a number")
+    if world == 1 and bytes(x_chk) != sl("x_dealer"):
+        raise SystemExit("verifier X_i differs from dealer X_i -- refusing to report a number")
+
+    imad_lo, imad_wide, peak_src = (measure_imad_peak() if rank == 0 else (0, 0, ""))
+    for _ in range(args.warmup):
+        run_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_s, kern_ms, p0_ms, launches = [], [], [], 0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        okv, kms, p0 = run_resident()
+        barrier()
+        step_s.append(maxr(time.perf_counter() - t0))
+        kern_ms.append(maxr(kms))
+        p0_ms.append(maxr(p0))
+        launches += group.ctx.last_kernel_launches
+        assert rank != 0 or okv == 1
+    # end to end through the reference-facing call, host buffers, copies inside the timed region
+    e2e_s = []
+    if world == 1:
+        for i in range(args.warmup + args.steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            group.ctx.check(lib.mpvss_verify_distribution(
+                h, n, t, P(host["commitments"]), positions, P(host["publickeys"]), P(host["shares"]),
+                P(host["responses"]), P(host["challenge"]), ctypes.byref(ok), None, None, None, None))
+            barrier()
+            if i >= args.warmup:
+                e2e_s.append(time.perf_counter() - t0)
+            assert ok.value == 1
+    else:
+        for i in range(args.warmup + args.steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            stage()
+            okv, _, _ = run_resident()
+            barrier()
+            if i >= args.warmup:
+                e2e_s.append(maxr(time.perf_counter() - t0))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        dist.destroy_process_group()
+        return 0
+
+    ms = statistics.mean(step_s) * 1e3
+    value = n_total / (ms * 1e-3)
+    e2e_ms = statistics.mean(e2e_s) * 1e3
+    h2d = t * 256 + 3 * n * 256 + 256 + 8 * n
+    d2h = 3 * n * 256
+    hm = horner_macs(lo, n, t)
+    p0 = statistics.mean(p0_ms)
+    achieved = 2.0 * hm / (p0 * 1e-3) / 1e12            # TIMAD/s, 1 MAC = 2 IMAD issues
+    total_macs = hm + dleq_macs(n)
+    line = {
+        "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (2048-bit integers)", "data": "synthetic", "config": config,
+        "timing": "per step: cuda-synchronize + barrier bracketed wall clock (kernels + D2H + host SHA-256), "
+                  "max over ranks; kernel_ms / roofline from CUDA events on the library's stream",
+        "kernel_ms_per_step": statistics.mean(kern_ms),
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "shares/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
+        "roofline": {"bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation)",
+                     "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
+                     "peak_source": peak_src + "; 32-bit IMAD issue rate, 1 MAC (32x32->64) = 2 IMAD",
+                     "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
+                     "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
+                     "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
+                     "share_of_step_macs": hm / total_macs, "traffic": None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        sample = spread_sample(n_total, min(cores, n_total))
+        dt, xs = cpu_reference_step(box, sample, cores)
+        for i, x in zip(sample, xs):       # the CPU restatement and the GPU agree on X_i
+            assert bytes(reversed(x)) == bytes(x_chk)[i * 256:(i + 1) * 256], "CPU baseline X_i != GPU X_i"
+        dt_h, _ = cpu_reference_step(box, sample, cores, schedule=1)
+        line["cpu_baseline"] = {
+            "value": len(sample) / dt, "unit": "shares/s", "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} participants (positions spread over 1..{n_total}), full t={t}, reference "
+                      "schedule (t+4 full exponentiations per share) on OpenSSL BN_mod_exp_mont, one participant "
+                      "per thread",
+            "same_algorithm_value": len(sample) / dt_h,
+            "same_algorithm_note": "CPU running the GPU's Horner schedule (baseline B, BASELINE.md section 3)"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

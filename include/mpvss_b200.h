@@ -65,6 +65,9 @@ size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);
  * and the number of kernel launches it made */
 float mpvss_last_kernel_ms(const mpvss_ctx* ctx);
 int mpvss_last_kernel_launches(const mpvss_ctx* ctx);
+/* kernel time (ms) of one phase of the last fused call.  verify_distribution: phase 0 = X_i
+ * (Montgomery conversion + Horner multi-exponentiation), phase 1 = DLEQ commitments. */
+float mpvss_last_phase_ms(const mpvss_ctx* ctx, int phase);
 
 /* ---- batch forms of `trait Group` methods ------------------------------------ */
 /* Group::exp (src/group.rs:58): out[i] = bases[i] ^ scalars[i].  base_stride = 0 means one
@@ -107,6 +110,15 @@ int mpvss_verify_distribution_stage(mpvss_ctx* ctx, size_t n, size_t t, const ui
                                     const uint8_t* responses, const uint8_t* challenge);
 int mpvss_verify_distribution_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out,
                                   uint8_t* digest_out);
+
+/* Sharded form (one process per GPU, each holding a contiguous slice of the participants):
+ * compute runs the kernels for the staged slice and copies X, a1, a2 (n elements each) to the
+ * caller's DEVICE buffers (e.g. torch tensors that are then all-gathered with NCCL);
+ * transcript_check hashes the gathered HOST rows in index order and compares the challenge
+ * (participant.rs:438-454).  Together they equal mpvss_verify_distribution_run. */
+int mpvss_verify_distribution_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev);
+int mpvss_transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
+                           const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out);
 
 /* Participant::distribute_secret (participant.rs:160-286 / 1094-1274 / 1573-1717) with the
  * randomness injected: `coeffs` (t scalars) replaces Polynomial::init (polynomial.rs:34-47),

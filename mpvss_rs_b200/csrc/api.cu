@@ -71,8 +71,14 @@ int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
   };
   if (cudaSetDevice(device) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
-  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess)
+  if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_mid) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess)
     return bail(MPVSS_ERR_CUDA);
+  for (int a = 0; a < 2; ++a)
+    if (cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming) != cudaSuccess)
+      return bail(MPVSS_ERR_CUDA);
   int s = MPVSS_OK;
   if (group == MPVSS_GROUP_MODP) s = modp_api::init(ctx);
   if (s != MPVSS_OK) return bail(s);
@@ -87,8 +93,10 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx) {
   modp_api::destroy(ctx);
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_mid, ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1]})
+    if (e) cudaEventDestroy(e);
+  for (int a = 0; a < 2; ++a)
+    if (ctx->aux[a]) cudaStreamDestroy(ctx->aux[a]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -116,6 +124,9 @@ size_t mpvss_scalar_bytes(const mpvss_ctx* ctx) {
 }
 float mpvss_last_kernel_ms(const mpvss_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
 int mpvss_last_kernel_launches(const mpvss_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+float mpvss_last_phase_ms(const mpvss_ctx* ctx, int phase) {
+  return (ctx && phase >= 0 && phase < 4) ? ctx->phase_ms[phase] : 0.f;
+}
 
 int mpvss_batch_exp(mpvss_ctx* ctx, const uint8_t* bases, size_t base_stride, const uint8_t* scalars, size_t n,
                     uint8_t* out) {
@@ -151,6 +162,13 @@ int mpvss_verify_distribution_stage(mpvss_ctx* ctx, size_t n, size_t t, const ui
 int mpvss_verify_distribution_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out,
                                   uint8_t* digest_out) {
   DISPATCH(ctx, verify_run, ok, x_out, a1_out, a2_out, digest_out);
+}
+int mpvss_verify_distribution_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev) {
+  DISPATCH(ctx, verify_compute, x_dev, a1_dev, a2_dev);
+}
+int mpvss_transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
+                           const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out) {
+  DISPATCH(ctx, transcript_check, n, x, y, a1, a2, challenge, ok, digest_out);
 }
 int mpvss_verify_distribution(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
                               const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,

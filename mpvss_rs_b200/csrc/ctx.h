@@ -54,7 +54,9 @@ struct mpvss_ctx {
   int group = 0;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t aux[2] = {nullptr, nullptr};  // side streams for concurrent launches
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  float phase_ms[4] = {0, 0, 0, 0};  // per-phase kernel time of the last fused call
   std::mutex mu;
   std::string err;
   float last_ms = 0.f;
@@ -70,9 +72,10 @@ struct mpvss_ctx {
   std::vector<PinBuf> pinned;   // call-local pinned host buffers
   // staged verify_distribution state
   size_t v_n = 0, v_t = 0;
-  uint32_t v_ndigits = 0, v_rwin = 0, v_cwin = 0;
-  std::vector<uint8_t> v_challenge;
-  DevBuf v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+  uint32_t v_rwin = 0, v_cwin = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> v_classes;  // (base-4 digits, count) launch classes
+  std::vector<uint8_t> v_challenge, v_y_host;
+  DevBuf v_slot, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
 
   // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call
   mpvss_ctx() : scratch(24), pinned(8) {}
@@ -114,6 +117,9 @@ int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
 int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
                  const uint8_t*, const uint8_t*);
 int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int verify_compute(mpvss_ctx*, void*, void*, void*);
+int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                     int*, uint8_t*);
 int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
                uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
 int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,

@@ -207,7 +207,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot})
     b->release();
 }
 
@@ -256,44 +256,71 @@ int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint
   return sync(ctx);
 }
 
-// positions -> u32 array + digit count
-static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, std::vector<uint32_t>& pos,
-                          uint32_t* ndigits) {
-  pos.resize(n);
-  uint64_t mx = 1;
+// Positions are grouped by their number of base-4 digits: every group of a launch runs the
+// same fixed-window schedule, so one launch per digit class (concurrently, on the auxiliary
+// streams) keeps a single large position from lengthening everybody's schedule.
+struct PosPlan {
+  std::vector<uint32_t> pos, slot;           // instances sorted by digit class
+  std::vector<std::pair<uint32_t, uint32_t>> classes;  // (ndigits, count), in `pos` order
+};
+static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
+  std::vector<std::vector<uint32_t>> by(17);
   for (size_t i = 0; i < n; ++i) {
     int64_t p = positions ? positions[i] : (int64_t)i + 1;
     if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
-    pos[i] = (uint32_t)p;
-    if ((uint64_t)p > mx) mx = (uint64_t)p;
+    by[ndigits_for((uint64_t)p)].push_back((uint32_t)i);
   }
-  *ndigits = ndigits_for(mx);
+  plan.pos.clear(); plan.slot.clear(); plan.classes.clear();
+  for (uint32_t d = 1; d <= 16; ++d) {
+    if (by[d].empty()) continue;
+    plan.classes.push_back({d, (uint32_t)by[d].size()});
+    for (uint32_t i : by[d]) {
+      plan.slot.push_back(i);
+      plan.pos.push_back((uint32_t)(positions ? positions[i] : (int64_t)i + 1));
+    }
+  }
   return MPVSS_OK;
 }
 
 // commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
-static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos, size_t n,
-                      uint32_t ndigits, uint32_t* x) {
+static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
+                      const uint32_t* slot, const std::vector<std::pair<uint32_t, uint32_t>>& classes, uint32_t* x) {
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, x, (uint32_t)t, (uint32_t)n, ndigits};
-  MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
-  timing_launch(ctx);
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  size_t off = 0, k = 0;
+  for (auto& cl : classes) {
+    cudaStream_t s = (classes.size() == 1) ? ctx->stream : ctx->aux[k % 2];
+    if (s != ctx->stream) MPVSS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+    modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos + off, slot + off, x,
+                       (uint32_t)t,                  cl.second,          cl.first};
+    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, s));
+    timing_launch(ctx);
+    off += cl.second;
+    ++k;
+  }
+  if (classes.size() > 1) {
+    for (int a = 0; a < 2; ++a) {
+      MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
+      MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
+    }
+  }
   return MPVSS_OK;
 }
 
 int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
                   uint8_t* out) {
   MPVSS_TRY(check_args(ctx, commitments && out && n > 0 && t > 0, "poly_eval_exp: bad arguments"));
-  std::vector<uint32_t> pos;
-  uint32_t nd;
-  MPVSS_TRY(prep_positions(ctx, positions, n, pos, &nd));
-  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3);
+  PosPlan plan;
+  MPVSS_TRY(prep_positions(ctx, positions, n, plan));
+  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4);
   MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, dp, pos.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), n * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
   timing_begin(ctx);
-  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), n, nd, dout.as<uint32_t>()));
+  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), plan.classes,
+                       dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
@@ -385,10 +412,12 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
                  const uint8_t* publickeys, const uint8_t* shares, const uint8_t* responses, const uint8_t* challenge) {
   MPVSS_TRY(check_args(ctx, n > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
                        "verify_distribution: bad arguments"));
-  std::vector<uint32_t> pos;
-  MPVSS_TRY(prep_positions(ctx, positions, n, pos, &ctx->v_ndigits));
+  PosPlan plan;
+  MPVSS_TRY(prep_positions(ctx, positions, n, plan));
+  ctx->v_classes = plan.classes;
   MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_pos, pos.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), n * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
@@ -399,52 +428,80 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   ctx->v_rwin = windows_for(responses, EB, n);
   ctx->v_cwin = windows_for(challenge, EB, 1);
   ctx->v_challenge.assign(challenge, challenge + EB);
+  ctx->v_y_host.assign(shares, shares + n * EB);
   ctx->v_n = n;
   ctx->v_t = t;
   return sync(ctx);  // the host buffers may be released by the caller after return
 }
 
-int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
-  MPVSS_TRY(check_args(ctx, ok && ctx->v_n > 0, "verify_distribution_run: nothing staged"));
+// kernels of the staged verification: X (Horner), then a1 = g^r * X^c, a2 = y^r * Y^c
+static int verify_kernels(mpvss_ctx* ctx) {
   const size_t n = ctx->v_n, t = ctx->v_t;
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   uint32_t* X = ctx->v_x.as<uint32_t>();
   timing_begin(ctx);
   // X_i from the commitments (participant.rs:423-434)
-  MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(), n, ctx->v_ndigits, X));
-  // a1 = g^r * X^c ; a2 = y^r * Y^c  (dleq.rs:66-84)
+  MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
+                       ctx->v_slot.as<uint32_t>(), ctx->v_classes, X));
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
+  // dleq.rs:66-84
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
                      ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>()));
   MPVSS_TRY(dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
                      ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
                      ctx->v_a2.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
-  // results back in index order; Y comes from the staged copy so the hash sees what was verified
-  PinBuf &hx = ctx->pin(0), &ha1 = ctx->pin(1), &ha2 = ctx->pin(2), &hy = ctx->pin(3);
-  MPVSS_CUDA(ctx, hx.ensure(n * EB));
-  MPVSS_CUDA(ctx, ha1.ensure(n * EB));
-  MPVSS_CUDA(ctx, ha2.ensure(n * EB));
-  MPVSS_CUDA(ctx, hy.ensure(n * EB));
-  MPVSS_TRY(d2h(ctx, hx.p, ctx->v_x, n * EB));
-  MPVSS_TRY(d2h(ctx, hy.p, ctx->v_y, n * EB));
-  MPVSS_TRY(d2h(ctx, ha1.p, ctx->v_a1, n * EB));
-  MPVSS_TRY(d2h(ctx, ha2.p, ctx->v_a2, n * EB));
-  MPVSS_TRY(sync(ctx));
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // to-Montgomery + Horner
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));  // DLEQ commitments
+  return MPVSS_OK;
+}
+
+int transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
+                     const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out) {
+  MPVSS_TRY(check_args(ctx, n > 0 && x && y && a1 && a2 && challenge && ok, "transcript_check: bad arguments"));
   sha2::Sha256 h;
   for (size_t i = 0; i < n; ++i) {  // participant.rs:438-447 -> dleq.rs:87-99, order (X, Y, a1, a2)
-    framed_update(h, hx.as<uint8_t>() + i * EB);
-    framed_update(h, hy.as<uint8_t>() + i * EB);
-    framed_update(h, ha1.as<uint8_t>() + i * EB);
-    framed_update(h, ha2.as<uint8_t>() + i * EB);
+    framed_update(h, x + i * EB);
+    framed_update(h, y + i * EB);
+    framed_update(h, a1 + i * EB);
+    framed_update(h, a2 + i * EB);
   }
   uint8_t digest[32], c[EB];
   h.finalize(digest);
   challenge_from_digest(ctx, digest, c);
-  *ok = memcmp(c, ctx->v_challenge.data(), EB) == 0;  // participant.rs:451-454
+  *ok = memcmp(c, challenge, EB) == 0;  // participant.rs:451-454
+  if (digest_out) memcpy(digest_out, digest, 32);
+  return MPVSS_OK;
+}
+
+int verify_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev) {
+  MPVSS_TRY(check_args(ctx, x_dev && a1_dev && a2_dev && ctx->v_n > 0, "verify_distribution_compute: nothing staged"));
+  MPVSS_TRY(verify_kernels(ctx));
+  const size_t bytes = ctx->v_n * EB;
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(x_dev, ctx->v_x.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(a1_dev, ctx->v_a1.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(a2_dev, ctx->v_a2.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return sync(ctx);
+}
+
+int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
+  MPVSS_TRY(check_args(ctx, ok && ctx->v_n > 0, "verify_distribution_run: nothing staged"));
+  const size_t n = ctx->v_n;
+  MPVSS_TRY(verify_kernels(ctx));
+  // results back in index order
+  PinBuf &hx = ctx->pin(0), &ha1 = ctx->pin(1), &ha2 = ctx->pin(2);
+  MPVSS_CUDA(ctx, hx.ensure(n * EB));
+  MPVSS_CUDA(ctx, ha1.ensure(n * EB));
+  MPVSS_CUDA(ctx, ha2.ensure(n * EB));
+  MPVSS_TRY(d2h(ctx, hx.p, ctx->v_x, n * EB));
+  MPVSS_TRY(d2h(ctx, ha1.p, ctx->v_a1, n * EB));
+  MPVSS_TRY(d2h(ctx, ha2.p, ctx->v_a2, n * EB));
+  MPVSS_TRY(sync(ctx));
+  MPVSS_TRY(transcript_check(ctx, n, hx.as<uint8_t>(), ctx->v_y_host.data(), ha1.as<uint8_t>(), ha2.as<uint8_t>(),
+                             ctx->v_challenge.data(), ok, digest_out));
   if (x_out) memcpy(x_out, hx.p, n * EB);
   if (a1_out) memcpy(a1_out, ha1.p, n * EB);
   if (a2_out) memcpy(a2_out, ha2.p, n * EB);
-  if (digest_out) memcpy(digest_out, digest, 32);
   return MPVSS_OK;
 }
 

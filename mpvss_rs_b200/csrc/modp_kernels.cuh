@@ -61,7 +61,8 @@ struct HornerArgs {
   const uint32_t* consts;  // constant block
   const uint32_t* cm;      // t commitments, Montgomery form, 64 limbs each
   const uint32_t* pos;     // n positions (1-based, < 2^(2*ndigits))
-  uint32_t* out;           // n results, canonical, 64 limbs each
+  const uint32_t* slot;    // n output slots (nullptr: instance i writes slot i)
+  uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
   uint32_t t, n, ndigits;  // ndigits = base-4 digits of the largest position
 };
 
@@ -112,7 +113,8 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
     }
     mont_mul<TPI>(acc, acc, cbuf, M, ln);
   }
-  finish_store<TPI>(acc, sq, A.out + (size_t)inst * 64, live, M, ln);
+  const uint32_t slot = A.slot ? A.slot[inst] : inst;
+  finish_store<TPI>(acc, sq, A.out + (size_t)slot * 64, live, M, ln);
 }
 
 // ------------------------------------------------- (double) exponentiation ----

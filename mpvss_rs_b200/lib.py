@@ -33,6 +33,7 @@ SIGNATURES = {
     "mpvss_scalar_bytes": (_sz, [_ctxp]),
     "mpvss_last_kernel_ms": (ctypes.c_float, [_ctxp]),
     "mpvss_last_kernel_launches": (ctypes.c_int, [_ctxp]),
+    "mpvss_last_phase_ms": (ctypes.c_float, [_ctxp, ctypes.c_int]),
     "mpvss_batch_exp": (ctypes.c_int, [_ctxp, _u8p, _sz, _u8p, _sz, _u8p]),
     "mpvss_fixed_base_exp": (ctypes.c_int, [_ctxp, ctypes.c_int, _u8p, _sz, _u8p]),
     "mpvss_batch_mul": (ctypes.c_int, [_ctxp, _u8p, _u8p, _sz, _u8p]),
@@ -44,6 +45,8 @@ SIGNATURES = {
                                                  _u8p, _u8p, _u8p, _u8p]),
     "mpvss_verify_distribution_stage": (ctypes.c_int, [_ctxp, _sz, _sz, _u8p, _i64p, _u8p, _u8p, _u8p, _u8p]),
     "mpvss_verify_distribution_run": (ctypes.c_int, [_ctxp, _intp, _u8p, _u8p, _u8p, _u8p]),
+    "mpvss_verify_distribution_compute": (ctypes.c_int, [_ctxp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mpvss_transcript_check": (ctypes.c_int, [_ctxp, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _intp, _u8p]),
     "mpvss_distribute": (ctypes.c_int, [_ctxp, _sz, _sz, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p,
                                         _u8p, _u8p]),
     "mpvss_extract_shares": (ctypes.c_int, [_ctxp, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _intp]),
@@ -122,6 +125,9 @@ class Context:
     @property
     def last_kernel_ms(self):
         return float(self.lib.mpvss_last_kernel_ms(self.h))
+
+    def last_phase_ms(self, phase):
+        return float(self.lib.mpvss_last_phase_ms(self.h, phase))
 
     @property
     def last_kernel_launches(self):

@@ -1,0 +1,103 @@
+/* CPU baseline / C oracle for the ModpGroup hot path.  TEST + BENCH INFRASTRUCTURE ONLY
+ * (see oracle/groups.py header): never linked into libmpvss_b200.so.
+ *
+ * The reference's arithmetic lives in num-bigint 0.2 (Cargo.toml:15), which is not
+ * vendored under /root/reference and cannot be built here (no Rust).  This file restates the
+ * reference's *loop structure* for verify_distribution_shares on OpenSSL libcrypto big
+ * numbers ("OpenSSL proxy for num-bigint"):
+ *   schedule 0 (reference): X_i = prod_j C_j^(i^j mod (q-1)), t full-width exponentiations and
+ *       t multiplications per participant (src/participant.rs:423-434, mpvss.rs:114-123), then
+ *       a1 = g^r * X^c, a2 = y^r * Y^c as four separate exponentiations (src/dleq.rs:66-84).
+ *   schedule 1 (same algorithm as the GPU): Horner in the exponent.
+ * One participant per thread.  All values are 256-byte big-endian.
+ *
+ * build:  gcc -O2 -shared -fPIC -pthread -o oracle/_build/libcpu_baseline.so oracle/cpu_baseline.c -lcrypto
+ */
+#include <openssl/bn.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EB 256
+
+typedef struct {
+  const uint8_t *q, *commitments, *pk, *y, *r, *c;
+  const int64_t* positions;
+  size_t t, s, first, stride;
+  int schedule;
+  uint8_t *x_out, *a1_out, *a2_out;
+} job_t;
+
+static void put(const BIGNUM* v, uint8_t* out) { BN_bn2binpad(v, out, EB); }
+
+static void* worker(void* arg) {
+  job_t* J = (job_t*)arg;
+  BN_CTX* ctx = BN_CTX_new();
+  BIGNUM *q = BN_bin2bn(J->q, EB, NULL), *qm1 = BN_dup(q), *g = BN_new(), *c = BN_bin2bn(J->c, EB, NULL);
+  BN_sub_word(qm1, 1);
+  BN_set_word(g, 4); /* subgroup generator, src/groups/modp.rs:65-66 */
+  BN_MONT_CTX* mont = BN_MONT_CTX_new();
+  BN_MONT_CTX_set(mont, q, ctx);
+  BIGNUM** C = malloc(J->t * sizeof(BIGNUM*));
+  for (size_t j = 0; j < J->t; ++j) C[j] = BN_bin2bn(J->commitments + j * EB, EB, NULL);
+  BIGNUM *x = BN_new(), *e = BN_new(), *tmp = BN_new(), *pos = BN_new(), *a = BN_new(), *b = BN_new();
+  for (size_t i = J->first; i < J->s; i += J->stride) {
+    BN_set_word(pos, (BN_ULONG)J->positions[i]);
+    if (J->schedule == 0) {
+      BN_one(x);
+      BN_one(e);
+      for (size_t j = 0; j < J->t; ++j) { /* participant.rs:423-434 */
+        BN_mod_exp_mont(tmp, C[j], e, q, ctx, mont);
+        BN_mod_mul(x, x, tmp, q, ctx);
+        BN_mod_mul(e, e, pos, qm1, ctx);
+      }
+    } else {
+      BN_copy(x, C[J->t - 1]);
+      for (size_t j = J->t - 1; j-- > 0;) {
+        BN_mod_exp_mont(x, x, pos, q, ctx, mont);
+        BN_mod_mul(x, x, C[j], q, ctx);
+      }
+    }
+    put(x, J->x_out + i * EB);
+    BIGNUM *r = BN_bin2bn(J->r + i * EB, EB, NULL), *pk = BN_bin2bn(J->pk + i * EB, EB, NULL),
+           *y = BN_bin2bn(J->y + i * EB, EB, NULL);
+    /* dleq.rs:66-84 */
+    BN_mod_exp_mont(a, g, r, q, ctx, mont);
+    BN_mod_exp_mont(b, x, c, q, ctx, mont);
+    BN_mod_mul(a, a, b, q, ctx);
+    put(a, J->a1_out + i * EB);
+    BN_mod_exp_mont(a, pk, r, q, ctx, mont);
+    BN_mod_exp_mont(b, y, c, q, ctx, mont);
+    BN_mod_mul(a, a, b, q, ctx);
+    put(a, J->a2_out + i * EB);
+    BN_free(r); BN_free(pk); BN_free(y);
+  }
+  for (size_t j = 0; j < J->t; ++j) BN_free(C[j]);
+  free(C);
+  BN_free(x); BN_free(e); BN_free(tmp); BN_free(pos); BN_free(a); BN_free(b);
+  BN_free(q); BN_free(qm1); BN_free(g); BN_free(c);
+  BN_MONT_CTX_free(mont);
+  BN_CTX_free(ctx);
+  return NULL;
+}
+
+/* X_i, a1_i, a2_i for `s` participants (arrays of s entries; positions 1-based), `nthreads`
+ * host threads, participant i handled by thread i % nthreads. */
+int cpu_modp_verify(const uint8_t* q, const uint8_t* commitments, size_t t, const int64_t* positions,
+                    const uint8_t* pk, const uint8_t* y, const uint8_t* r, const uint8_t* c, size_t s, int nthreads,
+                    int schedule, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > s) nthreads = (int)s;
+  pthread_t* th = malloc(nthreads * sizeof(pthread_t));
+  job_t* jobs = malloc(nthreads * sizeof(job_t));
+  for (int k = 0; k < nthreads; ++k) {
+    job_t j = {q, commitments, pk, y, r, c, positions, t, s, (size_t)k, (size_t)nthreads, schedule, x_out, a1_out, a2_out};
+    jobs[k] = j;
+    pthread_create(&th[k], NULL, worker, &jobs[k]);
+  }
+  for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+  free(th);
+  free(jobs);
+  return 0;
+}

@@ -1,0 +1,41 @@
+"""ctypes driver for oracle/cpu_baseline.c (OpenSSL proxy for the reference's CPU path).
+TEST + BENCH INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cpu_baseline.c")
+SO = os.path.join(HERE, "_build", "libcpu_baseline.so")
+
+
+def build(force=False):
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if force or not os.path.exists(SO) or os.path.getmtime(SRC) > os.path.getmtime(SO):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", SO, SRC, "-lcrypto"])
+    return SO
+
+
+def load():
+    lib = ctypes.CDLL(build())
+    p, sz = ctypes.c_char_p, ctypes.c_size_t
+    lib.cpu_modp_verify.argtypes = [p, p, sz, ctypes.POINTER(ctypes.c_int64), p, p, p, p, sz, ctypes.c_int,
+                                    ctypes.c_int, p, p, p]
+    lib.cpu_modp_verify.restype = ctypes.c_int
+    return lib
+
+
+def be(x):
+    return int(x).to_bytes(256, "big")
+
+
+def modp_verify(q, commitments, positions, pks, ys, rs, c, nthreads=1, schedule=0):
+    """Returns (X, a1, a2) lists of ints for the given participants."""
+    lib = load()
+    s = len(positions)
+    xo, a1o, a2o = (ctypes.create_string_buffer(256 * s) for _ in range(3))
+    lib.cpu_modp_verify(be(q), b"".join(be(v) for v in commitments), len(commitments),
+                        (ctypes.c_int64 * s)(*positions), b"".join(be(v) for v in pks), b"".join(be(v) for v in ys),
+                        b"".join(be(v) for v in rs), be(c), s, nthreads, schedule, xo, a1o, a2o)
+    dec = lambda b: [int.from_bytes(b.raw[i * 256:(i + 1) * 256], "big") for i in range(s)]
+    return dec(xo), dec(a1o), dec(a2o)
