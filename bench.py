@@ -135,6 +135,8 @@ def measure_imad_peak():
     """Measured 32-bit integer multiply-add issue peak of this GPU (tools/imad_peak.cu)."""
     exe = os.path.join(ROOT, "tools", "imad_peak")
     try:
+        if os.environ.get("MPVSS_SKIP_PEAK"):
+            raise RuntimeError("skipped (profiling run)")
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
         j = json.loads(out)
         lo = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_lo_"))

@@ -73,9 +73,9 @@ struct mpvss_ctx {
   // staged verify_distribution state
   size_t v_n = 0, v_t = 0;
   uint32_t v_rwin = 0, v_cwin = 0;
-  std::vector<std::pair<uint32_t, uint32_t>> v_classes;  // (base-4 digits, count) launch classes
+  size_t v_np = 0;  // padded instance count of the Horner launch
   std::vector<uint8_t> v_challenge, v_y_host;
-  DevBuf v_slot, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+  DevBuf v_slot, v_nd, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
 
   // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call
   mpvss_ctx() : scratch(24), pinned(8) {}

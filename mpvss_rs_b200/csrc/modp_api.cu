@@ -207,7 +207,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd})
     b->release();
 }
 
@@ -256,12 +256,12 @@ int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint
   return sync(ctx);
 }
 
-// Positions are grouped by their number of base-4 digits: every group of a launch runs the
-// same fixed-window schedule, so one launch per digit class (concurrently, on the auxiliary
-// streams) keeps a single large position from lengthening everybody's schedule.
+// Positions are sorted by their number of base-4 digits (longest first) and every digit class
+// is padded to a whole number of warps, so all groups of a warp run the same fixed-window
+// schedule while one launch covers every class (a single large position no longer lengthens
+// everybody's schedule, and the long chains start first).
 struct PosPlan {
-  std::vector<uint32_t> pos, slot;           // instances sorted by digit class
-  std::vector<std::pair<uint32_t, uint32_t>> classes;  // (ndigits, count), in `pos` order
+  std::vector<uint32_t> pos, slot, nd;  // padded instance arrays; slot 0xffffffff = padding
 };
 static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
   std::vector<std::vector<uint32_t>> by(17);
@@ -270,13 +270,19 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
     if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
     by[ndigits_for((uint64_t)p)].push_back((uint32_t)i);
   }
-  plan.pos.clear(); plan.slot.clear(); plan.classes.clear();
-  for (uint32_t d = 1; d <= 16; ++d) {
+  const size_t gpw = 32 / ctx->modp_tpi;
+  plan.pos.clear(); plan.slot.clear(); plan.nd.clear();
+  for (uint32_t d = 16; d >= 1; --d) {
     if (by[d].empty()) continue;
-    plan.classes.push_back({d, (uint32_t)by[d].size()});
     for (uint32_t i : by[d]) {
       plan.slot.push_back(i);
       plan.pos.push_back((uint32_t)(positions ? positions[i] : (int64_t)i + 1));
+      plan.nd.push_back(d);
+    }
+    while (plan.pos.size() % gpw) {
+      plan.slot.push_back(0xffffffffu);
+      plan.pos.push_back(plan.pos.back());
+      plan.nd.push_back(d);
     }
   }
   return MPVSS_OK;
@@ -284,27 +290,13 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
 
 // commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
 static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
-                      const uint32_t* slot, const std::vector<std::pair<uint32_t, uint32_t>>& classes, uint32_t* x) {
+                      const uint32_t* slot, const uint32_t* nd, size_t n_padded, uint32_t* x) {
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-  size_t off = 0, k = 0;
-  for (auto& cl : classes) {
-    cudaStream_t s = (classes.size() == 1) ? ctx->stream : ctx->aux[k % 2];
-    if (s != ctx->stream) MPVSS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_fork, 0));
-    modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos + off, slot + off, x,
-                       (uint32_t)t,                  cl.second,          cl.first};
-    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, s));
-    timing_launch(ctx);
-    off += cl.second;
-    ++k;
-  }
-  if (classes.size() > 1) {
-    for (int a = 0; a < 2; ++a) {
-      MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[a], ctx->aux[a]));
-      MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[a], 0));
-    }
-  }
+  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, x, (uint32_t)t,
+                     (uint32_t)n_padded, 0};
+  MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
+  timing_launch(ctx);
   return MPVSS_OK;
 }
 
@@ -313,13 +305,16 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
   MPVSS_TRY(check_args(ctx, commitments && out && n > 0 && t > 0, "poly_eval_exp: bad arguments"));
   PosPlan plan;
   MPVSS_TRY(prep_positions(ctx, positions, n, plan));
-  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4);
+  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4),
+         &dnd = ctx->buf(5);
+  const size_t np = plan.pos.size();
   MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), n * 4));
-  MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), np * 4));
+  MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), np * 4));
+  MPVSS_TRY(h2d(ctx, dnd, plan.nd.data(), np * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
   timing_begin(ctx);
-  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), plan.classes,
+  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(), np,
                        dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
@@ -414,10 +409,11 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
                        "verify_distribution: bad arguments"));
   PosPlan plan;
   MPVSS_TRY(prep_positions(ctx, positions, n, plan));
-  ctx->v_classes = plan.classes;
+  ctx->v_np = plan.pos.size();
   MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), n * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), n * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), ctx->v_np * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nd.data(), ctx->v_np * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
@@ -442,7 +438,7 @@ static int verify_kernels(mpvss_ctx* ctx) {
   timing_begin(ctx);
   // X_i from the commitments (participant.rs:423-434)
   MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                       ctx->v_slot.as<uint32_t>(), ctx->v_classes, X));
+                       ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
   // dleq.rs:66-84
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,

@@ -60,10 +60,12 @@ MP_DEV void finish_store(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, uint32_t* d
 struct HornerArgs {
   const uint32_t* consts;  // constant block
   const uint32_t* cm;      // t commitments, Montgomery form, 64 limbs each
-  const uint32_t* pos;     // n positions (1-based, < 2^(2*ndigits))
-  const uint32_t* slot;    // n output slots (nullptr: instance i writes slot i)
+  const uint32_t* pos;     // n positions (1-based)
+  const uint32_t* slot;    // n output slots (nullptr: instance i writes slot i; 0xffffffff: padding)
+  const uint32_t* nd;      // n base-4 digit counts; all instances of one warp carry the same value
+                           // (nullptr: `ndigits` for every instance)
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
-  uint32_t t, n, ndigits;  // ndigits = base-4 digits of the largest position
+  uint32_t t, n, ndigits;
 };
 
 template <int TPI>
@@ -88,6 +90,8 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
   uint32_t* sq = tbl + 192;
   warp_copy64(one, A.consts + C_ONE);
   const uint32_t pos = A.pos[inst];
+  const uint32_t w0 = wg * GPW;
+  const uint32_t ndigits = A.nd ? A.nd[w0 < A.n ? w0 : A.n - 1] : A.ndigits;  // warp-uniform schedule
   uint32_t acc[L];
   load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
   simt::syncwarp();
@@ -103,9 +107,9 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
     mont_mul<TPI>(x, x, tbl, M, ln);
     stage<TPI>(tbl + 128, x, ln);
     simt::syncwarp();
-    uint32_t d = (pos >> (2 * (A.ndigits - 1))) & 3u;
+    uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
     load_slice<TPI>(acc, d ? tbl + (d - 1) * 64 : one, ln);
-    for (int s = (int)A.ndigits - 2; s >= 0; --s) {
+    for (int s = (int)ndigits - 2; s >= 0; --s) {
       sqr_inplace<TPI>(acc, sq, M, ln);
       sqr_inplace<TPI>(acc, sq, M, ln);
       d = (pos >> (2 * s)) & 3u;
@@ -114,7 +118,8 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
     mont_mul<TPI>(acc, acc, cbuf, M, ln);
   }
   const uint32_t slot = A.slot ? A.slot[inst] : inst;
-  finish_store<TPI>(acc, sq, A.out + (size_t)slot * 64, live, M, ln);
+  finish_store<TPI>(acc, sq, A.out + (size_t)(slot == 0xffffffffu ? 0 : slot) * 64, live && slot != 0xffffffffu, M,
+                    ln);
 }
 
 // ------------------------------------------------- (double) exponentiation ----

@@ -38,7 +38,7 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
 
 extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
                                uint32_t n, uint32_t ndigits, uint32_t* out) {
-  modp::HornerArgs A{consts, cm, pos, nullptr, out, t, n, ndigits};
+  modp::HornerArgs A{consts, cm, pos, nullptr, nullptr, out, t, n, ndigits};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
                           [&](uint32_t w, uint32_t* s) { modp::horner_body<T>(A, w, s); }));
   return 0;
