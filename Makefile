@@ -5,7 +5,7 @@ CXX       ?= g++
 CSRC      := mpvss_rs_b200/csrc
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread
 LIB       := mpvss_rs_b200/libmpvss_b200.so
-CU        := $(CSRC)/api.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu
+CU        := $(CSRC)/api.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu $(CSRC)/ec_api.cu $(CSRC)/ec.cu
 OBJ       := $(CU:.cu=.o)
 HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/mpvss_b200.h
 
@@ -17,8 +17,8 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 $(LIB): $(OBJ)
 	$(NVCC) -shared -o $@ $(OBJ) -Xcompiler -pthread
 
-emu: tests/emu/libemu_modp.so
-tests/emu/libemu_modp.so: tests/emu/emu_modp.cpp $(HDR)
+emu: tests/emu/libemu_modp.so tests/emu/libemu_ec.so
+tests/emu/libemu_%.so: tests/emu/emu_%.cpp $(HDR)
 	$(CXX) -std=c++20 -O2 -DMPVSS_SIMT_EMU -shared -fPIC -pthread -o $@ $<
 
 clean:

@@ -47,6 +47,8 @@ int unsupported(mpvss_ctx* ctx, const char* fn) {
     Guard _g(ctx);                                                         \
     switch ((ctx)->group) {                                                \
       case MPVSS_GROUP_MODP: return modp_api::fn(ctx, __VA_ARGS__);        \
+      case MPVSS_GROUP_SECP256K1: return secp_api::fn(ctx, __VA_ARGS__);   \
+      case MPVSS_GROUP_RISTRETTO255: return rist_api::fn(ctx, __VA_ARGS__); \
       default: return unsupported(ctx, #fn);                               \
     }                                                                      \
   } while (0)
@@ -81,6 +83,8 @@ int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
       return bail(MPVSS_ERR_CUDA);
   int s = MPVSS_OK;
   if (group == MPVSS_GROUP_MODP) s = modp_api::init(ctx);
+  if (group == MPVSS_GROUP_SECP256K1) s = secp_api::init(ctx);
+  if (group == MPVSS_GROUP_RISTRETTO255) s = rist_api::init(ctx);
   if (s != MPVSS_OK) return bail(s);
   *out = ctx;
   return MPVSS_OK;
@@ -91,6 +95,7 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   modp_api::destroy(ctx);
+  ctx->ec_consts.release();
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
   for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_mid, ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1]})

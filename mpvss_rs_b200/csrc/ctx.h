@@ -68,6 +68,10 @@ struct mpvss_ctx {
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
+  // ---- elliptic-curve groups ----
+  DevBuf ec_consts;             // secp::Consts / rist::Consts
+  big::Int ec_order;            // group order (scalar field modulus)
+  std::vector<uint8_t> ec_gen;  // encoded generator (both generators of the trait are this point)
   std::vector<DevBuf> scratch;  // call-local device buffers, reused across calls
   std::vector<PinBuf> pinned;   // call-local pinned host buffers
   // staged verify_distribution state
@@ -128,3 +132,51 @@ int verify_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint
                   int*);
 int reconstruct(mpvss_ctx*, size_t, const int64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*);
 }  // namespace modp_api
+namespace secp_api {
+int init(mpvss_ctx* ctx);
+int batch_exp(mpvss_ctx*, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*);
+int fixed_base_exp(mpvss_ctx*, int, const uint8_t*, size_t, uint8_t*);
+int batch_mul(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int poly_eval_exp(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
+int dleq_verify_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                       const uint8_t*, size_t, size_t, uint8_t*, uint8_t*);
+int dleq_prove_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, uint8_t*, uint8_t*);
+int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
+                 const uint8_t*, const uint8_t*);
+int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int verify_compute(mpvss_ctx*, void*, void*, void*);
+int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                     int*, uint8_t*);
+int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
+               uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,
+                   uint8_t*, int*);
+int verify_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                  int*);
+int reconstruct(mpvss_ctx*, size_t, const int64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*);
+}  // namespace secp_api
+namespace rist_api {
+int init(mpvss_ctx* ctx);
+int batch_exp(mpvss_ctx*, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*);
+int fixed_base_exp(mpvss_ctx*, int, const uint8_t*, size_t, uint8_t*);
+int batch_mul(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int poly_eval_exp(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
+int dleq_verify_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                       const uint8_t*, size_t, size_t, uint8_t*, uint8_t*);
+int dleq_prove_commit(mpvss_ctx*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, uint8_t*, uint8_t*);
+int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
+int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
+                 const uint8_t*, const uint8_t*);
+int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int verify_compute(mpvss_ctx*, void*, void*, void*);
+int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                     int*, uint8_t*);
+int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
+               uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
+int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,
+                   uint8_t*, int*);
+int verify_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                  int*);
+int reconstruct(mpvss_ctx*, size_t, const int64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*);
+}  // namespace rist_api

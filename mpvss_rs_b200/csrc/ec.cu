@@ -1,0 +1,70 @@
+// __global__ entry points for the elliptic-curve kernels, instantiated for secp256k1 and
+// ristretto255 (bodies in ec_kernels.cuh).
+#include "ec_launch.h"
+
+namespace ec {
+
+constexpr int TPB = 128;
+static inline unsigned blocks(uint32_t n) { return (n + TPB - 1) / TPB; }
+#define TID (blockIdx.x * TPB + threadIdx.x)
+
+template <class Cv> __global__ void __launch_bounds__(TPB) exp2_kernel(Exp2Args<Cv> A) { exp2_body<Cv>(A, TID); }
+template <class Cv> __global__ void __launch_bounds__(TPB) decode_kernel(DecodeArgs<Cv> A) { decode_body<Cv>(A, TID); }
+template <class Cv> __global__ void __launch_bounds__(TPB) horner_kernel(HornerArgs<Cv> A) { horner_body<Cv>(A, TID); }
+template <class Cv> __global__ void __launch_bounds__(TPB) sum_kernel(SumArgs<Cv> A) { sum_body<Cv>(A, TID); }
+template <class Cv> __global__ void __launch_bounds__(TPB) add_kernel(AddArgs<Cv> A) { add_body<Cv>(A, TID); }
+__global__ void __launch_bounds__(TPB) poly_kernel(PolyArgs A) { poly_body(A, TID); }
+__global__ void __launch_bounds__(TPB) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, TID); }
+__global__ void __launch_bounds__(TPB) inv_kernel(InvArgs A) { inv_body(A, TID); }
+
+template <class Cv> cudaError_t launch_exp2(const Exp2Args<Cv>& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  exp2_kernel<Cv><<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+template <class Cv> cudaError_t launch_decode(const DecodeArgs<Cv>& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  decode_kernel<Cv><<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+template <class Cv> cudaError_t launch_horner(const HornerArgs<Cv>& A, cudaStream_t s) {
+  if (A.n == 0 || A.K == 0 || A.t == 0) return cudaErrorInvalidValue;
+  horner_kernel<Cv><<<blocks(A.n * A.K), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+template <class Cv> cudaError_t launch_sum(const SumArgs<Cv>& A, cudaStream_t s) {
+  if (A.groups == 0) return cudaErrorInvalidValue;
+  sum_kernel<Cv><<<blocks(A.groups), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+template <class Cv> cudaError_t launch_add(const AddArgs<Cv>& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  add_kernel<Cv><<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s) {
+  if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
+  poly_kernel<<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s) {
+  if (A.k == 0) return cudaErrorInvalidValue;
+  lagrange_kernel<<<blocks(A.k), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_inv(const InvArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  inv_kernel<<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+#define INSTANTIATE(Cv)                                                                  \
+  template cudaError_t launch_exp2<Cv>(const Exp2Args<Cv>&, cudaStream_t);               \
+  template cudaError_t launch_decode<Cv>(const DecodeArgs<Cv>&, cudaStream_t);           \
+  template cudaError_t launch_horner<Cv>(const HornerArgs<Cv>&, cudaStream_t);           \
+  template cudaError_t launch_sum<Cv>(const SumArgs<Cv>&, cudaStream_t);                 \
+  template cudaError_t launch_add<Cv>(const AddArgs<Cv>&, cudaStream_t);
+INSTANTIATE(secp::SecpCurve)
+INSTANTIATE(rist::RistCurve)
+
+}  // namespace ec

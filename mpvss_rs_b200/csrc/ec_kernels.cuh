@@ -1,0 +1,325 @@
+// Kernel bodies for the elliptic-curve groups (Secp256k1Group, Ristretto255Group), one
+// instance per thread, templated on a curve policy (secp.cuh: SecpCurve, rist.cuh:
+// RistCurve).  `tid` is the global thread index; bodies return immediately for tid >= n (no
+// warp-collective operations are used).
+//
+// Reference call sites replaced (paths under /root/reference/src; secp256k1 / ristretto255):
+//   exp2_body    : group.exp / DLEQ commitments  secp256k1.rs:91-100, ristretto255.rs:161-170,
+//                  dleq.rs:37-39, 66-84, participant.rs:1143,1187,1202-1203,1300,1316-1317,1544 /
+//                  1608,1645,1660-1661,1743,1759-1760,1992
+//   horner_body  : X_i = sum_j (i^j) C_j  participant.rs:1174-1184, 1411-1421 / 1630-1642, 1854-1864
+//   add_body     : group.mul  secp256k1.rs:102-107, ristretto255.rs:172-177
+//   poly_body    : P(i) mod order  polynomial.rs:50-58 via participant.rs:1155-1157 / 1619-1621
+//   lagrange_body: lambda_i  participant.rs:1518-1557 / 1955-2002
+//   inv_body     : scalar inverse  secp256k1.rs:109-112, ristretto255.rs:179-187
+#pragma once
+#include "fp256.cuh"
+
+namespace ec {
+
+using fp256::Fe;
+using fp256::Modulus;
+
+MP_DEV uint32_t nibble(const uint32_t* e, int w) { return (e[w >> 3] >> ((w & 7) * 4)) & 15u; }
+
+// table[i] = i * p for i = 0..15
+template <class Cv>
+MP_DEV void build_table(typename Cv::Point* tbl, const typename Cv::Point& p, const typename Cv::Consts& C) {
+  tbl[0] = Cv::infinity(C);
+  tbl[1] = p;
+  tbl[2] = Cv::dbl(p, C);
+#pragma unroll 1
+  for (int i = 3; i < 16; ++i) tbl[i] = (i & 1) ? Cv::add(tbl[i - 1], p, C) : Cv::dbl(tbl[i >> 1], C);
+}
+
+// e1 * p1 [+ e2 * p2]: fixed 4-bit windows, doublings shared between the two scalars
+// (scalars: 8 little-endian u32 limbs)
+template <class Cv>
+MP_DEV typename Cv::Point scalar_mul2(const typename Cv::Point& p1, const uint32_t* e1, const typename Cv::Point* p2,
+                                      const uint32_t* e2, typename Cv::Point* tbl1, typename Cv::Point* tbl2,
+                                      const typename Cv::Consts& C) {
+  build_table<Cv>(tbl1, p1, C);
+  if (p2) build_table<Cv>(tbl2, *p2, C);
+  typename Cv::Point acc = Cv::infinity(C);
+#pragma unroll 1
+  for (int w = 63; w >= 0; --w) {
+    if (w != 63) {
+      acc = Cv::dbl(acc, C);
+      acc = Cv::dbl(acc, C);
+      acc = Cv::dbl(acc, C);
+      acc = Cv::dbl(acc, C);
+    }
+    uint32_t d = nibble(e1, w);
+    if (d) acc = Cv::add(acc, tbl1[d], C);
+    if (p2) {
+      d = nibble(e2, w);
+      if (d) acc = Cv::add(acc, tbl2[d], C);
+    }
+  }
+  return acc;
+}
+
+// small-integer multiple [k]p for k < 2^(2*nd): fixed 2-bit windows
+template <class Cv>
+MP_DEV typename Cv::Point small_mul(const typename Cv::Point& p, uint32_t k, uint32_t nd,
+                                    const typename Cv::Consts& C) {
+  typename Cv::Point t2 = Cv::dbl(p, C), t3 = Cv::add(t2, p, C);
+  typename Cv::Point acc = Cv::infinity(C);
+#pragma unroll 1
+  for (int s = (int)nd - 1; s >= 0; --s) {
+    if (s != (int)nd - 1) {
+      acc = Cv::dbl(acc, C);
+      acc = Cv::dbl(acc, C);
+    }
+    uint32_t d = (k >> (2 * s)) & 3u;
+    if (d == 1) acc = Cv::add(acc, p, C);
+    else if (d == 2) acc = Cv::add(acc, t2, C);
+    else if (d == 3) acc = Cv::add(acc, t3, C);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------ e1*B1 [+ e2*B2] ----
+template <class Cv>
+struct Exp2Args {
+  const typename Cv::Consts* C;
+  const uint8_t* b1;   // compressed points, stride b1_stride bytes (0 = one shared base)
+  const uint32_t* e1;  // scalars, 8 little-endian limbs each, stride e1_stride limbs
+  const uint8_t* b2;   // optional second base / scalar
+  const uint32_t* e2;
+  uint8_t* out;        // encoded results (Cv::EB bytes each), or nullptr
+  typename Cv::Point* out_jac;  // projective results, or nullptr
+  uint32_t* status;    // per instance: 0 ok, 1 invalid encoding
+  uint32_t n, b1_stride, e1_stride, b2_stride, e2_stride;
+  uint32_t negate_mask_stride;  // unused (reserved)
+};
+
+template <class Cv>
+MP_DEV void exp2_body(const Exp2Args<Cv>& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  using Point = typename Cv::Point;
+  const typename Cv::Consts& C = *A.C;
+  typename Cv::Affine a1, a2;
+  bool ok = Cv::decode(a1, A.b1 + (size_t)tid * A.b1_stride, C);
+  if (A.b2) ok = Cv::decode(a2, A.b2 + (size_t)tid * A.b2_stride, C) && ok;
+  if (A.status) A.status[tid] = ok ? 0u : 1u;
+  Point tbl1[16], tbl2[16];
+  Point p1 = Cv::from_aff(a1, C), p2;
+  if (A.b2) p2 = Cv::from_aff(a2, C);
+  uint32_t e1[8], e2[8];
+  for (int i = 0; i < 8; ++i) {
+    e1[i] = A.e1[(size_t)tid * A.e1_stride + i];
+    e2[i] = A.b2 ? A.e2[(size_t)tid * A.e2_stride + i] : 0u;
+  }
+  Point r = ok ? scalar_mul2<Cv>(p1, e1, A.b2 ? &p2 : nullptr, e2, tbl1, tbl2, C) : Cv::infinity(C);
+  if (A.out_jac) A.out_jac[tid] = r;
+  if (A.out) Cv::encode(A.out + (size_t)tid * Cv::EB, r, C);
+}
+
+// ----------------------------------------------------------------- decode ----
+template <class Cv>
+struct DecodeArgs {
+  const typename Cv::Consts* C;
+  const uint8_t* in;   // n compressed points
+  uint32_t* xy;        // n x 16 limbs: x, y in Montgomery form (identity: all zero)
+  uint32_t* status;
+  uint32_t n;
+};
+template <class Cv>
+MP_DEV void decode_body(const DecodeArgs<Cv>& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  typename Cv::Affine a;
+  bool ok = Cv::decode(a, A.in + (size_t)tid * Cv::EB, *A.C);
+  fp256::store(A.xy + (size_t)tid * 16, a.x);
+  fp256::store(A.xy + (size_t)tid * 16 + 8, a.y);
+  A.status[tid] = ok ? (a.inf ? 2u : 0u) : 1u;
+}
+
+// ----------------------------------------------------------------- Horner ----
+// Instance (k, i) = tid / n, tid % n evaluates chunk k of the commitment polynomial at
+// position pos[i] by Horner in the group, then scales by pos^(k*B) so that the K partial
+// results of a position add up to X_i (chunking only adds parallelism; the group element is
+// the same as the reference's sum of t scalar multiplications).
+template <class Cv>
+struct HornerArgs {
+  const typename Cv::Consts* C;
+  const uint32_t* cxy;     // t commitments, affine Montgomery (decode_body layout)
+  const uint32_t* cstatus; // decode status per commitment (2 = identity)
+  const uint32_t* pos;     // n positions
+  typename Cv::Point* out; // K * n partial results, index k * n + i
+  uint32_t t, n, K, B;     // K chunks of B coefficients (last one shorter)
+};
+
+MP_DEV uint32_t digits4(uint32_t p) {
+  uint32_t d = 1;
+  while (d < 16 && (p >> (2 * d))) ++d;
+  return d;
+}
+template <class Cv>
+MP_DEV typename Cv::Affine load_aff(const uint32_t* xy, uint32_t status) {
+  typename Cv::Affine a;
+  a.x = fp256::load(xy);
+  a.y = fp256::load(xy + 8);
+  a.inf = status == 2u;
+  return a;
+}
+
+template <class Cv>
+MP_DEV void horner_body(const HornerArgs<Cv>& A, uint32_t tid) {
+  if (tid >= A.n * A.K) return;
+  using Point = typename Cv::Point;
+  const typename Cv::Consts& C = *A.C;
+  const uint32_t k = tid / A.n, i = tid % A.n;
+  const uint32_t lo = k * A.B, hi = (lo + A.B < A.t) ? lo + A.B : A.t;
+  const uint32_t pos = A.pos[i], nd = digits4(pos);
+  Point acc = Cv::from_aff(load_aff<Cv>(A.cxy + (size_t)(hi - 1) * 16, A.cstatus[hi - 1]), C);
+#pragma unroll 1
+  for (int j = (int)hi - 2; j >= (int)lo; --j) {
+    acc = small_mul<Cv>(acc, pos, nd, C);
+    acc = Cv::madd(acc, load_aff<Cv>(A.cxy + (size_t)j * 16, A.cstatus[j]), C);
+  }
+  if (k > 0) {
+    // e = pos^(k*B) mod n in the scalar field, then acc <- e * acc
+    using namespace fp256;
+    Fe b = fe_zero();
+    b.v[0] = pos;
+    b = to_mont(b, C.N);
+    Fe e = mont_one(C.N);
+    uint32_t ex = lo;
+    bool started = false;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      if (started) e = sqr(e, C.N);
+      if ((ex >> bit) & 1u) {
+        e = started ? mul(e, b, C.N) : b;
+        started = true;
+      }
+    }
+    e = from_mont(e, C.N);
+    Point tbl[16];
+    acc = scalar_mul2<Cv>(acc, e.v, nullptr, e.v, tbl, tbl, C);
+  }
+  A.out[tid] = acc;
+}
+
+// --------------------------------------------------------- sums / encoding ----
+template <class Cv>
+struct SumArgs {
+  const typename Cv::Consts* C;
+  const typename Cv::Point* in;  // element (g, j) at in[g * g_stride + j * j_stride], j < count (clipped to total)
+  typename Cv::Point* out_jac;   // groups results (or nullptr)
+  uint8_t* out;                  // groups encoded results (or nullptr)
+  uint32_t groups, count, g_stride, j_stride, total;
+};
+template <class Cv>
+MP_DEV void sum_body(const SumArgs<Cv>& A, uint32_t tid) {
+  if (tid >= A.groups) return;
+  const typename Cv::Consts& C = *A.C;
+  typename Cv::Point acc = A.in[(size_t)tid * A.g_stride];
+#pragma unroll 1
+  for (uint32_t j = 1; j < A.count; ++j) {
+    size_t idx = (size_t)tid * A.g_stride + (size_t)j * A.j_stride;
+    if (idx >= A.total) break;
+    acc = Cv::add(acc, A.in[idx], C);
+  }
+  if (A.out_jac) A.out_jac[tid] = acc;
+  if (A.out) Cv::encode(A.out + (size_t)tid * Cv::EB, acc, C);
+}
+
+// out[i] = a[i] + b[i]   (Group::mul)
+template <class Cv>
+struct AddArgs {
+  const typename Cv::Consts* C;
+  const uint8_t *a, *b;
+  uint8_t* out;
+  uint32_t* status;
+  uint32_t n;
+};
+template <class Cv>
+MP_DEV void add_body(const AddArgs<Cv>& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  const typename Cv::Consts& C = *A.C;
+  typename Cv::Affine a, b;
+  bool ok = Cv::decode(a, A.a + (size_t)tid * Cv::EB, C);
+  ok = Cv::decode(b, A.b + (size_t)tid * Cv::EB, C) && ok;
+  A.status[tid] = ok ? 0u : 1u;
+  typename Cv::Point r = Cv::madd(Cv::from_aff(a, C), b, C);
+  Cv::encode(A.out + (size_t)tid * Cv::EB, r, C);
+}
+
+// ---------------------------------------------------------- scalar kernels ----
+// p_i = P(pos_i) mod n by Horner in the scalar field (coefficients: 8 LE limbs, < n)
+struct PolyArgs {
+  const Modulus* N;
+  const uint32_t* coeffs;  // t x 8 limbs
+  const uint32_t* pos;     // n positions
+  uint32_t* out;           // n x 8 limbs
+  uint32_t t, n;
+};
+MP_DEV void poly_body(const PolyArgs& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  using namespace fp256;
+  const Modulus& N = *A.N;
+  Fe x = fe_zero();
+  x.v[0] = A.pos[tid];
+  x = to_mont(x, N);
+  Fe acc = to_mont(load(A.coeffs + (size_t)(A.t - 1) * 8), N);
+#pragma unroll 1
+  for (int j = (int)A.t - 2; j >= 0; --j) acc = add(mul(acc, x, N), to_mont(load(A.coeffs + (size_t)j * 8), N), N);
+  store(A.out + (size_t)tid * 8, from_mont(acc, N));
+}
+
+// Lagrange coefficients at 0 for the given positions, in the scalar field, with the sign of
+// the reference folded in:  lambda_i = prod_{j != i} x_j / (x_j - x_i)  (participant.rs:1518-1557
+// computes |x_j - x_i| and a separate sign, then negates the point; negating the scalar gives
+// the same group element).
+struct LagrangeArgs {
+  const Modulus* N;
+  const uint32_t* pos;  // k positions
+  uint32_t* out;        // k x 8 limbs
+  uint32_t k;
+};
+MP_DEV void lagrange_body(const LagrangeArgs& A, uint32_t tid) {
+  if (tid >= A.k) return;
+  using namespace fp256;
+  const Modulus& N = *A.N;
+  const uint32_t xi = A.pos[tid];
+  Fe num = mont_one(N), den = mont_one(N);
+  bool negative = false;
+#pragma unroll 1
+  for (uint32_t j = 0; j < A.k; ++j) {
+    if (j == tid) continue;
+    uint32_t xj = A.pos[j];
+    Fe a = fe_zero(), d = fe_zero();
+    a.v[0] = xj;
+    if (xj < xi) {
+      negative = !negative;
+      d.v[0] = xi - xj;
+    } else {
+      d.v[0] = xj - xi;
+    }
+    num = mul(num, to_mont(a, N), N);
+    den = mul(den, to_mont(d, N), N);
+  }
+  Fe lam = mul(num, inv(den, N), N);  // den = 0 (duplicate position) -> lambda = 0, as ristretto255.rs falls back
+  if (negative) lam = neg(lam, N);
+  store(A.out + (size_t)tid * 8, from_mont(lam, N));
+}
+
+// out[i] = in[i]^-1 in the scalar field (0 -> 0, flagged in status)
+struct InvArgs {
+  const Modulus* N;
+  const uint32_t* in;
+  uint32_t* out;
+  uint32_t* status;
+  uint32_t n;
+};
+MP_DEV void inv_body(const InvArgs& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  using namespace fp256;
+  Fe x = load(A.in + (size_t)tid * 8);
+  A.status[tid] = is_zero(x) ? 1u : 0u;
+  store(A.out + (size_t)tid * 8, from_mont(inv(to_mont(x, *A.N), *A.N), *A.N));
+}
+
+}  // namespace ec

@@ -1,0 +1,17 @@
+// Host-side launchers for the elliptic-curve kernels (bodies in ec_kernels.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include "secp.cuh"
+#include "rist.cuh"
+#include "ec_kernels.cuh"
+
+namespace ec {
+template <class Cv> cudaError_t launch_exp2(const Exp2Args<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_decode(const DecodeArgs<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_horner(const HornerArgs<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_sum(const SumArgs<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_add(const AddArgs<Cv>& A, cudaStream_t s);
+cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s);
+cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s);
+cudaError_t launch_inv(const InvArgs& A, cudaStream_t s);
+}  // namespace ec

@@ -1,0 +1,183 @@
+// ristretto255 group operations, one point per thread (replaces curve25519-dalek's
+// RistrettoPoint * Scalar / + / compress / decompress behind
+// /root/reference/src/groups/ristretto255.rs:161-220).  Extended twisted-Edwards coordinates
+// (a = -1) over the Montgomery-form field 2^255-19 of fp256.cuh; encoding and decoding follow
+// RFC 9496 sections 4.3.1-4.3.2.
+#pragma once
+#include "fp256.cuh"
+
+namespace rist {
+
+using fp256::Fe;
+using fp256::Modulus;
+
+struct Consts {
+  Modulus P;                   // 2^255 - 19
+  Modulus N;                   // l = 2^252 + 27742317777372353535851937790883648493
+  uint32_t d[8], d2[8];        // d, 2d (Montgomery form)
+  uint32_t sqrt_m1[8];         // sqrt(-1)
+  uint32_t invsqrt_a_minus_d[8];
+  uint32_t bx[8], by[8];       // basepoint, affine, Montgomery form
+  uint32_t pm5d8[8];           // (p - 5) / 8
+};
+
+struct Ext {
+  Fe X, Y, Z, T;
+};
+struct Aff {  // affine Edwards coordinates of a representative, Montgomery form
+  Fe x, y;
+  uint32_t inf;  // unused (the identity (0, 1) is an ordinary point); kept for the policy interface
+};
+
+MP_DEV Ext ext_identity(const Modulus& P) {
+  Ext r;
+  r.X = fp256::fe_zero();
+  r.Y = fp256::mont_one(P);
+  r.Z = fp256::mont_one(P);
+  r.T = fp256::fe_zero();
+  return r;
+}
+MP_DEV Ext ext_from_aff(const Aff& a, const Modulus& P) {
+  Ext r;
+  r.X = a.x;
+  r.Y = a.y;
+  r.Z = fp256::mont_one(P);
+  r.T = fp256::mul(a.x, a.y, P);
+  return r;
+}
+
+// add-2008-hwcd-3 (unified, complete for a = -1 and non-square d): 9M
+MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  Fe A = mul(sub(p.Y, p.X, P), sub(q.Y, q.X, P), P);
+  Fe B = mul(add(p.Y, p.X, P), add(q.Y, q.X, P), P);
+  Fe Cc = mul(mul(p.T, load(C.d2), P), q.T, P);
+  Fe D = dbl(mul(p.Z, q.Z, P), P);
+  Fe E = sub(B, A, P), F = sub(D, Cc, P), G = add(D, Cc, P), H = add(B, A, P);
+  Ext r;
+  r.X = mul(E, F, P);
+  r.Y = mul(G, H, P);
+  r.T = mul(E, H, P);
+  r.Z = mul(F, G, P);
+  return r;
+}
+// dbl-2008-hwcd with a = -1: 4M + 4S
+MP_NOINLINE Ext ext_dbl(const Ext& p, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  Fe A = sqr(p.X, P), B = sqr(p.Y, P), Cc = dbl(sqr(p.Z, P), P);
+  Fe D = neg(A, P);
+  Fe E = sub(sub(sqr(add(p.X, p.Y, P), P), A, P), B, P);
+  Fe G = add(D, B, P), F = sub(G, Cc, P), H = sub(D, B, P);
+  Ext r;
+  r.X = mul(E, F, P);
+  r.Y = mul(G, H, P);
+  r.T = mul(E, H, P);
+  r.Z = mul(F, G, P);
+  return r;
+}
+
+// canonical-form helpers (RFC 9496 section 4.1)
+MP_DEV bool is_negative(const Fe& a_mont, const Modulus& P) { return fp256::from_mont(a_mont, P).v[0] & 1u; }
+MP_DEV Fe ct_abs(const Fe& a, const Modulus& P) { return is_negative(a, P) ? fp256::neg(a, P) : a; }
+
+// SQRT_RATIO_M1 (RFC 9496 section 4.2); returns was_square, r in *out
+MP_NOINLINE bool sqrt_ratio_m1(Fe* out, const Fe& u, const Fe& v, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  Fe v3 = mul(sqr(v, P), v, P);
+  Fe v7 = mul(sqr(v3, P), v, P);
+  Fe r = mul(mul(u, v3, P), pow(mul(u, v7, P), C.pm5d8, P), P);
+  Fe check = mul(v, sqr(r, P), P);
+  Fe sm1 = load(C.sqrt_m1);
+  Fe nu = neg(u, P);
+  bool correct = eq(check, u);
+  bool flipped = eq(check, nu);
+  bool flipped_i = eq(check, mul(nu, sm1, P));
+  if (flipped || flipped_i) r = mul(r, sm1, P);
+  *out = ct_abs(r, P);
+  return correct || flipped;
+}
+
+// RFC 9496 section 4.3.2
+MP_NOINLINE void encode(uint8_t* out, const Ext& p, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  Fe u1 = mul(add(p.Z, p.Y, P), sub(p.Z, p.Y, P), P);
+  Fe u2 = mul(p.X, p.Y, P);
+  Fe invsqrt;
+  sqrt_ratio_m1(&invsqrt, mont_one(P), mul(u1, sqr(u2, P), P), C);
+  Fe den1 = mul(invsqrt, u1, P), den2 = mul(invsqrt, u2, P);
+  Fe z_inv = mul(mul(den1, den2, P), p.T, P);
+  Fe sm1 = load(C.sqrt_m1);
+  Fe ix0 = mul(p.X, sm1, P), iy0 = mul(p.Y, sm1, P);
+  Fe enchanted = mul(den1, load(C.invsqrt_a_minus_d), P);
+  bool rotate = is_negative(mul(p.T, z_inv, P), P);
+  Fe x = rotate ? iy0 : p.X;
+  Fe y = rotate ? ix0 : p.Y;
+  Fe den_inv = rotate ? enchanted : den2;
+  if (is_negative(mul(x, z_inv, P), P)) y = neg(y, P);
+  Fe s = from_mont(ct_abs(mul(den_inv, sub(p.Z, y, P), P), P), P);
+  for (int i = 0; i < 8; ++i) {
+    out[4 * i] = (uint8_t)s.v[i];
+    out[4 * i + 1] = (uint8_t)(s.v[i] >> 8);
+    out[4 * i + 2] = (uint8_t)(s.v[i] >> 16);
+    out[4 * i + 3] = (uint8_t)(s.v[i] >> 24);
+  }
+}
+
+// RFC 9496 section 4.3.1; false for non-canonical or invalid encodings
+MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  a.inf = 0;
+  a.x = fe_zero();
+  a.y = mont_one(P);
+  Fe s;
+  for (int i = 0; i < 8; ++i)
+    s.v[i] = (uint32_t)in[4 * i] | (uint32_t)in[4 * i + 1] << 8 | (uint32_t)in[4 * i + 2] << 16 |
+             (uint32_t)in[4 * i + 3] << 24;
+  // canonical: s < p and s non-negative (even)
+  Fe t;
+  t.v[0] = simt::sub_cc(s.v[0], P.m[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(s.v[i], P.m[i]);
+  if (simt::subc(0, 0) == 0) return false;
+  if (s.v[0] & 1u) return false;
+  Fe sm = to_mont(s, P), one = mont_one(P);
+  Fe ss = sqr(sm, P);
+  Fe u1 = sub(one, ss, P), u2 = add(one, ss, P);
+  Fe u2_sqr = sqr(u2, P);
+  Fe v = sub(neg(mul(load(C.d), sqr(u1, P), P), P), u2_sqr, P);
+  Fe invsqrt;
+  bool was_square = sqrt_ratio_m1(&invsqrt, one, mul(v, u2_sqr, P), C);
+  Fe den_x = mul(invsqrt, u2, P);
+  Fe den_y = mul(mul(invsqrt, den_x, P), v, P);
+  Fe x = ct_abs(mul(dbl(sm, P), den_x, P), P);
+  Fe y = mul(u1, den_y, P);
+  Fe tt = mul(x, y, P);
+  if (!was_square || is_negative(tt, P) || is_zero(y)) return false;
+  a.x = x;
+  a.y = y;
+  return true;
+}
+
+// ---- curve policy for ec_kernels.cuh ---------------------------------------------------------
+struct RistCurve {
+  using Consts = rist::Consts;
+  using Point = Ext;
+  using Affine = Aff;
+  static constexpr int EB = 32;
+  MP_DEV static Point infinity(const Consts& C) { return ext_identity(C.P); }
+  MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return ext_from_aff(a, C.P); }
+  MP_DEV static Point dbl(const Point& p, const Consts& C) { return ext_dbl(p, C); }
+  MP_DEV static Point add(const Point& p, const Point& q, const Consts& C) { return ext_add(p, q, C); }
+  MP_DEV static Point madd(const Point& p, const Affine& q, const Consts& C) {
+    return ext_add(p, ext_from_aff(q, C.P), C);
+  }
+  MP_DEV static bool decode(Affine& a, const uint8_t* in, const Consts& C) { return rist::decode(a, in, C); }
+  MP_DEV static void encode(uint8_t* out, const Point& p, const Consts& C) { rist::encode(out, p, C); }
+};
+
+}  // namespace rist

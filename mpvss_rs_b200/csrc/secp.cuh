@@ -1,0 +1,197 @@
+// secp256k1 group operations, one point per thread (replaces k256's
+// ProjectivePoint * Scalar / + / to_bytes / from_bytes behind
+// /root/reference/src/groups/secp256k1.rs:91-152).  Jacobian coordinates over the
+// Montgomery-form base field of fp256.cuh; Z = 0 encodes the identity.  Kernel bodies are
+// written against simt.h, so tests/emu runs them on the CPU as well.
+#pragma once
+#include "fp256.cuh"
+
+namespace secp {
+
+using fp256::Fe;
+using fp256::Modulus;
+
+// Device-resident constants (built on the host in secp_api.cu).
+struct Consts {
+  Modulus P;             // base field  2^256 - 2^32 - 977
+  Modulus N;             // scalar field (group order)
+  uint32_t b7[8];        // 7 in Montgomery form
+  uint32_t gx[8], gy[8]; // generator, affine, Montgomery form
+  uint32_t sqrt_e[8];    // (p + 1) / 4
+};
+
+struct Jac {
+  Fe X, Y, Z;
+};
+struct Aff {  // affine, Montgomery form; inf = identity
+  Fe x, y;
+  uint32_t inf;
+};
+
+MP_DEV Jac jac_infinity(const Modulus& P) {
+  Jac r;
+  r.X = fp256::mont_one(P);
+  r.Y = fp256::mont_one(P);
+  r.Z = fp256::fe_zero();
+  return r;
+}
+MP_DEV bool jac_is_inf(const Jac& p) { return fp256::is_zero(p.Z); }
+MP_DEV Jac jac_from_aff(const Aff& a, const Modulus& P) {
+  if (a.inf) return jac_infinity(P);
+  Jac r;
+  r.X = a.x;
+  r.Y = a.y;
+  r.Z = fp256::mont_one(P);
+  return r;
+}
+MP_DEV Jac jac_neg(const Jac& p, const Modulus& P) {
+  Jac r = p;
+  r.Y = fp256::neg(p.Y, P);
+  return r;
+}
+
+// dbl-2009-l (a = 0): 2M + 5S
+MP_NOINLINE Jac jac_dbl(const Jac& p, const Modulus& P) {
+  using namespace fp256;
+  if (jac_is_inf(p)) return p;
+  Fe A = sqr(p.X, P), B = sqr(p.Y, P), C = sqr(B, P);
+  Fe t = add(p.X, B, P);
+  Fe D = dbl(sub(sub(sqr(t, P), A, P), C, P), P);
+  Fe E = add(dbl(A, P), A, P);
+  Fe F = sqr(E, P);
+  Jac r;
+  r.X = sub(F, dbl(D, P), P);
+  Fe C8 = dbl(dbl(dbl(C, P), P), P);
+  r.Y = sub(mul(E, sub(D, r.X, P), P), C8, P);
+  r.Z = dbl(mul(p.Y, p.Z, P), P);
+  return r;
+}
+
+// add-2007-bl with the exceptional cases handled: 11M + 5S
+MP_NOINLINE Jac jac_add(const Jac& p, const Jac& q, const Modulus& P) {
+  using namespace fp256;
+  if (jac_is_inf(p)) return q;
+  if (jac_is_inf(q)) return p;
+  Fe Z1Z1 = sqr(p.Z, P), Z2Z2 = sqr(q.Z, P);
+  Fe U1 = mul(p.X, Z2Z2, P), U2 = mul(q.X, Z1Z1, P);
+  Fe S1 = mul(mul(p.Y, q.Z, P), Z2Z2, P), S2 = mul(mul(q.Y, p.Z, P), Z1Z1, P);
+  Fe H = sub(U2, U1, P), rr = sub(S2, S1, P);
+  if (is_zero(H)) {
+    if (is_zero(rr)) return jac_dbl(p, P);
+    return jac_infinity(P);
+  }
+  Fe I = sqr(dbl(H, P), P), J = mul(H, I, P), r2 = dbl(rr, P), V = mul(U1, I, P);
+  Jac r;
+  r.X = sub(sub(sqr(r2, P), J, P), dbl(V, P), P);
+  r.Y = sub(mul(r2, sub(V, r.X, P), P), dbl(mul(S1, J, P), P), P);
+  Fe zz = add(p.Z, q.Z, P);
+  r.Z = mul(sub(sub(sqr(zz, P), Z1Z1, P), Z2Z2, P), H, P);
+  return r;
+}
+
+// mixed addition (q affine): madd-2007-bl, 7M + 4S
+MP_NOINLINE Jac jac_madd(const Jac& p, const Aff& q, const Modulus& P) {
+  using namespace fp256;
+  if (q.inf) return p;
+  if (jac_is_inf(p)) return jac_from_aff(q, P);
+  Fe Z1Z1 = sqr(p.Z, P);
+  Fe U2 = mul(q.x, Z1Z1, P), S2 = mul(mul(q.y, p.Z, P), Z1Z1, P);
+  Fe H = sub(U2, p.X, P), rr = sub(S2, p.Y, P);
+  if (is_zero(H)) {
+    if (is_zero(rr)) return jac_dbl(p, P);
+    return jac_infinity(P);
+  }
+  Fe HH = sqr(H, P), I = dbl(dbl(HH, P), P), J = mul(H, I, P), r2 = dbl(rr, P), V = mul(p.X, I, P);
+  Jac r;
+  r.X = sub(sub(sqr(r2, P), J, P), dbl(V, P), P);
+  r.Y = sub(mul(r2, sub(V, r.X, P), P), dbl(mul(p.Y, J, P), P), P);
+  r.Z = sub(sub(sqr(add(p.Z, H, P), P), Z1Z1, P), HH, P);
+  return r;
+}
+
+MP_NOINLINE Aff jac_to_aff(const Jac& p, const Modulus& P) {
+  using namespace fp256;
+  Aff a;
+  if (jac_is_inf(p)) {
+    a.x = fe_zero();
+    a.y = fe_zero();
+    a.inf = 1;
+    return a;
+  }
+  Fe zi = inv(p.Z, P), zi2 = sqr(zi, P);
+  a.x = mul(p.X, zi2, P);
+  a.y = mul(p.Y, mul(zi2, zi, P), P);
+  a.inf = 0;
+  return a;
+}
+
+// ---- SEC1 compressed encoding (secp256k1.rs:133-152) ---------------------------------
+// 33 bytes 02/03 || x (big-endian).  The identity is 33 zero bytes (k256's encoding).
+MP_NOINLINE void encode(uint8_t* out, const Aff& a, const Modulus& P) {
+  if (a.inf) {
+    for (int i = 0; i < 33; ++i) out[i] = 0;
+    return;
+  }
+  Fe x = fp256::from_mont(a.x, P), y = fp256::from_mont(a.y, P);
+  out[0] = 2 + (y.v[0] & 1u);
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w = x.v[7 - i];
+    out[1 + 4 * i] = (uint8_t)(w >> 24);
+    out[2 + 4 * i] = (uint8_t)(w >> 16);
+    out[3 + 4 * i] = (uint8_t)(w >> 8);
+    out[4 + 4 * i] = (uint8_t)w;
+  }
+}
+// returns false for an invalid encoding (reference: bytes_to_element -> None)
+MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
+  using namespace fp256;
+  const Modulus& P = C.P;
+  bool all_zero = true;
+  for (int i = 0; i < 33; ++i) all_zero = all_zero && in[i] == 0;
+  a.inf = 0;
+  a.x = fe_zero();
+  a.y = fe_zero();
+  if (all_zero) {
+    a.inf = 1;
+    return true;
+  }
+  if (in[0] != 2 && in[0] != 3) return false;
+  Fe x;
+  for (int i = 0; i < 8; ++i)
+    x.v[7 - i] = (uint32_t)in[1 + 4 * i] << 24 | (uint32_t)in[2 + 4 * i] << 16 | (uint32_t)in[3 + 4 * i] << 8 |
+                 in[4 + 4 * i];
+  // x < p
+  Fe t;
+  t.v[0] = simt::sub_cc(x.v[0], P.m[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(x.v[i], P.m[i]);
+  if (simt::subc(0, 0) == 0) return false;
+  Fe xm = to_mont(x, P);
+  Fe y2 = add(mul(sqr(xm, P), xm, P), load(C.b7), P);
+  Fe y = pow(y2, C.sqrt_e, P);
+  if (!eq(sqr(y, P), y2)) return false;
+  Fe yn = from_mont(y, P);
+  if ((yn.v[0] & 1u) != (uint32_t)(in[0] & 1)) y = neg(y, P);
+  a.x = xm;
+  a.y = y;
+  return true;
+}
+
+// ---- curve policy for ec_kernels.cuh ---------------------------------------------------------
+struct SecpCurve {
+  using Consts = secp::Consts;
+  using Point = Jac;
+  using Affine = Aff;
+  static constexpr int EB = 33;
+  MP_DEV static Point infinity(const Consts& C) { return jac_infinity(C.P); }
+  MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return jac_from_aff(a, C.P); }
+  MP_DEV static Point dbl(const Point& p, const Consts& C) { return jac_dbl(p, C.P); }
+  MP_DEV static Point add(const Point& p, const Point& q, const Consts& C) { return jac_add(p, q, C.P); }
+  MP_DEV static Point madd(const Point& p, const Affine& q, const Consts& C) { return jac_madd(p, q, C.P); }
+  MP_DEV static bool decode(Affine& a, const uint8_t* in, const Consts& C) { return secp::decode(a, in, C); }
+  MP_DEV static void encode(uint8_t* out, const Point& p, const Consts& C) {
+    secp::encode(out, jac_to_aff(p, C.P), C.P);
+  }
+};
+
+}  // namespace secp

@@ -17,6 +17,7 @@
 // ------------------------------------------------------------------ device ----
 #define MP_DEV __device__ __forceinline__
 #define MP_HOSTDEV __host__ __device__ __forceinline__
+#define MP_NOINLINE static __device__ __noinline__
 
 namespace simt {
 
@@ -92,6 +93,7 @@ MP_DEV void syncwarp() { __syncwarp(); }
 #include <cstring>
 #define MP_DEV inline
 #define MP_HOSTDEV inline
+#define MP_NOINLINE inline
 
 struct alignas(16) uint4 {
   uint32_t x, y, z, w;

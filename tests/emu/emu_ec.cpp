@@ -1,0 +1,90 @@
+// CPU execution of the elliptic-curve kernel bodies (tests only): thread-per-instance bodies are
+// simply called in a loop; simt.h's emulation back-end supplies the carry-chain primitives.
+#include "../../mpvss_rs_b200/csrc/secp.cuh"
+#include "../../mpvss_rs_b200/csrc/rist.cuh"
+#include "../../mpvss_rs_b200/csrc/ec_kernels.cuh"
+#include <vector>
+
+namespace {
+template <class Cv>
+int t_exp2(const void* consts, const uint8_t* b1, uint32_t b1s, const uint32_t* e1, uint32_t e1s, const uint8_t* b2,
+           uint32_t b2s, const uint32_t* e2, uint32_t e2s, uint32_t n, uint8_t* out, uint32_t* status) {
+  ec::Exp2Args<Cv> A{(const typename Cv::Consts*)consts, b1, e1, b2, e2, out, nullptr, status, n, b1s, e1s, b2s, e2s, 0};
+  for (uint32_t t = 0; t < n; ++t) ec::exp2_body<Cv>(A, t);
+  return 0;
+}
+template <class Cv>
+int t_add(const void* consts, const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* out, uint32_t* status) {
+  ec::AddArgs<Cv> A{(const typename Cv::Consts*)consts, a, b, out, status, n};
+  for (uint32_t t = 0; t < n; ++t) ec::add_body<Cv>(A, t);
+  return 0;
+}
+// chunked Horner end to end: decode commitments, K*n partials, per-position sum, encode
+template <class Cv>
+int t_poly_eval_exp(const void* consts, const uint8_t* commitments, uint32_t t, const uint32_t* pos, uint32_t n,
+                    uint32_t K, uint8_t* out, uint32_t* status) {
+  const typename Cv::Consts* C = (const typename Cv::Consts*)consts;
+  std::vector<uint32_t> cxy((size_t)t * 16), cst(t);
+  ec::DecodeArgs<Cv> D{C, commitments, cxy.data(), cst.data(), t};
+  for (uint32_t i = 0; i < t; ++i) ec::decode_body<Cv>(D, i);
+  for (uint32_t i = 0; i < t; ++i) status[i] = cst[i];
+  uint32_t B = (t + K - 1) / K;
+  K = (t + B - 1) / B;
+  std::vector<typename Cv::Point> part((size_t)K * n);
+  ec::HornerArgs<Cv> H{C, cxy.data(), cst.data(), pos, part.data(), t, n, K, B};
+  for (uint32_t i = 0; i < K * n; ++i) ec::horner_body<Cv>(H, i);
+  ec::SumArgs<Cv> S{C, part.data(), nullptr, out, n, K, 1, n, K * n};
+  for (uint32_t i = 0; i < n; ++i) ec::sum_body<Cv>(S, i);
+  return 0;
+}
+}  // namespace
+
+#define EXPORT_CURVE(prefix, Cv)                                                                                      \
+  extern "C" int emu_##prefix##_sizeof_consts() { return (int)sizeof(Cv::Consts); }                                   \
+  extern "C" int emu_##prefix##_exp2(const void* c, const uint8_t* b1, uint32_t b1s, const uint32_t* e1, uint32_t e1s, \
+                                     const uint8_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s, uint32_t n,   \
+                                     uint8_t* out, uint32_t* st) {                                                    \
+    return t_exp2<Cv>(c, b1, b1s, e1, e1s, b2, b2s, e2, e2s, n, out, st);                                             \
+  }                                                                                                                   \
+  extern "C" int emu_##prefix##_add(const void* c, const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* out,      \
+                                    uint32_t* st) {                                                                   \
+    return t_add<Cv>(c, a, b, n, out, st);                                                                            \
+  }                                                                                                                   \
+  extern "C" int emu_##prefix##_poly_eval_exp(const void* c, const uint8_t* cm, uint32_t t, const uint32_t* pos,      \
+                                              uint32_t n, uint32_t K, uint8_t* out, uint32_t* st) {                   \
+    return t_poly_eval_exp<Cv>(c, cm, t, pos, n, K, out, st);                                                         \
+  }
+
+EXPORT_CURVE(secp, secp::SecpCurve)
+EXPORT_CURVE(rist, rist::RistCurve)
+
+extern "C" {
+int emu_ec_poly(const void* modN, const uint32_t* coeffs, uint32_t t, const uint32_t* pos, uint32_t n, uint32_t* out) {
+  ec::PolyArgs A{(const fp256::Modulus*)modN, coeffs, pos, out, t, n};
+  for (uint32_t i = 0; i < n; ++i) ec::poly_body(A, i);
+  return 0;
+}
+int emu_ec_lagrange(const void* modN, const uint32_t* pos, uint32_t k, uint32_t* out) {
+  ec::LagrangeArgs A{(const fp256::Modulus*)modN, pos, out, k};
+  for (uint32_t i = 0; i < k; ++i) ec::lagrange_body(A, i);
+  return 0;
+}
+int emu_ec_inv(const void* modN, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* status) {
+  ec::InvArgs A{(const fp256::Modulus*)modN, in, out, status, n};
+  for (uint32_t i = 0; i < n; ++i) ec::inv_body(A, i);
+  return 0;
+}
+// field-level checks: out = a*b/R, a+b, a-b, a^-1 (mod the modulus in `mod`)
+int emu_fp_ops(const void* mod, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* mul, uint32_t* add,
+               uint32_t* sub, uint32_t* inv) {
+  const fp256::Modulus& M = *(const fp256::Modulus*)mod;
+  for (uint32_t i = 0; i < n; ++i) {
+    fp256::Fe x = fp256::load(a + 8 * i), y = fp256::load(b + 8 * i);
+    fp256::store(mul + 8 * i, fp256::mul(x, y, M));
+    fp256::store(add + 8 * i, fp256::add(x, y, M));
+    fp256::store(sub + 8 * i, fp256::sub(x, y, M));
+    fp256::store(inv + 8 * i, fp256::from_mont(fp256::inv(fp256::to_mont(x, M), M), M));
+  }
+  return 0;
+}
+}

@@ -1,0 +1,140 @@
+"""CPU execution of the elliptic-curve *kernel bodies* (fp256.cuh, secp.cuh, rist.cuh,
+ec_kernels.cuh -- the source nvcc compiles) through tests/emu, bit-exact against the oracle."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+import emu_util as eu
+from oracle import pvss
+from oracle.groups import ED_L, SECP_N, Ristretto255Group, Secp256k1Group
+
+U8 = lambda b: (ctypes.c_uint8 * len(b)).from_buffer_copy(b)
+
+
+@pytest.fixture(scope="module")
+def L():
+    return eu.build_ec()
+
+
+@pytest.mark.parametrize("m", [eu.SECP_P, eu.SECP_N, eu.ED_P, eu.ED_L])
+def test_fp256_field_ops(L, m):
+    rng = random.Random(m & 0xFFFF)
+    M = eu.modulus_words(m)
+    n = 64
+    A = [rng.randrange(m) for _ in range(n)]
+    B = [rng.randrange(m) for _ in range(n)]
+    A[:4] = [m - 1, 0, 1, m - 2]
+    B[:4] = [m - 1, 5, 1, m - 1]
+    a = np.concatenate([eu.to_limbs(x, 8) for x in A])
+    b = np.concatenate([eu.to_limbs(x, 8) for x in B])
+    o = [np.zeros(8 * n, dtype=np.uint32) for _ in range(4)]
+    L.emu_fp_ops(eu.P(M), eu.P(a), eu.P(b), n, eu.P(o[0]), eu.P(o[1]), eu.P(o[2]), eu.P(o[3]))
+    Ri = pow(1 << 256, -1, m)
+    for i in range(n):
+        assert eu.from_limbs(o[0][8 * i:8 * i + 8]) == A[i] * B[i] * Ri % m
+        assert eu.from_limbs(o[1][8 * i:8 * i + 8]) == (A[i] + B[i]) % m
+        assert eu.from_limbs(o[2][8 * i:8 * i + 8]) == (A[i] - B[i]) % m
+        assert eu.from_limbs(o[3][8 * i:8 * i + 8]) == (pow(A[i], -1, m) if A[i] else 0)
+
+
+CURVES = {
+    "secp": (Secp256k1Group, eu.secp_consts, SECP_N, 33),
+    "rist": (Ristretto255Group, eu.rist_consts, ED_L, 32),
+}
+
+
+@pytest.mark.parametrize("cv", ["secp", "rist"])
+def test_point_kernels(L, cv):
+    Gc, consts, order, EB = CURVES[cv]
+    G = Gc()
+    C = consts()
+    assert getattr(L, f"emu_{cv}_sizeof_consts")() == C.size * 4
+    exp2 = getattr(L, f"emu_{cv}_exp2")
+    rng = random.Random(11)
+    n = 7
+    pts = [G.exp(G.generator(), rng.randrange(1, order)) for _ in range(n)]
+    pts2 = [G.exp(G.generator(), rng.randrange(1, order)) for _ in range(n)]
+    e1 = [rng.randrange(order) for _ in range(n)]
+    e2 = [rng.randrange(order) for _ in range(n)]
+    e1[0], e2[1], e1[2], e2[2] = 0, 0, 1, order - 1
+    pts2[3], e2[3] = pts[3], order - e1[3]      # sums to the identity
+    pts2[4], e2[4] = pts[4], e1[4]              # equal addends (doubling inside add)
+    pts[5] = G.identity()                       # identity as a base
+    enc = lambda ps: U8(b"".join(G.element_to_bytes(p) for p in ps))
+    b1, b2 = enc(pts), enc(pts2)
+    E1 = np.concatenate([eu.to_limbs(x, 8) for x in e1])
+    E2 = np.concatenate([eu.to_limbs(x, 8) for x in e2])
+    out = (ctypes.c_uint8 * (EB * n))()
+    st = np.zeros(n, dtype=np.uint32)
+    exp2(eu.P(C), b1, EB, eu.P(E1), 8, b2, EB, eu.P(E2), 8, n, out, eu.P(st))
+    for i in range(n):
+        want = G.element_to_bytes(G.mul(G.exp(pts[i], e1[i]), G.exp(pts2[i], e2[i])))
+        assert bytes(out)[EB * i:EB * i + EB] == want, i
+    assert not st.any()
+    exp2(eu.P(C), b2, 0, eu.P(E1), 8, None, 0, None, 0, n, out, eu.P(st))   # one shared base
+    for i in range(n):
+        assert bytes(out)[EB * i:EB * i + EB] == G.element_to_bytes(G.exp(pts2[0], e1[i]))
+    bad = bytearray(bytes(b2))
+    bad[0] ^= 5                                                          # invalid prefix / odd s
+    bad[EB + 1:2 * EB] = b"\xff" * (EB - 1)                              # x >= p / s >= p
+    exp2(eu.P(C), U8(bytes(bad)), EB, eu.P(E1), 8, None, 0, None, 0, n, out, eu.P(st))
+    assert list(st[:3]) == [1, 1, 0]
+    getattr(L, f"emu_{cv}_add")(eu.P(C), b1, b2, n, out, eu.P(st))
+    for i in range(n):
+        assert bytes(out)[EB * i:EB * i + EB] == G.element_to_bytes(G.mul(pts[i], pts2[i]))
+
+
+@pytest.mark.parametrize("cv", ["secp", "rist"])
+@pytest.mark.parametrize("K", [1, 2, 7])
+def test_chunked_horner_equals_reference_schedule(L, cv, K):
+    Gc, consts, order, EB = CURVES[cv]
+    G = Gc()
+    C = consts()
+    rng = random.Random(K)
+    t = 7
+    comm = [G.exp(G.generator(), rng.randrange(1, order)) for _ in range(t)]
+    cb = U8(b"".join(G.element_to_bytes(p) for p in comm))
+    positions = [1, 2, 3, 4, 5, 17, 255, 4096, 65536]
+    pos = np.array(positions, dtype=np.uint32)
+    n = len(positions)
+    out = (ctypes.c_uint8 * (EB * n))()
+    st = np.zeros(t, dtype=np.uint32)
+    getattr(L, f"emu_{cv}_poly_eval_exp")(eu.P(C), cb, t, eu.P(pos), n, K, out, eu.P(st))
+    for i in range(n):
+        want = G.element_to_bytes(pvss.x_reference_schedule(G, comm, positions[i]))
+        assert bytes(out)[EB * i:EB * i + EB] == want, (K, i)
+
+
+@pytest.mark.parametrize("order", [SECP_N, ED_L])
+def test_scalar_kernels(L, order):
+    rng = random.Random(3)
+    MN = eu.modulus_words(order)
+    t = 9
+    positions = [1, 2, 3, 1000, 65536]
+    pos = np.array(positions, dtype=np.uint32)
+    n = len(positions)
+    co = [rng.randrange(order) for _ in range(t)]
+    o = np.zeros(8 * n, dtype=np.uint32)
+    L.emu_ec_poly(eu.P(MN), eu.P(np.concatenate([eu.to_limbs(x, 8) for x in co])), t, eu.P(pos), n, eu.P(o))
+    for i in range(n):
+        assert eu.from_limbs(o[8 * i:8 * i + 8]) == pvss.poly_get_value(co, positions[i]) % order
+    vals = [1, 3, 5, 6, 40]
+    k = len(vals)
+    o = np.zeros(8 * k, dtype=np.uint32)
+    L.emu_ec_lagrange(eu.P(MN), eu.P(np.array(vals, dtype=np.uint32)), k, eu.P(o))
+    for i, xi in enumerate(vals):
+        num = den = 1
+        for xj in vals:
+            if xj != xi:
+                num = num * xj % order
+                den = den * (xj - xi) % order
+        assert eu.from_limbs(o[8 * i:8 * i + 8]) == num * pow(den, -1, order) % order
+    xs = [rng.randrange(order) for _ in range(5)] + [0]
+    o = np.zeros(8 * 6, dtype=np.uint32)
+    st = np.zeros(6, dtype=np.uint32)
+    L.emu_ec_inv(eu.P(MN), eu.P(np.concatenate([eu.to_limbs(x, 8) for x in xs])), 6, eu.P(o), eu.P(st))
+    for i, x in enumerate(xs):
+        assert eu.from_limbs(o[8 * i:8 * i + 8]) == (pow(x, -1, order) if x else 0)
+    assert list(st) == [0, 0, 0, 0, 0, 1]
