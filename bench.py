@@ -29,7 +29,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "verified DLEQ shares/sec (MODP n=4096 t=2731, verify_distribution_shares)"
+METRICS = {"modp": "verified DLEQ shares/sec (MODP n=4096 t=2731, verify_distribution_shares)",
+           "secp256k1": "verified DLEQ shares/sec (secp256k1 n=4096 t=2731, verify_distribution_shares)",
+           "ristretto255": "verified DLEQ shares/sec (ristretto255 n=4096 t=2731, verify_distribution_shares)"}
+CPU_PROXY = {"modp": "OpenSSL BN_mod_exp_mont (proxy for num-bigint 0.2)",
+             "secp256k1": "OpenSSL EC_POINT_mul on secp256k1 (proxy for k256 0.13; OpenSSL has no specialised "
+                          "secp256k1 code, so this under-states k256)"}
+DTYPE = {"modp": "u32 limbs (2048-bit integers)", "secp256k1": "u32 limbs (256-bit prime fields)",
+         "ristretto255": "u32 limbs (255-bit prime field)"}
 SQR_MACS, MUL_MACS = 6240, 8256          # 2048-bit Montgomery sqr / mul, 32x32->64 MACs
 Q = None
 
@@ -91,24 +98,25 @@ class ClockSampler:
 # --------------------------------------------------------------- workload ----
 def build_box(group, n_total, t, seed):
     """Synthetic DistributionSharesBox made with the library's own dealer path.
-    Returns flat little-endian arrays in publickeys order."""
+    Returns flat boundary-encoded arrays in publickeys order."""
     from mpvss_rs_b200 import synth
     from mpvss_rs_b200.lib import buf, ptr
-    from mpvss_rs_b200.participant import RFC3526_2048 as q
     c = group.codec
-    sks = synth.private_keys(seed, n_total, "modp", q - 1, q)
-    coeffs = synth.coefficients(seed, t, q - 1)
-    ws = synth.witnesses(seed, n_total, q)
+    eb, sb = c.eb, c.sb
+    sks = synth.private_keys(seed, n_total, c.name, c.order, c.key_bound)
+    coeffs = synth.coefficients(seed, t, c.order)
+    ws = synth.witnesses(seed, n_total, c.key_bound)
     pks = group.fixed_base_exp(sks)
     pk_b = c.enc_elems(pks)
-    comm, shares = buf(size=t * 256), buf(size=n_total * 256)
-    chal, resp, u, x = buf(size=256), buf(size=n_total * 256), buf(size=256), buf(size=n_total * 256)
+    comm, shares = buf(size=t * eb), buf(size=n_total * eb)
+    chal, resp, u, x = buf(size=sb), buf(size=n_total * sb), buf(size=eb), buf(size=n_total * eb)
     secret = b"Hello MPVSS Example."
     group.ctx.check(group.ctx.lib.mpvss_distribute(
         group.ctx.h, n_total, t, ptr(buf(secret)), len(secret), ptr(buf(c.enc_scalars(coeffs))),
         ptr(buf(c.enc_scalars(ws))), ptr(buf(pk_b)), ptr(comm), ptr(shares), ptr(chal), ptr(resp), ptr(u), ptr(x)))
     return {"commitments": bytes(comm), "publickeys": pk_b, "shares": bytes(shares), "responses": bytes(resp),
-            "challenge": bytes(chal), "x_dealer": bytes(x), "n": n_total, "t": t}
+            "challenge": bytes(chal), "x_dealer": bytes(x), "n": n_total, "t": t, "eb": eb, "sb": sb,
+            "group": c.name}
 
 
 def horner_macs(n0, n, t):
@@ -154,23 +162,31 @@ def measure_imad_peak():
 
 # ------------------------------------------------------------ CPU baseline ----
 def cpu_reference_step(box, sample_idx, threads, schedule=0):
-    """One bounded sample of the workload on the host cores; returns seconds."""
+    """One bounded sample of the workload on the host cores; returns (seconds, X rows as boundary bytes)."""
     from oracle import cpu_baseline
-    from mpvss_rs_b200.participant import RFC3526_2048 as q
     lib = cpu_baseline.load()
-    be = lambda b: bytes(reversed(b))
     s = len(sample_idx)
-    t = box["t"]
-    comm = b"".join(be(box["commitments"][j * 256:(j + 1) * 256]) for j in range(t))
-    sel = lambda key: b"".join(be(box[key][i * 256:(i + 1) * 256]) for i in sample_idx)
-    xo, a1o, a2o = (ctypes.create_string_buffer(256 * s) for _ in range(3))
+    t, eb, sb = box["t"], box["eb"], box["sb"]
     pos = (ctypes.c_int64 * s)(*[i + 1 for i in sample_idx])
-    t0 = time.perf_counter()
-    lib.cpu_modp_verify(q.to_bytes(256, "big"), comm, t, pos, sel("publickeys"), sel("shares"), sel("responses"),
-                        be(box["challenge"]), s, threads, schedule, xo, a1o, a2o)
-    dt = time.perf_counter() - t0
-    xs = [xo.raw[i * 256:(i + 1) * 256] for i in range(s)]
-    return dt, xs
+    row = lambda key, w: [box[key][i * w:(i + 1) * w] for i in sample_idx]
+    xo, a1o, a2o = (ctypes.create_string_buffer(eb * s) for _ in range(3))
+    if box["group"] == "modp":
+        from mpvss_rs_b200.participant import RFC3526_2048 as q
+        be = lambda b: bytes(reversed(b))
+        comm = b"".join(be(box["commitments"][j * 256:(j + 1) * 256]) for j in range(t))
+        sel = lambda key: b"".join(be(r) for r in row(key, 256))
+        t0 = time.perf_counter()
+        lib.cpu_modp_verify(q.to_bytes(256, "big"), comm, t, pos, sel("publickeys"), sel("shares"), sel("responses"),
+                            be(box["challenge"]), s, threads, schedule, xo, a1o, a2o)
+        dt = time.perf_counter() - t0
+        return dt, [bytes(reversed(xo.raw[i * 256:(i + 1) * 256])) for i in range(s)]
+    if box["group"] == "secp256k1":
+        t0 = time.perf_counter()
+        lib.cpu_secp_verify(box["commitments"], t, pos, b"".join(row("publickeys", 33)), b"".join(row("shares", 33)),
+                            b"".join(row("responses", 32)), box["challenge"], s, threads, schedule, xo, a1o, a2o)
+        dt = time.perf_counter() - t0
+        return dt, [xo.raw[i * 33:(i + 1) * 33] for i in range(s)]
+    raise ValueError("no CPU baseline for " + box["group"])
 
 
 def spread_sample(n, s):
@@ -188,6 +204,8 @@ def main():
     ap.add_argument("--t", type=int, default=0, help="threshold (default ceil(2n/3))")
     ap.add_argument("--tpi", type=int, default=0, help="override lanes per 2048-bit value")
     ap.add_argument("--seed", type=int, default=0x6D70767373)
+    ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary secp256k1 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -209,13 +227,15 @@ def main():
 
     import mpvss_rs_b200 as m
     from mpvss_rs_b200.lib import buf, ptr
-    group = m.Group("modp", device=local)
-    if args.tpi:
+    METRIC = METRICS[args.group]
+    group = m.Group(args.group, device=local)
+    eb, sb = group.codec.eb, group.codec.sb
+    if args.tpi and args.group == "modp":
         group.ctx.set_int("modp_tpi", args.tpi)
     lib, h = group.ctx.lib, group.ctx.h
     box = build_box(group, n_total, t, args.seed)
-    config = {"workload": f"ModpGroup verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
-              "group": "modp-rfc3526-2048", "n_per_gpu": n, "n_total": n_total, "t": t,
+    config = {"workload": f"{args.group} verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
+              "group": args.group, "n_per_gpu": n, "n_total": n_total, "t": t,
               "x_schedule": "Horner in the exponent, fixed 2-bit windows (DESIGN.md)",
               "l2": "flushed between timed steps (256 MiB write)", "sharding": f"participants/{world}"}
 
@@ -229,19 +249,19 @@ def main():
         val = len(sample) / per
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "shares/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (2048-bit integers)",
+                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.group],
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "shares/s", "cores": cores, "kind": "port",
                                  "sample": f"{len(sample)} participants per step at positions spread over "
                                            f"1..{n_total}, full t={t}, reference schedule (t+4 exponentiations per "
-                                           "share, participant.rs:423-447) on OpenSSL BN_mod_exp_mont"},
+                                           "share, participant.rs:423-447) on " + CPU_PROXY[args.group]},
                 "e2e": {"value": val, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     # --------------------------------------------------------------- our arm ----
     lo, hi = rank * n, (rank + 1) * n
-    sl = lambda key: box[key][lo * 256:hi * 256]
+    sl = lambda key: box[key][lo * (sb if key == "responses" else eb):hi * (sb if key == "responses" else eb)]
     positions = (ctypes.c_int64 * n)(*range(lo + 1, hi + 1))
     pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
     host = {k: pin(v) for k, v in (("commitments", box["commitments"]), ("publickeys", sl("publickeys")),
@@ -250,10 +270,10 @@ def main():
     P = lambda tns: ctypes.cast(tns.data_ptr(), ctypes.POINTER(ctypes.c_uint8))
     ok = ctypes.c_int(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    out_local = torch.empty((3, n, 256), dtype=torch.uint8, device="cuda")
-    out_all = torch.empty((world, 3, n, 256), dtype=torch.uint8, device="cuda") if world > 1 else None
-    out_host = torch.empty((world, 3, n, 256), dtype=torch.uint8).pin_memory() if world > 1 else None
-    x_chk = buf(size=n * 256)
+    out_local = torch.empty((3, n, eb), dtype=torch.uint8, device="cuda")
+    out_all = torch.empty((world, 3, n, eb), dtype=torch.uint8, device="cuda") if world > 1 else None
+    out_host = torch.empty((world, 3, n, eb), dtype=torch.uint8).pin_memory() if world > 1 else None
+    x_chk = buf(size=n * eb)
 
     def stage():
         group.ctx.check(lib.mpvss_verify_distribution_stage(
@@ -302,7 +322,7 @@ def main():
     if world == 1 and bytes(x_chk) != sl("x_dealer"):
         raise SystemExit("verifier X_i differs from dealer X_i -- refusing to report a number")
 
-    imad_lo, imad_wide, peak_src = (measure_imad_peak() if rank == 0 else (0, 0, ""))
+    imad_lo, imad_wide, peak_src = (measure_imad_peak() if rank == 0 and args.group == "modp" else (0, 0, ""))
     for _ in range(args.warmup):
         run_resident()
     sampler = ClockSampler(local)
@@ -352,16 +372,13 @@ def main():
     ms = statistics.mean(step_s) * 1e3
     value = n_total / (ms * 1e-3)
     e2e_ms = statistics.mean(e2e_s) * 1e3
-    h2d = t * 256 + 3 * n * 256 + 256 + 8 * n
-    d2h = 3 * n * 256
-    hm = horner_macs(lo, n, t)
+    h2d = t * eb + 2 * n * eb + n * sb + sb + 8 * n
+    d2h = 3 * n * eb
     p0 = statistics.mean(p0_ms)
-    achieved = 2.0 * hm / (p0 * 1e-3) / 1e12            # TIMAD/s, 1 MAC = 2 IMAD issues
-    total_macs = hm + dleq_macs(n)
     line = {
         "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 limbs (2048-bit integers)", "data": "synthetic", "config": config,
+        "dtype": DTYPE[args.group], "data": "synthetic", "config": config,
         "timing": "per step: cuda-synchronize + barrier bracketed wall clock (kernels + D2H + host SHA-256), "
                   "max over ranks; kernel_ms / roofline from CUDA events on the library's stream",
         "kernel_ms_per_step": statistics.mean(kern_ms),
@@ -370,27 +387,48 @@ def main():
         "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "shares/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
-        "roofline": {"bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation)",
-                     "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
-                     "peak_source": peak_src + "; 32-bit IMAD issue rate, 1 MAC (32x32->64) = 2 IMAD",
-                     "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
-                     "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
-                     "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
-                     "share_of_step_macs": hm / total_macs, "traffic": None},
     }
-    if not args.no_cpu_baseline and world == 1:
+    if args.group == "modp":
+        hm = horner_macs(lo, n, t)
+        achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
+        total_macs = hm + dleq_macs(n)
+        line["roofline"] = {
+            "bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation)",
+            "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
+            "peak_source": peak_src + "; 32-bit IMAD issue rate, 1 MAC (32x32->64) = 2 IMAD",
+            "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
+            "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
+            "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
+            "share_of_step_macs": hm / total_macs, "traffic": None}
+    else:
+        line["roofline"] = None
+        line["phase_ms"] = {"x_horner": p0, "dleq": statistics.mean(kern_ms) - p0}
+    if not args.no_cpu_baseline and world == 1 and args.group in CPU_PROXY:
         sample = spread_sample(n_total, min(cores, n_total))
         dt, xs = cpu_reference_step(box, sample, cores)
         for i, x in zip(sample, xs):       # the CPU restatement and the GPU agree on X_i
-            assert bytes(reversed(x)) == bytes(x_chk)[i * 256:(i + 1) * 256], "CPU baseline X_i != GPU X_i"
+            assert x == bytes(x_chk)[i * eb:(i + 1) * eb], "CPU baseline X_i != GPU X_i"
         dt_h, _ = cpu_reference_step(box, sample, cores, schedule=1)
         line["cpu_baseline"] = {
             "value": len(sample) / dt, "unit": "shares/s", "cores": cores, "kind": "port",
             "sample": f"{len(sample)} participants (positions spread over 1..{n_total}), full t={t}, reference "
-                      "schedule (t+4 full exponentiations per share) on OpenSSL BN_mod_exp_mont, one participant "
-                      "per thread",
+                      "schedule (t+4 full exponentiations per share) on " + CPU_PROXY[args.group] +
+                      ", one participant per thread",
             "same_algorithm_value": len(sample) / dt_h,
             "same_algorithm_note": "CPU running the GPU's Horner schedule (baseline B, BASELINE.md section 3)"}
+    if args.group == "modp" and world == 1 and not args.no_also:
+        # the metric names MODP + secp256k1: the same step for Secp256k1Group, reported alongside
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", "secp256k1", "--steps",
+                                  str(args.steps), "--warmup", str(args.warmup), "--n", str(n), "--t", str(t)] +
+                                 (["--no-cpu-baseline"] if args.no_cpu_baseline else []),
+                                 capture_output=True, text=True, timeout=900)
+            sec = json.loads(out.stdout.strip().splitlines()[-1])
+            line["also"] = {"secp256k1": {k: sec.get(k) for k in ("metric", "value", "unit", "ms_per_step",
+                                                                 "kernel_ms_per_step", "e2e", "cpu_baseline",
+                                                                 "phase_ms", "gpu_launches")}}
+        except Exception as ex:  # the primary line stands on its own
+            line["also"] = {"secp256k1": {"error": str(ex)[:200]}}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -14,6 +14,8 @@
  * build:  gcc -O2 -shared -fPIC -pthread -o oracle/_build/libcpu_baseline.so oracle/cpu_baseline.c -lcrypto
  */
 #include <openssl/bn.h>
+#include <openssl/ec.h>
+#include <openssl/obj_mac.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -95,6 +97,100 @@ int cpu_modp_verify(const uint8_t* q, const uint8_t* commitments, size_t t, cons
     job_t j = {q, commitments, pk, y, r, c, positions, t, s, (size_t)k, (size_t)nthreads, schedule, x_out, a1_out, a2_out};
     jobs[k] = j;
     pthread_create(&th[k], NULL, worker, &jobs[k]);
+  }
+  for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+  free(th);
+  free(jobs);
+  return 0;
+}
+
+
+/* ---- secp256k1 (OpenSSL proxy for k256 0.13, Cargo.toml:24) -------------------------------
+ * schedule 0 (reference): X_i = sum_j (i^j mod n) * C_j, t variable-base scalar multiplications
+ * each converted back to affine like k256's `.into()` (src/groups/secp256k1.rs:99,106), then
+ * a1 = r*G + c*X, a2 = r*y + c*Y as four multiplications and two additions (src/dleq.rs:66-84).
+ * schedule 1: Horner in the group.  Points: 33-byte SEC1 compressed; scalars: 32-byte big-endian. */
+typedef struct {
+  const uint8_t *commitments, *pk, *y, *r, *c;
+  const int64_t* positions;
+  size_t t, s, first, stride;
+  int schedule;
+  uint8_t *x_out, *a1_out, *a2_out;
+} sjob_t;
+
+static void put_pt(const EC_GROUP* g, const EC_POINT* p, uint8_t* out, BN_CTX* ctx) {
+  if (EC_POINT_is_at_infinity(g, p)) { memset(out, 0, 33); return; }
+  EC_POINT_point2oct(g, p, POINT_CONVERSION_COMPRESSED, out, 33, ctx);
+}
+
+static void* sworker(void* arg) {
+  sjob_t* J = (sjob_t*)arg;
+  BN_CTX* ctx = BN_CTX_new();
+  EC_GROUP* g = EC_GROUP_new_by_curve_name(NID_secp256k1);
+  BIGNUM* n = BN_new();
+  EC_GROUP_get_order(g, n, ctx);
+  const EC_POINT* G = EC_GROUP_get0_generator(g);
+  EC_POINT** C = malloc(J->t * sizeof(EC_POINT*));
+  for (size_t j = 0; j < J->t; ++j) {
+    C[j] = EC_POINT_new(g);
+    EC_POINT_oct2point(g, C[j], J->commitments + j * 33, 33, ctx);
+  }
+  BIGNUM *e = BN_new(), *pos = BN_new(), *c = BN_bin2bn(J->c, 32, NULL);
+  EC_POINT *x = EC_POINT_new(g), *tmp = EC_POINT_new(g), *a = EC_POINT_new(g), *b = EC_POINT_new(g),
+           *pk = EC_POINT_new(g), *y = EC_POINT_new(g);
+  for (size_t i = J->first; i < J->s; i += J->stride) {
+    BN_set_word(pos, (BN_ULONG)J->positions[i]);
+    if (J->schedule == 0) {
+      EC_POINT_set_to_infinity(g, x);
+      BN_one(e);
+      for (size_t j = 0; j < J->t; ++j) { /* participant.rs:1411-1421 */
+        EC_POINT_mul(g, tmp, NULL, C[j], e, ctx);
+        EC_POINT_make_affine(g, tmp, ctx);
+        EC_POINT_add(g, x, x, tmp, ctx);
+        EC_POINT_make_affine(g, x, ctx);
+        BN_mod_mul(e, e, pos, n, ctx);
+      }
+    } else {
+      EC_POINT_copy(x, C[J->t - 1]);
+      for (size_t j = J->t - 1; j-- > 0;) {
+        EC_POINT_mul(g, x, NULL, x, pos, ctx);
+        EC_POINT_add(g, x, x, C[j], ctx);
+      }
+    }
+    put_pt(g, x, J->x_out + i * 33, ctx);
+    BIGNUM* r = BN_bin2bn(J->r + i * 32, 32, NULL);
+    EC_POINT_oct2point(g, pk, J->pk + i * 33, 33, ctx);
+    EC_POINT_oct2point(g, y, J->y + i * 33, 33, ctx);
+    EC_POINT_mul(g, a, NULL, G, r, ctx);
+    EC_POINT_mul(g, b, NULL, x, c, ctx);
+    EC_POINT_add(g, a, a, b, ctx);
+    put_pt(g, a, J->a1_out + i * 33, ctx);
+    EC_POINT_mul(g, a, NULL, pk, r, ctx);
+    EC_POINT_mul(g, b, NULL, y, c, ctx);
+    EC_POINT_add(g, a, a, b, ctx);
+    put_pt(g, a, J->a2_out + i * 33, ctx);
+    BN_free(r);
+  }
+  for (size_t j = 0; j < J->t; ++j) EC_POINT_free(C[j]);
+  free(C);
+  EC_POINT_free(x); EC_POINT_free(tmp); EC_POINT_free(a); EC_POINT_free(b); EC_POINT_free(pk); EC_POINT_free(y);
+  BN_free(e); BN_free(pos); BN_free(c); BN_free(n);
+  EC_GROUP_free(g);
+  BN_CTX_free(ctx);
+  return NULL;
+}
+
+int cpu_secp_verify(const uint8_t* commitments, size_t t, const int64_t* positions, const uint8_t* pk,
+                    const uint8_t* y, const uint8_t* r, const uint8_t* c, size_t s, int nthreads, int schedule,
+                    uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > s) nthreads = (int)s;
+  pthread_t* th = malloc(nthreads * sizeof(pthread_t));
+  sjob_t* jobs = malloc(nthreads * sizeof(sjob_t));
+  for (int k = 0; k < nthreads; ++k) {
+    sjob_t j = {commitments, pk, y, r, c, positions, t, s, (size_t)k, (size_t)nthreads, schedule, x_out, a1_out, a2_out};
+    jobs[k] = j;
+    pthread_create(&th[k], NULL, sworker, &jobs[k]);
   }
   for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
   free(th);

@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "_build", "libcpu_baseline.so")
 def build(force=False):
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     if force or not os.path.exists(SO) or os.path.getmtime(SRC) > os.path.getmtime(SO):
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", SO, SRC, "-lcrypto"])
+        subprocess.check_call(["gcc", "-O2", "-Wno-deprecated-declarations", "-shared", "-fPIC", "-pthread", "-o", SO, SRC, "-lcrypto"])
     return SO
 
 
@@ -22,6 +22,9 @@ def load():
     lib.cpu_modp_verify.argtypes = [p, p, sz, ctypes.POINTER(ctypes.c_int64), p, p, p, p, sz, ctypes.c_int,
                                     ctypes.c_int, p, p, p]
     lib.cpu_modp_verify.restype = ctypes.c_int
+    lib.cpu_secp_verify.argtypes = [p, sz, ctypes.POINTER(ctypes.c_int64), p, p, p, p, sz, ctypes.c_int, ctypes.c_int,
+                                    p, p, p]
+    lib.cpu_secp_verify.restype = ctypes.c_int
     return lib
 
 
@@ -38,4 +41,16 @@ def modp_verify(q, commitments, positions, pks, ys, rs, c, nthreads=1, schedule=
                         (ctypes.c_int64 * s)(*positions), b"".join(be(v) for v in pks), b"".join(be(v) for v in ys),
                         b"".join(be(v) for v in rs), be(c), s, nthreads, schedule, xo, a1o, a2o)
     dec = lambda b: [int.from_bytes(b.raw[i * 256:(i + 1) * 256], "big") for i in range(s)]
+    return dec(xo), dec(a1o), dec(a2o)
+
+
+def secp_verify(commitments, positions, pks, ys, rs, c, nthreads=1, schedule=0):
+    """Inputs: 33-byte SEC1 points, integer scalars.  Returns (X, a1, a2) lists of 33-byte encodings."""
+    lib = load()
+    s = len(positions)
+    xo, a1o, a2o = (ctypes.create_string_buffer(33 * s) for _ in range(3))
+    lib.cpu_secp_verify(b"".join(commitments), len(commitments), (ctypes.c_int64 * s)(*positions), b"".join(pks),
+                        b"".join(ys), b"".join(int(v).to_bytes(32, "big") for v in rs), int(c).to_bytes(32, "big"),
+                        s, nthreads, schedule, xo, a1o, a2o)
+    dec = lambda b: [b.raw[i * 33:(i + 1) * 33] for i in range(s)]
     return dec(xo), dec(a1o), dec(a2o)
