@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--tpi", type=int, default=0, help="override lanes per 2048-bit value")
     ap.add_argument("--seed", type=int, default=0x6D70767373)
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
+    ap.add_argument("--dual", type=int, default=-1, help="override modp_dual (0/1/2)")
+    ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0/1)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary secp256k1 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -232,6 +234,10 @@ def main():
     eb, sb = group.codec.eb, group.codec.sb
     if args.tpi and args.group == "modp":
         group.ctx.set_int("modp_tpi", args.tpi)
+    if args.overlap >= 0 and args.group == "modp":
+        group.ctx.set_int("modp_overlap", args.overlap)
+    if args.dual >= 0 and args.group == "modp":
+        group.ctx.set_int("modp_dual", args.dual)
     lib, h = group.ctx.lib, group.ctx.h
     box = build_box(group, n_total, t, args.seed)
     config = {"workload": f"{args.group} verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
@@ -275,20 +281,22 @@ def main():
     out_host = torch.empty((world, 3, n, eb), dtype=torch.uint8).pin_memory() if world > 1 else None
     x_chk = buf(size=n * eb)
 
+    PH = 2 if args.group == "modp" else 0   # phase index of the dominant (Horner) launch
+
     def stage():
         group.ctx.check(lib.mpvss_verify_distribution_stage(
             h, n, t, P(host["commitments"]), positions, P(host["publickeys"]), P(host["shares"]),
             P(host["responses"]), P(host["challenge"])))
 
     def run_resident(want_x=False):
-        """one step with the box resident in HBM; returns (ok, kernel_ms, phase0_ms)"""
+        """one step with the box resident in HBM; returns (ok, kernel_ms, Horner-launch ms)"""
         if world == 1:
             group.ctx.check(lib.mpvss_verify_distribution_run(h, ctypes.byref(ok), ptr(x_chk) if want_x else None,
                                                               None, None, None))
-            return ok.value, group.ctx.last_kernel_ms, group.ctx.last_phase_ms(0)
+            return ok.value, group.ctx.last_kernel_ms, group.ctx.last_phase_ms(PH)
         group.ctx.check(lib.mpvss_verify_distribution_compute(
             h, out_local[0].data_ptr(), out_local[1].data_ptr(), out_local[2].data_ptr()))
-        kms, p0 = group.ctx.last_kernel_ms, group.ctx.last_phase_ms(0)
+        kms, p0 = group.ctx.last_kernel_ms, group.ctx.last_phase_ms(PH)
         dist.all_gather_into_tensor(out_all, out_local)          # one NCCL all-gather per phase
         res = 1
         if rank == 0:
@@ -391,7 +399,10 @@ def main():
     if args.group == "modp":
         hm = horner_macs(lo, n, t)
         achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
-        total_macs = hm + dleq_macs(n)
+        dual = (args.dual != 0) and t >= 8   # library default: two half-length chunks
+        combine = n * (4 * 511 * SQR_MACS + (15 + 511 + 15 + 2) * MUL_MACS) if dual else 0
+        total_macs = hm + combine + dleq_macs(n)
+        step_timad = 2.0 * total_macs / (statistics.mean(kern_ms) * 1e-3) / 1e12
         line["roofline"] = {
             "bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation)",
             "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
@@ -399,7 +410,13 @@ def main():
             "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
             "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
             "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
-            "share_of_step_macs": hm / total_macs, "traffic": None}
+            "share_of_step_macs": hm / total_macs, "traffic": 976640,
+            "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full, profiles/horner_r01_ncu.txt",
+            "note": "the a2 = y^r Y^c launch runs on a side stream underneath this kernel; its time share is not "
+                    "subtracted, so frac is a lower bound for the kernel alone",
+            "whole_step": {"achieved": step_timad, "frac": step_timad / imad_lo if imad_lo else None,
+                           "algorithmic_macs": total_macs, "kernel_ms": statistics.mean(kern_ms),
+                           "what": "all kernels of the step (Horner + chunk combination + both DLEQ launches)"}}
     else:
         line["roofline"] = None
         line["phase_ms"] = {"x_horner": p0, "dleq": statistics.mean(kern_ms) - p0}

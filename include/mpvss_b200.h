@@ -57,7 +57,8 @@ enum mpvss_generator {
 int mpvss_ctx_create(int group, int device, mpvss_ctx** out);
 void mpvss_ctx_destroy(mpvss_ctx* ctx);
 const char* mpvss_last_error(const mpvss_ctx* ctx);
-/* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16) */
+/* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16); "modp_dual" (0/1: evaluate the
+ * commitment polynomial as two half-length chunks side by side on every lane group) */
 int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value);
 size_t mpvss_element_bytes(const mpvss_ctx* ctx);
 size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);
@@ -66,7 +67,8 @@ size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);
 float mpvss_last_kernel_ms(const mpvss_ctx* ctx);
 int mpvss_last_kernel_launches(const mpvss_ctx* ctx);
 /* kernel time (ms) of one phase of the last fused call.  verify_distribution: phase 0 = X_i
- * (Montgomery conversion + Horner multi-exponentiation), phase 1 = DLEQ commitments. */
+ * (Montgomery conversion + Horner multi-exponentiation [+ chunk combination]; a2 runs underneath on
+ * a side stream), phase 1 = remaining DLEQ commitments, phase 2 = the Horner launch alone (MODP). */
 float mpvss_last_phase_ms(const mpvss_ctx* ctx, int phase);
 
 /* ---- batch forms of `trait Group` methods ------------------------------------ */

@@ -74,7 +74,8 @@ int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev_mid) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_mid) != cudaSuccess || cudaEventCreate(&ctx->ev_h0) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_h1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess)
     return bail(MPVSS_ERR_CUDA);
   for (int a = 0; a < 2; ++a)
@@ -98,7 +99,7 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx) {
   ctx->ec_consts.release();
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
-  for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_mid, ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1]})
+  for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_mid, ctx->ev_h0, ctx->ev_h1, ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1]})
     if (e) cudaEventDestroy(e);
   for (int a = 0; a < 2; ++a)
     if (ctx->aux[a]) cudaStreamDestroy(ctx->aux[a]);
@@ -114,6 +115,14 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
   if (std::string(key) == "modp_tpi") {
     if (value != 4 && value != 8 && value != 16) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_tpi must be 4, 8 or 16");
     ctx->modp_tpi = value;
+    return MPVSS_OK;
+  }
+  if (std::string(key) == "modp_overlap") {
+    ctx->modp_overlap = value != 0;
+    return MPVSS_OK;
+  }
+  if (std::string(key) == "modp_dual") {
+    ctx->modp_dual = value;  // 0: one chain, 1: two interleaved chains per lane group, 2: two launches
     return MPVSS_OK;
   }
   return mpvss_fail(ctx, MPVSS_ERR_ARG, std::string("unknown tunable: ") + key);

@@ -55,7 +55,7 @@ struct mpvss_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t aux[2] = {nullptr, nullptr};  // side streams for concurrent launches
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_h0 = nullptr, ev_h1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   float phase_ms[4] = {0, 0, 0, 0};  // per-phase kernel time of the last fused call
   std::mutex mu;
   std::string err;
@@ -65,6 +65,8 @@ struct mpvss_ctx {
 
   // ---- ModpGroup ----
   int modp_tpi = 8;
+  int modp_overlap = 0;  // run the X-independent a2 launch on a side stream underneath the Horner kernel
+  int modp_dual = 2;  // two-chunk Horner: 0 off, 1 two interleaved chains per lane group, 2 two concurrent launches
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
@@ -79,6 +81,8 @@ struct mpvss_ctx {
   uint32_t v_rwin = 0, v_cwin = 0;
   size_t v_np = 0;  // padded instance count of the Horner launch
   std::vector<uint8_t> v_challenge, v_y_host;
+  bool v_dual = false;
+  DevBuf v_e, v_h;  // chunk exponents pos^B mod (q-1); H0/H1 of the two-chunk Horner
   DevBuf v_slot, v_nd, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
 
   // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call

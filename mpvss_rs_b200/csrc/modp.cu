@@ -5,13 +5,20 @@
 
 namespace modp {
 
-constexpr int WARPS_PER_CTA = 4;
 
 template <int TPI>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
+__global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
-  horner_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>);
+  horner_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>,
+                   A.nd ? A.nd[blockIdx.x] : A.ndigits);
+}
+
+template <int TPI>
+__global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner2_kernel(Horner2Args A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t w = threadIdx.x >> 5;
+  horner2_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner2_smem_words<TPI>, A.nd[blockIdx.x]);
 }
 
 template <int TPI>
@@ -50,10 +57,23 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 cudaError_t launch_horner(int tpi, const HornerArgs& A, cudaStream_t s) {
   if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
   MODP_DISPATCH(tpi, {
-    size_t sm = WARPS_PER_CTA * horner_smem_words<T> * 4;
+    size_t sm = HORNER_WARPS_PER_CTA * horner_smem_words<T> * 4;
     cudaError_t e = set_smem(horner_kernel<T>, sm);
     if (e != cudaSuccess) return e;
-    horner_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+    uint32_t per_cta = HORNER_WARPS_PER_CTA * (32 / T);
+    horner_kernel<T><<<(A.n + per_cta - 1) / per_cta, HORNER_WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s) {
+  if (A.n == 0 || A.t < 4 || A.B < 2) return cudaErrorInvalidValue;
+  MODP_DISPATCH(tpi, {
+    size_t sm = HORNER_WARPS_PER_CTA * horner2_smem_words<T> * 4;
+    cudaError_t e = set_smem(horner2_kernel<T>, sm);
+    if (e != cudaSuccess) return e;
+    uint32_t per_cta = HORNER_WARPS_PER_CTA * (32 / T);
+    horner2_kernel<T><<<(A.n + per_cta - 1) / per_cta, HORNER_WARPS_PER_CTA * 32, sm, s>>>(A);
   });
   return cudaGetLastError();
 }

@@ -114,9 +114,9 @@ int sync(mpvss_ctx* ctx) {
 // device-pointer exponentiation:  out = b1^e1 [* b2^e2]
 int dev_exp2(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s,
-             uint32_t e2w, size_t n, uint32_t* out) {
+             uint32_t e2w, size_t n, uint32_t* out, cudaStream_t stream = nullptr) {
   modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w};
-  MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, ctx->stream));
+  MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, stream ? stream : ctx->stream));
   timing_launch(ctx);
   return MPVSS_OK;
 }
@@ -198,16 +198,17 @@ int init(mpvss_ctx* ctx) {
   MPVSS_TRY(h2d(ctx, ctx->consts_q, blk.data(), blk.size() * 4));
   fill_consts(ctx->g, blk.data());
   MPVSS_TRY(h2d(ctx, ctx->consts_g, blk.data(), blk.size() * 4));
-  std::vector<uint32_t> gens(128, 0);
-  gens[0] = 2;   // Group::generator()           modp.rs:64
-  gens[64] = 4;  // Group::subgroup_generator()  modp.rs:65-66
+  std::vector<uint32_t> gens(192, 0);
+  gens[0] = 2;    // Group::generator()           modp.rs:64
+  gens[64] = 4;   // Group::subgroup_generator()  modp.rs:65-66
+  gens[128] = 1;  // the scalar / element 1
   MPVSS_TRY(h2d(ctx, ctx->gens, gens.data(), gens.size() * 4));
   return sync(ctx);
 }
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_e, &ctx->v_h})
     b->release();
 }
 
@@ -257,11 +258,12 @@ int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint
 }
 
 // Positions are sorted by their number of base-4 digits (longest first) and every digit class
-// is padded to a whole number of warps, so all groups of a warp run the same fixed-window
+// is padded to a whole number of CTAs, so all groups of a CTA run the same fixed-window
 // schedule while one launch covers every class (a single large position no longer lengthens
-// everybody's schedule, and the long chains start first).
+// everybody's schedule, and the long chains start first).  The digit count is stored per CTA.
 struct PosPlan {
-  std::vector<uint32_t> pos, slot, nd;  // padded instance arrays; slot 0xffffffff = padding
+  std::vector<uint32_t> pos, slot;  // padded instance arrays; slot 0xffffffff = padding
+  std::vector<uint32_t> nd;         // base-4 digits per CTA
 };
 static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
   std::vector<std::vector<uint32_t>> by(17);
@@ -270,20 +272,19 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
     if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
     by[ndigits_for((uint64_t)p)].push_back((uint32_t)i);
   }
-  const size_t gpw = 32 / ctx->modp_tpi;
+  const size_t per_cta = modp::HORNER_WARPS_PER_CTA * (32 / ctx->modp_tpi);
   plan.pos.clear(); plan.slot.clear(); plan.nd.clear();
   for (uint32_t d = 16; d >= 1; --d) {
     if (by[d].empty()) continue;
     for (uint32_t i : by[d]) {
       plan.slot.push_back(i);
       plan.pos.push_back((uint32_t)(positions ? positions[i] : (int64_t)i + 1));
-      plan.nd.push_back(d);
     }
-    while (plan.pos.size() % gpw) {
+    while (plan.pos.size() % per_cta) {
       plan.slot.push_back(0xffffffffu);
       plan.pos.push_back(plan.pos.back());
-      plan.nd.push_back(d);
     }
+    plan.nd.resize(plan.pos.size() / per_cta, d);
   }
   return MPVSS_OK;
 }
@@ -295,9 +296,70 @@ static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
   modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, x, (uint32_t)t,
                      (uint32_t)n_padded, 0};
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
   MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
   timing_launch(ctx);
   return MPVSS_OK;
+}
+
+// e_i = pos_i^B mod (q-1) for the two-chunk Horner: q-1 = 2g, so by CRT e_i is the representative
+// of pos_i^B mod g (device modexp with the constants of modulus g) that has the parity of pos_i.
+static int dev_chunk_exponents(mpvss_ctx* ctx, const int64_t* positions, size_t n, uint32_t B, DevBuf& e_out) {
+  std::vector<uint8_t> base(n * EB, 0), bexp(EB, 0), e(n * EB);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t p = (uint32_t)(positions ? positions[i] : (int64_t)i + 1);
+    memcpy(base.data() + i * EB, &p, 4);
+  }
+  memcpy(bexp.data(), &B, 4);
+  DevBuf &db = ctx->buf(20), &dx = ctx->buf(21);
+  MPVSS_TRY(h2d(ctx, db, base.data(), n * EB));
+  MPVSS_TRY(h2d(ctx, dx, bexp.data(), EB));
+  MPVSS_CUDA(ctx, e_out.ensure(n * EB));
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_g.as<uint32_t>(), db.as<uint32_t>(), EW, dx.as<uint32_t>(), 0,
+                     windows_for(bexp.data(), EB, 1), nullptr, 0, nullptr, 0, 0, n, e_out.as<uint32_t>()));
+  MPVSS_TRY(d2h(ctx, e.data(), e_out, n * EB));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < n; ++i) {
+    if ((e[i * EB] & 1u) != (base[i * EB] & 1u)) {
+      big::Int v = big::add(big::from_le(e.data() + i * EB, EB), ctx->g);
+      big::to_le(v, e.data() + i * EB, EB);
+    }
+  }
+  return h2d(ctx, e_out, e.data(), n * EB);
+}
+
+// Two-chunk form of dev_horner: H0, H1 side by side on every lane group, then
+// X = H0 * H1^(pos^B mod (q-1)) with the exponentiation kernel.
+static int dev_horner2(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
+                       const uint32_t* slot, const uint32_t* nd, size_t n_padded, size_t n, const uint32_t* e,
+                       DevBuf& h, uint32_t* x) {
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  MPVSS_CUDA(ctx, cm.ensure(t * EB));
+  MPVSS_CUDA(ctx, h.ensure(2 * n * EB));
+  MPVSS_TRY(dev_mul(ctx, K, comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
+  uint32_t* h0 = h.as<uint32_t>();
+  uint32_t* h1 = h0 + n * EW;
+  const uint32_t B = (uint32_t)((t + 1) / 2);
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
+  if (ctx->modp_dual == 2) {
+    // the two halves as two concurrent launches of the single-chain kernel (twice the warps)
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0));
+    modp::HornerArgs A0{K, cm.as<uint32_t>(), pos, slot, nd, h0, B, (uint32_t)n_padded, 0};
+    modp::HornerArgs A1{K, cm.as<uint32_t>() + (size_t)B * EW, pos, slot, nd, h1, (uint32_t)t - B, (uint32_t)n_padded, 0};
+    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A0, ctx->stream));
+    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A1, ctx->aux[1]));
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
+    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
+    timing_launch(ctx);
+  } else {
+    modp::Horner2Args A{K, cm.as<uint32_t>(), pos, slot, nd, h0, h1, (uint32_t)t, (uint32_t)n_padded, B};
+    MPVSS_CUDA(ctx, modp::launch_horner2(ctx->modp_tpi, A, ctx->stream));
+  }
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
+  timing_launch(ctx);
+  return dev_exp2(ctx, K, h1, EW, e, EW, 512, h0, EW, ctx->gens.as<uint32_t>() + 128, 0, 1, n, x);
 }
 
 int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
@@ -311,11 +373,17 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
   MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
   MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), np * 4));
   MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), np * 4));
-  MPVSS_TRY(h2d(ctx, dnd, plan.nd.data(), np * 4));
+  MPVSS_TRY(h2d(ctx, dnd, plan.nd.data(), plan.nd.size() * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  const bool dual = ctx->modp_dual && t >= 8;
+  if (dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->buf(6)));
   timing_begin(ctx);
-  MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(), np,
-                       dout.as<uint32_t>()));
+  if (dual)
+    MPVSS_TRY(dev_horner2(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
+                          np, n, ctx->buf(6).as<uint32_t>(), ctx->buf(7), dout.as<uint32_t>()));
+  else
+    MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
+                         np, dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
@@ -413,7 +481,7 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), ctx->v_np * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nd.data(), ctx->v_np * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nd.data(), plan.nd.size() * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
@@ -421,6 +489,8 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   MPVSS_CUDA(ctx, ctx->v_x.ensure(n * EB));
   MPVSS_CUDA(ctx, ctx->v_a1.ensure(n * EB));
   MPVSS_CUDA(ctx, ctx->v_a2.ensure(n * EB));
+  ctx->v_dual = ctx->modp_dual && t >= 8;
+  if (ctx->v_dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->v_e));
   ctx->v_rwin = windows_for(responses, EB, n);
   ctx->v_cwin = windows_for(challenge, EB, 1);
   ctx->v_challenge.assign(challenge, challenge + EB);
@@ -436,19 +506,32 @@ static int verify_kernels(mpvss_ctx* ctx) {
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   uint32_t* X = ctx->v_x.as<uint32_t>();
   timing_begin(ctx);
-  // X_i from the commitments (participant.rs:423-434)
-  MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                       ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
-  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-  // dleq.rs:66-84
-  MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
-                     ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>()));
+  // a2 = y^r * Y^c does not depend on X: it runs on a side stream underneath the Horner kernel,
+  // whose lanes leave issue slots free (dleq.rs:66-84)
+  cudaStream_t side = ctx->modp_overlap ? ctx->aux[0] : ctx->stream;
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
   MPVSS_TRY(dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
                      ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
-                     ctx->v_a2.as<uint32_t>()));
+                     ctx->v_a2.as<uint32_t>(), side));
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+  // X_i from the commitments (participant.rs:423-434)
+  if (ctx->v_dual)
+    MPVSS_TRY(dev_horner2(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
+                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, n,
+                          ctx->v_e.as<uint32_t>(), ctx->v_h, X));
+  else
+    MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
+                         ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
+  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
+  // a1 = g^r * X^c
+  MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
+                     ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>()));
+  MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
   MPVSS_TRY(timing_end(ctx));
-  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // to-Montgomery + Horner
-  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));  // DLEQ commitments
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // X_i (with a2 underneath)
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));  // remaining DLEQ work
+  MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[2], ctx->ev_h0, ctx->ev_h1));  // the Horner launch alone
   return MPVSS_OK;
 }
 

@@ -163,6 +163,37 @@ MP_DEV void mm_digit(uint32_t (&P)[Cfg<TPI>::L + 2], uint32_t (&S)[Cfg<TPI>::L +
   in = (ln.k == TPI - 1) ? 0u : out;
 }
 
+// Fold the two accumulators of a finished digit loop (last call had P = A1, S = A0), hand the
+// window overflows to the next lane, resolve carries and apply the conditional subtraction.
+template <int TPI>
+MP_DEV void mm_finish(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&A0)[Cfg<TPI>::L + 2],
+                      const uint32_t (&A1)[Cfg<TPI>::L + 2], uint32_t in, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  // value = S + (P >> 32) + in * 2^(32(L-1))
+  r[0] = simt::add_cc(A0[0], A1[1]);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(A0[i], A1[i + 1]);
+  uint32_t ov = simt::addc(A0[L], A1[L + 1]);
+  r[L - 1] = simt::add_cc(r[L - 1], in);
+  ov = simt::addc(ov, 0);
+  // hand the (<= 2 bit) overflow of each window to the next lane, resolve carries
+  uint32_t ovin = simt::shfl(ov, (int)simt::lane_id() - 1);
+  uint32_t ovtop = simt::shfl(ov, ln.lane0 + TPI - 1);
+  if (ln.k == 0) ovin = 0;
+  r[0] = simt::add_cc(r[0], ovin);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
+  uint32_t c = simt::addc(0, 0);
+  uint32_t cout;
+  uint32_t cin = resolve<TPI>(ln, c != 0, all_ones<L>(r), &cout);
+  r[0] = simt::add_cc(r[0], cin);
+#pragma unroll
+  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
+  // value >= 2^2048  ->  subtract q once (add 2^2048 - q, drop the carry)
+  uint32_t over = ovtop + cout;
+  (void)add_resolve<TPI>(r, M.nq, 0u - over, ln);
+}
+
 // r = a * b * 2^-2048 mod q, result in [0, 2^2048).  `bs` points at the 64 limbs of
 // b (shared memory, visible to the whole group).  r may alias a.
 template <int TPI>
@@ -187,29 +218,46 @@ MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L
     mm_digit<TPI, false>(A0, A1, a, bw.z, M, ln, in);
     mm_digit<TPI, false>(A1, A0, a, bw.w, M, ln, in);
   }
-  // last call had P = A1, S = A0:  value = S + (P >> 32) + in * 2^(32(L-1))
-  r[0] = simt::add_cc(A0[0], A1[1]);
-#pragma unroll
-  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(A0[i], A1[i + 1]);
-  uint32_t ov = simt::addc(A0[L], A1[L + 1]);
-  r[L - 1] = simt::add_cc(r[L - 1], in);
-  ov = simt::addc(ov, 0);
-  // hand the (<= 2 bit) overflow of each window to the next lane, resolve carries
-  uint32_t ovin = simt::shfl(ov, (int)simt::lane_id() - 1);
-  uint32_t ovtop = simt::shfl(ov, ln.lane0 + TPI - 1);
-  if (ln.k == 0) ovin = 0;
-  r[0] = simt::add_cc(r[0], ovin);
-#pragma unroll
-  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
-  uint32_t c = simt::addc(0, 0);
-  uint32_t cout;
-  uint32_t cin = resolve<TPI>(ln, c != 0, all_ones<L>(r), &cout);
-  r[0] = simt::add_cc(r[0], cin);
-#pragma unroll
-  for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
-  // value >= 2^2048  ->  subtract q once (add 2^2048 - q, drop the carry)
-  uint32_t over = ovtop + cout;
-  (void)add_resolve<TPI>(r, M.nq, 0u - over, ln);
+  mm_finish<TPI>(r, A0, A1, in, M, ln);
+}
+
+// Two independent Montgomery products on the same lane group, digit loops interleaved so that
+// each lane always has two dependency chains in flight (the carry chains of one product hide
+// the fixed latencies and shuffle round trips of the other).
+template <int TPI>
+MP_DEV void mont_mul2(uint32_t (&r0)[Cfg<TPI>::L], const uint32_t (&a0)[Cfg<TPI>::L], const uint32_t* b0s,
+                      uint32_t (&r1)[Cfg<TPI>::L], const uint32_t (&a1)[Cfg<TPI>::L], const uint32_t* b1s,
+                      const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t A0[L + 2], A1[L + 2], B0[L + 2], B1[L + 2];
+  uint32_t in0 = 0, in1 = 0;
+  const uint4* p0 = reinterpret_cast<const uint4*>(b0s);
+  const uint4* p1 = reinterpret_cast<const uint4*>(b1s);
+  {
+    uint4 u = p0[0], v = p1[0];
+    mm_digit<TPI, true>(A0, A1, a0, u.x, M, ln, in0);
+    mm_digit<TPI, true>(B0, B1, a1, v.x, M, ln, in1);
+    mm_digit<TPI, false>(A1, A0, a0, u.y, M, ln, in0);
+    mm_digit<TPI, false>(B1, B0, a1, v.y, M, ln, in1);
+    mm_digit<TPI, false>(A0, A1, a0, u.z, M, ln, in0);
+    mm_digit<TPI, false>(B0, B1, a1, v.z, M, ln, in1);
+    mm_digit<TPI, false>(A1, A0, a0, u.w, M, ln, in0);
+    mm_digit<TPI, false>(B1, B0, a1, v.w, M, ln, in1);
+  }
+#pragma unroll 1
+  for (int j = 1; j < 16; ++j) {
+    uint4 u = p0[j], v = p1[j];
+    mm_digit<TPI, false>(A0, A1, a0, u.x, M, ln, in0);
+    mm_digit<TPI, false>(B0, B1, a1, v.x, M, ln, in1);
+    mm_digit<TPI, false>(A1, A0, a0, u.y, M, ln, in0);
+    mm_digit<TPI, false>(B1, B0, a1, v.y, M, ln, in1);
+    mm_digit<TPI, false>(A0, A1, a0, u.z, M, ln, in0);
+    mm_digit<TPI, false>(B0, B1, a1, v.z, M, ln, in1);
+    mm_digit<TPI, false>(A1, A0, a0, u.w, M, ln, in0);
+    mm_digit<TPI, false>(B1, B0, a1, v.w, M, ln, in1);
+  }
+  mm_finish<TPI>(r0, A0, A1, in0, M, ln);
+  mm_finish<TPI>(r1, B0, B1, in1, M, ln);
 }
 
 // Bring a value of [0, 2^2048) into [0, q): canonical representative.

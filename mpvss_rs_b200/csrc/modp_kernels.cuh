@@ -62,8 +62,9 @@ struct HornerArgs {
   const uint32_t* cm;      // t commitments, Montgomery form, 64 limbs each
   const uint32_t* pos;     // n positions (1-based)
   const uint32_t* slot;    // n output slots (nullptr: instance i writes slot i; 0xffffffff: padding)
-  const uint32_t* nd;      // n base-4 digit counts; all instances of one warp carry the same value
-                           // (nullptr: `ndigits` for every instance)
+  const uint32_t* nd;      // base-4 digit count per CTA (all instances of a CTA share it; the launcher
+                           // passes nd[blockIdx.x] so that the schedule is provably block-uniform and
+                           // ptxas needs no WARPSYNC around the shuffles); nullptr: `ndigits` everywhere
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
   uint32_t t, n, ndigits;
 };
@@ -74,7 +75,7 @@ constexpr int horner_smem_words = 128 + (32 / TPI) * 256;
 // X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
 // integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
 template <int TPI>
-MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
+MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
   Lane ln = make_lane<TPI>();
@@ -90,8 +91,6 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
   uint32_t* sq = tbl + 192;
   warp_copy64(one, A.consts + C_ONE);
   const uint32_t pos = A.pos[inst];
-  const uint32_t w0 = wg * GPW;
-  const uint32_t ndigits = A.nd ? A.nd[w0 < A.n ? w0 : A.n - 1] : A.ndigits;  // warp-uniform schedule
   uint32_t acc[L];
   load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
   simt::syncwarp();
@@ -120,6 +119,89 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm) {
   const uint32_t slot = A.slot ? A.slot[inst] : inst;
   finish_store<TPI>(acc, sq, A.out + (size_t)(slot == 0xffffffffu ? 0 : slot) * 64, live && slot != 0xffffffffu, M,
                     ln);
+}
+
+// -------------------------------------------------------- Horner, two chunks ----
+// Same computation with the polynomial cut in two halves of B coefficients: every lane group
+// evaluates both halves of ONE position side by side (mont_mul2), which doubles the
+// independent work per lane without changing the schedule (both halves share the position's
+// digits).  Outputs H0 = prod_{j<B} C_j^(i^j) and H1 = prod_{j>=B} C_j^(i^(j-B)); the caller
+// finishes X_i = H0 * H1^(i^B mod (q-1)) with the exponentiation kernel.
+struct Horner2Args {
+  const uint32_t* consts;
+  const uint32_t* cm;      // t commitments, Montgomery form
+  const uint32_t* pos;
+  const uint32_t* slot;
+  const uint32_t* nd;      // per CTA, as in HornerArgs
+  uint32_t* out0;          // H0, canonical, indexed by slot
+  uint32_t* out1;          // H1
+  uint32_t t, n, B;        // B = ceil(t / 2) >= 2
+};
+
+template <int TPI>
+constexpr int horner2_smem_words = 192 + (32 / TPI) * 512;
+
+template <int TPI>
+MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t inst = wg * GPW + gi;
+  const bool live = inst < A.n;
+  if (!live) inst = A.n - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* cbuf0 = wsm;
+  uint32_t* cbuf1 = wsm + 64;
+  uint32_t* one = wsm + 128;
+  uint32_t* t0 = wsm + 192 + gi * 512;  // X, X^2, X^3, squaring stage of the low half
+  uint32_t* t1 = t0 + 256;              // same for the high half
+  uint32_t* sq0 = t0 + 192;
+  uint32_t* sq1 = t1 + 192;
+  warp_copy64(one, A.consts + C_ONE);
+  const uint32_t pos = A.pos[inst];
+  const uint32_t B = A.B, t = A.t;
+  uint32_t acc0[L], acc1[L];
+  load_slice<TPI>(acc0, A.cm + (size_t)(B - 1) * 64, ln);
+  load_slice<TPI>(acc1, (2 * B - 1 < t) ? A.cm + (size_t)(2 * B - 1) * 64 : A.consts + C_ONE, ln);
+  simt::syncwarp();
+  for (int j = (int)B - 2; j >= 0; --j) {
+    warp_copy64(cbuf0, A.cm + (size_t)j * 64);
+    warp_copy64(cbuf1, (B + j < t) ? A.cm + (size_t)(B + j) * 64 : A.consts + C_ONE);
+    stage<TPI>(t0, acc0, ln);
+    stage<TPI>(t1, acc1, ln);
+    simt::syncwarp();
+    uint32_t x0[L], x1[L];
+    mont_mul2<TPI>(x0, acc0, t0, x1, acc1, t1, M, ln);
+    stage<TPI>(t0 + 64, x0, ln);
+    stage<TPI>(t1 + 64, x1, ln);
+    simt::syncwarp();
+    mont_mul2<TPI>(x0, x0, t0, x1, x1, t1, M, ln);
+    stage<TPI>(t0 + 128, x0, ln);
+    stage<TPI>(t1 + 128, x1, ln);
+    simt::syncwarp();
+    uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
+    load_slice<TPI>(acc0, d ? t0 + (d - 1) * 64 : one, ln);
+    load_slice<TPI>(acc1, d ? t1 + (d - 1) * 64 : one, ln);
+    for (int s = (int)ndigits - 2; s >= 0; --s) {
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        stage<TPI>(sq0, acc0, ln);
+        stage<TPI>(sq1, acc1, ln);
+        simt::syncwarp();
+        mont_mul2<TPI>(acc0, acc0, sq0, acc1, acc1, sq1, M, ln);
+      }
+      d = (pos >> (2 * s)) & 3u;
+      mont_mul2<TPI>(acc0, acc0, d ? t0 + (d - 1) * 64 : one, acc1, acc1, d ? t1 + (d - 1) * 64 : one, M, ln);
+    }
+    mont_mul2<TPI>(acc0, acc0, cbuf0, acc1, acc1, cbuf1, M, ln);
+  }
+  const uint32_t slot = A.slot ? A.slot[inst] : inst;
+  const bool st = live && slot != 0xffffffffu;
+  const size_t off = (size_t)(slot == 0xffffffffu ? 0 : slot) * 64;
+  finish_store<TPI>(acc0, sq0, A.out0 + off, st, M, ln);
+  finish_store<TPI>(acc1, sq1, A.out1 + off, st, M, ln);
 }
 
 // ------------------------------------------------- (double) exponentiation ----
