@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0x6D70767373)
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
     ap.add_argument("--dual", type=int, default=-1, help="override modp_dual (0/1/2)")
+    ap.add_argument("--ec-threads", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0/1)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary secp256k1 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -234,6 +235,8 @@ def main():
     eb, sb = group.codec.eb, group.codec.sb
     if args.tpi and args.group == "modp":
         group.ctx.set_int("modp_tpi", args.tpi)
+    if args.ec_threads and args.group != "modp":
+        group.ctx.set_int("ec_threads", args.ec_threads)
     if args.overlap >= 0 and args.group == "modp":
         group.ctx.set_int("modp_overlap", args.overlap)
     if args.dual >= 0 and args.group == "modp":
@@ -243,7 +246,7 @@ def main():
     config = {"workload": f"{args.group} verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
               "group": args.group, "n_per_gpu": n, "n_total": n_total, "t": t,
               "x_schedule": "Horner in the exponent, fixed 2-bit windows (DESIGN.md)",
-              "l2": "flushed between timed steps (256 MiB write)", "sharding": f"participants/{world}"}
+              "l2": "flushed between timed steps (256 MiB write)", "sharding": f"participants round-robin over {world} rank(s), one NCCL all-gather per step"}
 
     # ---------------------------------------------------------- reference arm ----
     if args.impl == "reference":
@@ -266,9 +269,17 @@ def main():
         return 0
 
     # --------------------------------------------------------------- our arm ----
-    lo, hi = rank * n, (rank + 1) * n
-    sl = lambda key: box[key][lo * (sb if key == "responses" else eb):hi * (sb if key == "responses" else eb)]
-    positions = (ctypes.c_int64 * n)(*range(lo + 1, hi + 1))
+    # rank r takes positions r+1, r+1+N, ... (round robin): every rank sees the same mix of small and
+    # large positions, so per-rank work is equal; the gathered rows are re-interleaved for the transcript
+    from mpvss_rs_b200.sharding import interleave, shard_indices
+    mine = shard_indices(rank, world, n_total)
+
+    def sl(key):
+        w = sb if key == "responses" else eb
+        if world == 1:
+            return box[key]
+        return b"".join(box[key][i * w:(i + 1) * w] for i in mine)
+    positions = (ctypes.c_int64 * n)(*[i + 1 for i in mine])
     pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
     host = {k: pin(v) for k, v in (("commitments", box["commitments"]), ("publickeys", sl("publickeys")),
                                    ("shares", sl("shares")), ("responses", sl("responses")),
@@ -301,10 +312,9 @@ def main():
         res = 1
         if rank == 0:
             out_host.copy_(out_all, non_blocking=False)
-            g = out_host.numpy()
-            cat = lambda k: g[:, k].reshape(-1).tobytes()
-            group.ctx.check(lib.mpvss_transcript_check(h, n_total, ptr(buf(cat(0))), ptr(buf(box["shares"])),
-                                                       ptr(buf(cat(1))), ptr(buf(cat(2))), ptr(buf(box["challenge"])),
+            xs, a1s, a2s = interleave(out_host.numpy(), world, 3, n, eb)
+            group.ctx.check(lib.mpvss_transcript_check(h, n_total, ptr(buf(xs)), ptr(buf(box["shares"])),
+                                                       ptr(buf(a1s)), ptr(buf(a2s)), ptr(buf(box["challenge"])),
                                                        ctypes.byref(ok), None))
             res = ok.value
         return res, kms, p0
@@ -327,7 +337,7 @@ def main():
     okv, _, _ = run_resident(want_x=(world == 1))
     if rank == 0 and okv != 1:
         raise SystemExit("verification of the synthetic box failed -- refusing to report a number")
-    if world == 1 and bytes(x_chk) != sl("x_dealer"):
+    if world == 1 and bytes(x_chk) != box["x_dealer"]:
         raise SystemExit("verifier X_i differs from dealer X_i -- refusing to report a number")
 
     imad_lo, imad_wide, peak_src = (measure_imad_peak() if rank == 0 and args.group == "modp" else (0, 0, ""))
@@ -397,7 +407,7 @@ def main():
                 "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
     }
     if args.group == "modp":
-        hm = horner_macs(lo, n, t)
+        hm = sum(horner_macs(i, 1, t) for i in mine) if world > 1 else horner_macs(0, n, t)
         achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
         dual = (args.dual != 0) and t >= 8   # library default: two half-length chunks
         combine = n * (4 * 511 * SQR_MACS + (15 + 511 + 15 + 2) * MUL_MACS) if dual else 0
@@ -412,8 +422,8 @@ def main():
             "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
             "share_of_step_macs": hm / total_macs, "traffic": 976640,
             "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full, profiles/horner_r01_ncu.txt",
-            "note": "the a2 = y^r Y^c launch runs on a side stream underneath this kernel; its time share is not "
-                    "subtracted, so frac is a lower bound for the kernel alone",
+            "note": "kernel_ms = CUDA events around the Horner launch(es): two concurrent half-polynomial launches "
+                    "of modp::horner_kernel by default (DESIGN.md section 2)",
             "whole_step": {"achieved": step_timad, "frac": step_timad / imad_lo if imad_lo else None,
                            "algorithmic_macs": total_macs, "kernel_ms": statistics.mean(kern_ms),
                            "what": "all kernels of the step (Horner + chunk combination + both DLEQ launches)"}}

@@ -117,6 +117,11 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->modp_tpi = value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "ec_threads") {
+    if (value < 32) return mpvss_fail(ctx, MPVSS_ERR_ARG, "ec_threads must be >= 32");
+    ctx->ec_threads = (size_t)value;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "modp_overlap") {
     ctx->modp_overlap = value != 0;
     return MPVSS_OK;

@@ -71,6 +71,7 @@ struct mpvss_ctx {
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
   // ---- elliptic-curve groups ----
+  size_t ec_threads = 65536;    // target thread count of the chunked Horner launch ("ec_threads")
   DevBuf ec_consts;             // secp::Consts / rist::Consts
   big::Int ec_order;            // group order (scalar field modulus)
   std::vector<uint8_t> ec_gen;  // encoded generator (both generators of the trait are this point)

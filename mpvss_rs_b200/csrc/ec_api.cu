@@ -228,8 +228,8 @@ struct Ec {
     ec::DecodeArgs<Cv> D{K(ctx), comm, cxy.as<uint32_t>(), cst.as<uint32_t>(), (uint32_t)t};
     MPVSS_CUDA(ctx, ec::launch_decode<Cv>(D, ctx->stream));
     timing_launch(ctx);
-    // enough chunks to fill the chip (~64k threads), at least 16 coefficients per chunk
-    size_t Kc = std::max<size_t>(1, std::min<size_t>(65536 / std::max<size_t>(n, 1), std::max<size_t>(1, t / 16)));
+    // enough chunks to fill the chip (ctx->ec_threads threads), at least 16 coefficients per chunk
+    size_t Kc = std::max<size_t>(1, std::min<size_t>(ctx->ec_threads / std::max<size_t>(n, 1), std::max<size_t>(1, t / 16)));
     size_t B = (t + Kc - 1) / Kc;
     Kc = (t + B - 1) / B;
     MPVSS_CUDA(ctx, part.ensure(Kc * n * sizeof(Point)));

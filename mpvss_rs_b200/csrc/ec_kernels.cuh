@@ -71,10 +71,11 @@ MP_DEV typename Cv::Point small_mul(const typename Cv::Point& p, uint32_t k, uin
       acc = Cv::dbl(acc, C);
       acc = Cv::dbl(acc, C);
     }
+    // one call site for the addition: lanes pick their table entry first, so a warp whose lanes
+    // hold different digits still executes a single point addition per window
     uint32_t d = (k >> (2 * s)) & 3u;
-    if (d == 1) acc = Cv::add(acc, p, C);
-    else if (d == 2) acc = Cv::add(acc, t2, C);
-    else if (d == 3) acc = Cv::add(acc, t3, C);
+    typename Cv::Point q = (d == 3) ? t3 : ((d == 2) ? t2 : p);
+    if (d) acc = Cv::add(acc, q, C);
   }
   return acc;
 }
