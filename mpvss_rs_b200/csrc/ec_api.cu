@@ -56,9 +56,9 @@ struct SecpTraits {
     big::Int p = hex_int("fffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f");
     fill_modulus(C.P, p);
     fill_modulus(C.N, order());
-    put_mont(C.b7, big::from_u64(7), p);
-    put_mont(C.gx, hex_int("79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"), p);
-    put_mont(C.gy, hex_int("483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8"), p);
+    put8(C.b7, big::from_u64(7));  // base-field constants in plain representation (fpspecial.cuh)
+    put8(C.gx, hex_int("79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"));
+    put8(C.gy, hex_int("483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8"));
     put8(C.sqrt_e, big::shr1(big::shr1(big::add(p, big::from_u64(1)))));
   }
   static void generator(uint8_t* out) {  // secp256k1.rs:78-85 (both generators are G)
@@ -92,12 +92,12 @@ struct RistTraits {
     big::Int p = hex_int("7fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffed");
     fill_modulus(C.P, p);
     fill_modulus(C.N, order());
-    put_mont(C.d, hex_int("52036cee2b6ffe738cc740797779e89800700a4d4141d8ab75eb4dca135978a3"), p);
-    put_mont(C.d2, hex_int("2406d9dc56dffce7198e80f2eef3d13000e0149a8283b156ebd69b9426b2f159"), p);
-    put_mont(C.sqrt_m1, hex_int("2b8324804fc1df0b2b4d00993dfbd7a72f431806ad2fe478c4ee1b274a0ea0b0"), p);
-    put_mont(C.invsqrt_a_minus_d, hex_int("786c8905cfaffca216c27b91fe01d8409d2f16175a4172be99c8fdaa805d40ea"), p);
-    put_mont(C.bx, hex_int("216936d3cd6e53fec0a4e231fdd6dc5c692cc7609525a7b2c9562d608f25d51a"), p);
-    put_mont(C.by, hex_int("6666666666666666666666666666666666666666666666666666666666666658"), p);
+    put8(C.d, hex_int("52036cee2b6ffe738cc740797779e89800700a4d4141d8ab75eb4dca135978a3"));
+    put8(C.d2, hex_int("2406d9dc56dffce7198e80f2eef3d13000e0149a8283b156ebd69b9426b2f159"));
+    put8(C.sqrt_m1, hex_int("2b8324804fc1df0b2b4d00993dfbd7a72f431806ad2fe478c4ee1b274a0ea0b0"));
+    put8(C.invsqrt_a_minus_d, hex_int("786c8905cfaffca216c27b91fe01d8409d2f16175a4172be99c8fdaa805d40ea"));
+    put8(C.bx, hex_int("216936d3cd6e53fec0a4e231fdd6dc5c692cc7609525a7b2c9562d608f25d51a"));
+    put8(C.by, hex_int("6666666666666666666666666666666666666666666666666666666666666658"));
     big::Int e;
     big::divmod(big::sub(p, big::from_u64(5)), big::from_u64(8), &e, nullptr);
     put8(C.pm5d8, e);

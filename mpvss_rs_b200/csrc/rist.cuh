@@ -1,124 +1,167 @@
 // ristretto255 group operations, one point per thread (replaces curve25519-dalek's
 // RistrettoPoint * Scalar / + / compress / decompress behind
 // /root/reference/src/groups/ristretto255.rs:161-220).  Extended twisted-Edwards coordinates
-// (a = -1) over the Montgomery-form field 2^255-19 of fp256.cuh; encoding and decoding follow
+// (a = -1) over the field 2^255-19 in plain representation (fpspecial.cuh); encoding and decoding follow
 // RFC 9496 sections 4.3.1-4.3.2.
 #pragma once
-#include "fp256.cuh"
+#include "fpspecial.cuh"
 
 namespace rist {
 
 using fp256::Fe;
 using fp256::Modulus;
 
+// Base-field arithmetic mod 2^255-19: plain representation, special-form reduction.
+namespace F {
+using fp256::add;
+using fp256::dbl;
+using fp256::eq;
+using fp256::fe_zero;
+using fp256::is_zero;
+using fp256::load;
+using fp256::neg;
+using fp256::store;
+using fp256::sub;
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
+  uint32_t t[16];
+  fpsp::mul_wide(t, a, b);
+  return fpsp::ed_reduce(t, P.m);
+}
+MP_DEV Fe sqr(const Fe& a, const Modulus& P) {
+  uint32_t t[16];
+  fpsp::sqr_wide(t, a);
+  return fpsp::ed_reduce(t, P.m);
+}
+MP_DEV Fe to_mont(const Fe& a, const Modulus&) { return a; }
+MP_DEV Fe from_mont(const Fe& a, const Modulus&) { return a; }
+MP_DEV Fe mont_one(const Modulus&) {
+  Fe r = fe_zero();
+  r.v[0] = 1;
+  return r;
+}
+MP_NOINLINE Fe pow(const Fe& a, const uint32_t (&e)[8], const Modulus& P) {
+  Fe r = F::mont_one(P);
+  bool started = false;
+#pragma unroll 1
+  for (int i = 255; i >= 0; --i) {
+    if (started) r = F::sqr(r, P);
+    if ((e[i >> 5] >> (i & 31)) & 1u) {
+      r = started ? F::mul(r, a, P) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+}  // namespace F
+
 struct Consts {
   Modulus P;                   // 2^255 - 19
   Modulus N;                   // l = 2^252 + 27742317777372353535851937790883648493
-  uint32_t d[8], d2[8];        // d, 2d (Montgomery form)
+  uint32_t d[8], d2[8];        // d, 2d
   uint32_t sqrt_m1[8];         // sqrt(-1)
   uint32_t invsqrt_a_minus_d[8];
-  uint32_t bx[8], by[8];       // basepoint, affine, Montgomery form
+  uint32_t bx[8], by[8];       // basepoint, affine
   uint32_t pm5d8[8];           // (p - 5) / 8
 };
 
 struct Ext {
   Fe X, Y, Z, T;
 };
-struct Aff {  // affine Edwards coordinates of a representative, Montgomery form
+struct Aff {  // affine Edwards coordinates of a representative
   Fe x, y;
   uint32_t inf;  // unused (the identity (0, 1) is an ordinary point); kept for the policy interface
 };
 
 MP_DEV Ext ext_identity(const Modulus& P) {
   Ext r;
-  r.X = fp256::fe_zero();
-  r.Y = fp256::mont_one(P);
-  r.Z = fp256::mont_one(P);
-  r.T = fp256::fe_zero();
+  r.X = F::fe_zero();
+  r.Y = F::mont_one(P);
+  r.Z = F::mont_one(P);
+  r.T = F::fe_zero();
   return r;
 }
 MP_DEV Ext ext_from_aff(const Aff& a, const Modulus& P) {
   Ext r;
   r.X = a.x;
   r.Y = a.y;
-  r.Z = fp256::mont_one(P);
-  r.T = fp256::mul(a.x, a.y, P);
+  r.Z = F::mont_one(P);
+  r.T = F::mul(a.x, a.y, P);
   return r;
 }
 
 // add-2008-hwcd-3 (unified, complete for a = -1 and non-square d): 9M
 MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
-  Fe A = mul(sub(p.Y, p.X, P), sub(q.Y, q.X, P), P);
-  Fe B = mul(add(p.Y, p.X, P), add(q.Y, q.X, P), P);
-  Fe Cc = mul(mul(p.T, load(C.d2), P), q.T, P);
-  Fe D = dbl(mul(p.Z, q.Z, P), P);
+  Fe A = F::mul(sub(p.Y, p.X, P), sub(q.Y, q.X, P), P);
+  Fe B = F::mul(add(p.Y, p.X, P), add(q.Y, q.X, P), P);
+  Fe Cc = F::mul(F::mul(p.T, load(C.d2), P), q.T, P);
+  Fe D = dbl(F::mul(p.Z, q.Z, P), P);
   Fe E = sub(B, A, P), F = sub(D, Cc, P), G = add(D, Cc, P), H = add(B, A, P);
   Ext r;
-  r.X = mul(E, F, P);
-  r.Y = mul(G, H, P);
-  r.T = mul(E, H, P);
-  r.Z = mul(F, G, P);
+  r.X = F::mul(E, F, P);
+  r.Y = F::mul(G, H, P);
+  r.T = F::mul(E, H, P);
+  r.Z = F::mul(F, G, P);
   return r;
 }
 // dbl-2008-hwcd with a = -1: 4M + 4S
 MP_NOINLINE Ext ext_dbl(const Ext& p, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
-  Fe A = sqr(p.X, P), B = sqr(p.Y, P), Cc = dbl(sqr(p.Z, P), P);
+  Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), Cc = dbl(F::sqr(p.Z, P), P);
   Fe D = neg(A, P);
-  Fe E = sub(sub(sqr(add(p.X, p.Y, P), P), A, P), B, P);
+  Fe E = sub(sub(F::sqr(add(p.X, p.Y, P), P), A, P), B, P);
   Fe G = add(D, B, P), F = sub(G, Cc, P), H = sub(D, B, P);
   Ext r;
-  r.X = mul(E, F, P);
-  r.Y = mul(G, H, P);
-  r.T = mul(E, H, P);
-  r.Z = mul(F, G, P);
+  r.X = F::mul(E, F, P);
+  r.Y = F::mul(G, H, P);
+  r.T = F::mul(E, H, P);
+  r.Z = F::mul(F, G, P);
   return r;
 }
 
 // canonical-form helpers (RFC 9496 section 4.1)
-MP_DEV bool is_negative(const Fe& a_mont, const Modulus& P) { return fp256::from_mont(a_mont, P).v[0] & 1u; }
-MP_DEV Fe ct_abs(const Fe& a, const Modulus& P) { return is_negative(a, P) ? fp256::neg(a, P) : a; }
+MP_DEV bool is_negative(const Fe& a_mont, const Modulus& P) { return F::from_mont(a_mont, P).v[0] & 1u; }
+MP_DEV Fe ct_abs(const Fe& a, const Modulus& P) { return is_negative(a, P) ? F::neg(a, P) : a; }
 
 // SQRT_RATIO_M1 (RFC 9496 section 4.2); returns was_square, r in *out
 MP_NOINLINE bool sqrt_ratio_m1(Fe* out, const Fe& u, const Fe& v, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
-  Fe v3 = mul(sqr(v, P), v, P);
-  Fe v7 = mul(sqr(v3, P), v, P);
-  Fe r = mul(mul(u, v3, P), pow(mul(u, v7, P), C.pm5d8, P), P);
-  Fe check = mul(v, sqr(r, P), P);
+  Fe v3 = F::mul(F::sqr(v, P), v, P);
+  Fe v7 = F::mul(F::sqr(v3, P), v, P);
+  Fe r = F::mul(F::mul(u, v3, P), F::pow(F::mul(u, v7, P), C.pm5d8, P), P);
+  Fe check = F::mul(v, F::sqr(r, P), P);
   Fe sm1 = load(C.sqrt_m1);
   Fe nu = neg(u, P);
   bool correct = eq(check, u);
   bool flipped = eq(check, nu);
-  bool flipped_i = eq(check, mul(nu, sm1, P));
-  if (flipped || flipped_i) r = mul(r, sm1, P);
+  bool flipped_i = eq(check, F::mul(nu, sm1, P));
+  if (flipped || flipped_i) r = F::mul(r, sm1, P);
   *out = ct_abs(r, P);
   return correct || flipped;
 }
 
 // RFC 9496 section 4.3.2
 MP_NOINLINE void encode(uint8_t* out, const Ext& p, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
-  Fe u1 = mul(add(p.Z, p.Y, P), sub(p.Z, p.Y, P), P);
-  Fe u2 = mul(p.X, p.Y, P);
+  Fe u1 = F::mul(add(p.Z, p.Y, P), sub(p.Z, p.Y, P), P);
+  Fe u2 = F::mul(p.X, p.Y, P);
   Fe invsqrt;
-  sqrt_ratio_m1(&invsqrt, mont_one(P), mul(u1, sqr(u2, P), P), C);
-  Fe den1 = mul(invsqrt, u1, P), den2 = mul(invsqrt, u2, P);
-  Fe z_inv = mul(mul(den1, den2, P), p.T, P);
+  sqrt_ratio_m1(&invsqrt, F::mont_one(P), F::mul(u1, F::sqr(u2, P), P), C);
+  Fe den1 = F::mul(invsqrt, u1, P), den2 = F::mul(invsqrt, u2, P);
+  Fe z_inv = F::mul(F::mul(den1, den2, P), p.T, P);
   Fe sm1 = load(C.sqrt_m1);
-  Fe ix0 = mul(p.X, sm1, P), iy0 = mul(p.Y, sm1, P);
-  Fe enchanted = mul(den1, load(C.invsqrt_a_minus_d), P);
-  bool rotate = is_negative(mul(p.T, z_inv, P), P);
+  Fe ix0 = F::mul(p.X, sm1, P), iy0 = F::mul(p.Y, sm1, P);
+  Fe enchanted = F::mul(den1, load(C.invsqrt_a_minus_d), P);
+  bool rotate = is_negative(F::mul(p.T, z_inv, P), P);
   Fe x = rotate ? iy0 : p.X;
   Fe y = rotate ? ix0 : p.Y;
   Fe den_inv = rotate ? enchanted : den2;
-  if (is_negative(mul(x, z_inv, P), P)) y = neg(y, P);
-  Fe s = from_mont(ct_abs(mul(den_inv, sub(p.Z, y, P), P), P), P);
+  if (is_negative(F::mul(x, z_inv, P), P)) y = neg(y, P);
+  Fe s = F::from_mont(ct_abs(F::mul(den_inv, sub(p.Z, y, P), P), P), P);
   for (int i = 0; i < 8; ++i) {
     out[4 * i] = (uint8_t)s.v[i];
     out[4 * i + 1] = (uint8_t)(s.v[i] >> 8);
@@ -129,11 +172,11 @@ MP_NOINLINE void encode(uint8_t* out, const Ext& p, const Consts& C) {
 
 // RFC 9496 section 4.3.1; false for non-canonical or invalid encodings
 MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
   a.inf = 0;
   a.x = fe_zero();
-  a.y = mont_one(P);
+  a.y = F::mont_one(P);
   Fe s;
   for (int i = 0; i < 8; ++i)
     s.v[i] = (uint32_t)in[4 * i] | (uint32_t)in[4 * i + 1] << 8 | (uint32_t)in[4 * i + 2] << 16 |
@@ -145,18 +188,18 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
   for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(s.v[i], P.m[i]);
   if (simt::subc(0, 0) == 0) return false;
   if (s.v[0] & 1u) return false;
-  Fe sm = to_mont(s, P), one = mont_one(P);
-  Fe ss = sqr(sm, P);
+  Fe sm = F::to_mont(s, P), one = F::mont_one(P);
+  Fe ss = F::sqr(sm, P);
   Fe u1 = sub(one, ss, P), u2 = add(one, ss, P);
-  Fe u2_sqr = sqr(u2, P);
-  Fe v = sub(neg(mul(load(C.d), sqr(u1, P), P), P), u2_sqr, P);
+  Fe u2_sqr = F::sqr(u2, P);
+  Fe v = sub(neg(F::mul(load(C.d), F::sqr(u1, P), P), P), u2_sqr, P);
   Fe invsqrt;
-  bool was_square = sqrt_ratio_m1(&invsqrt, one, mul(v, u2_sqr, P), C);
-  Fe den_x = mul(invsqrt, u2, P);
-  Fe den_y = mul(mul(invsqrt, den_x, P), v, P);
-  Fe x = ct_abs(mul(dbl(sm, P), den_x, P), P);
-  Fe y = mul(u1, den_y, P);
-  Fe tt = mul(x, y, P);
+  bool was_square = sqrt_ratio_m1(&invsqrt, one, F::mul(v, u2_sqr, P), C);
+  Fe den_x = F::mul(invsqrt, u2, P);
+  Fe den_y = F::mul(F::mul(invsqrt, den_x, P), v, P);
+  Fe x = ct_abs(F::mul(dbl(sm, P), den_x, P), P);
+  Fe y = F::mul(u1, den_y, P);
+  Fe tt = F::mul(x, y, P);
   if (!was_square || is_negative(tt, P) || is_zero(y)) return false;
   a.x = x;
   a.y = y;

@@ -1,116 +1,167 @@
 // secp256k1 group operations, one point per thread (replaces k256's
 // ProjectivePoint * Scalar / + / to_bytes / from_bytes behind
-// /root/reference/src/groups/secp256k1.rs:91-152).  Jacobian coordinates over the
-// Montgomery-form base field of fp256.cuh; Z = 0 encodes the identity.  Kernel bodies are
+// /root/reference/src/groups/secp256k1.rs:91-152).  Jacobian coordinates over the base
+// field in plain representation (special-form reduction, fpspecial.cuh); Z = 0 is the identity.  Kernel bodies are
 // written against simt.h, so tests/emu runs them on the CPU as well.
 #pragma once
-#include "fp256.cuh"
+#include "fpspecial.cuh"
 
 namespace secp {
 
 using fp256::Fe;
 using fp256::Modulus;
 
+// Base-field arithmetic: plain representation with the special-form reduction of fpspecial.cuh
+// (the scalar field keeps the generic Montgomery code of fp256.cuh).
+namespace F {
+using fp256::add;
+using fp256::dbl;
+using fp256::eq;
+using fp256::fe_zero;
+using fp256::is_zero;
+using fp256::load;
+using fp256::neg;
+using fp256::store;
+using fp256::sub;
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
+  uint32_t t[16];
+  fpsp::mul_wide(t, a, b);
+  return fpsp::secp_reduce(t, P.m);
+}
+MP_DEV Fe sqr(const Fe& a, const Modulus& P) {
+  uint32_t t[16];
+  fpsp::sqr_wide(t, a);
+  return fpsp::secp_reduce(t, P.m);
+}
+MP_DEV Fe to_mont(const Fe& a, const Modulus&) { return a; }
+MP_DEV Fe from_mont(const Fe& a, const Modulus&) { return a; }
+MP_DEV Fe mont_one(const Modulus&) {
+  Fe r = fe_zero();
+  r.v[0] = 1;
+  return r;
+}
+MP_NOINLINE Fe pow(const Fe& a, const uint32_t (&e)[8], const Modulus& P) {
+  Fe r = F::mont_one(P);
+  bool started = false;
+#pragma unroll 1
+  for (int i = 255; i >= 0; --i) {
+    if (started) r = F::sqr(r, P);
+    if ((e[i >> 5] >> (i & 31)) & 1u) {
+      r = started ? F::mul(r, a, P) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+MP_NOINLINE Fe inv(const Fe& a, const Modulus& P) {
+  uint32_t e[8];
+  e[0] = simt::sub_cc(P.m[0], 2);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) e[i] = simt::subc_cc(P.m[i], 0);
+  return F::pow(a, e, P);
+}
+}  // namespace F
+
 // Device-resident constants (built on the host in secp_api.cu).
 struct Consts {
   Modulus P;             // base field  2^256 - 2^32 - 977
   Modulus N;             // scalar field (group order)
-  uint32_t b7[8];        // 7 in Montgomery form
-  uint32_t gx[8], gy[8]; // generator, affine, Montgomery form
+  uint32_t b7[8];        // 7
+  uint32_t gx[8], gy[8]; // generator, affine
   uint32_t sqrt_e[8];    // (p + 1) / 4
 };
 
 struct Jac {
   Fe X, Y, Z;
 };
-struct Aff {  // affine, Montgomery form; inf = identity
+struct Aff {  // affine; inf = identity
   Fe x, y;
   uint32_t inf;
 };
 
 MP_DEV Jac jac_infinity(const Modulus& P) {
   Jac r;
-  r.X = fp256::mont_one(P);
-  r.Y = fp256::mont_one(P);
-  r.Z = fp256::fe_zero();
+  r.X = F::mont_one(P);
+  r.Y = F::mont_one(P);
+  r.Z = F::fe_zero();
   return r;
 }
-MP_DEV bool jac_is_inf(const Jac& p) { return fp256::is_zero(p.Z); }
+MP_DEV bool jac_is_inf(const Jac& p) { return F::is_zero(p.Z); }
 MP_DEV Jac jac_from_aff(const Aff& a, const Modulus& P) {
   if (a.inf) return jac_infinity(P);
   Jac r;
   r.X = a.x;
   r.Y = a.y;
-  r.Z = fp256::mont_one(P);
+  r.Z = F::mont_one(P);
   return r;
 }
 MP_DEV Jac jac_neg(const Jac& p, const Modulus& P) {
   Jac r = p;
-  r.Y = fp256::neg(p.Y, P);
+  r.Y = F::neg(p.Y, P);
   return r;
 }
 
 // dbl-2009-l (a = 0): 2M + 5S
 MP_NOINLINE Jac jac_dbl(const Jac& p, const Modulus& P) {
-  using namespace fp256;
+  using namespace F;
   if (jac_is_inf(p)) return p;
-  Fe A = sqr(p.X, P), B = sqr(p.Y, P), C = sqr(B, P);
+  Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), C = F::sqr(B, P);
   Fe t = add(p.X, B, P);
-  Fe D = dbl(sub(sub(sqr(t, P), A, P), C, P), P);
+  Fe D = dbl(sub(sub(F::sqr(t, P), A, P), C, P), P);
   Fe E = add(dbl(A, P), A, P);
-  Fe F = sqr(E, P);
+  Fe F = F::sqr(E, P);
   Jac r;
   r.X = sub(F, dbl(D, P), P);
   Fe C8 = dbl(dbl(dbl(C, P), P), P);
-  r.Y = sub(mul(E, sub(D, r.X, P), P), C8, P);
-  r.Z = dbl(mul(p.Y, p.Z, P), P);
+  r.Y = sub(F::mul(E, sub(D, r.X, P), P), C8, P);
+  r.Z = dbl(F::mul(p.Y, p.Z, P), P);
   return r;
 }
 
 // add-2007-bl with the exceptional cases handled: 11M + 5S
 MP_NOINLINE Jac jac_add(const Jac& p, const Jac& q, const Modulus& P) {
-  using namespace fp256;
+  using namespace F;
   if (jac_is_inf(p)) return q;
   if (jac_is_inf(q)) return p;
-  Fe Z1Z1 = sqr(p.Z, P), Z2Z2 = sqr(q.Z, P);
-  Fe U1 = mul(p.X, Z2Z2, P), U2 = mul(q.X, Z1Z1, P);
-  Fe S1 = mul(mul(p.Y, q.Z, P), Z2Z2, P), S2 = mul(mul(q.Y, p.Z, P), Z1Z1, P);
+  Fe Z1Z1 = F::sqr(p.Z, P), Z2Z2 = F::sqr(q.Z, P);
+  Fe U1 = F::mul(p.X, Z2Z2, P), U2 = F::mul(q.X, Z1Z1, P);
+  Fe S1 = F::mul(F::mul(p.Y, q.Z, P), Z2Z2, P), S2 = F::mul(F::mul(q.Y, p.Z, P), Z1Z1, P);
   Fe H = sub(U2, U1, P), rr = sub(S2, S1, P);
   if (is_zero(H)) {
     if (is_zero(rr)) return jac_dbl(p, P);
     return jac_infinity(P);
   }
-  Fe I = sqr(dbl(H, P), P), J = mul(H, I, P), r2 = dbl(rr, P), V = mul(U1, I, P);
+  Fe I = F::sqr(dbl(H, P), P), J = F::mul(H, I, P), r2 = dbl(rr, P), V = F::mul(U1, I, P);
   Jac r;
-  r.X = sub(sub(sqr(r2, P), J, P), dbl(V, P), P);
-  r.Y = sub(mul(r2, sub(V, r.X, P), P), dbl(mul(S1, J, P), P), P);
+  r.X = sub(sub(F::sqr(r2, P), J, P), dbl(V, P), P);
+  r.Y = sub(F::mul(r2, sub(V, r.X, P), P), dbl(F::mul(S1, J, P), P), P);
   Fe zz = add(p.Z, q.Z, P);
-  r.Z = mul(sub(sub(sqr(zz, P), Z1Z1, P), Z2Z2, P), H, P);
+  r.Z = F::mul(sub(sub(F::sqr(zz, P), Z1Z1, P), Z2Z2, P), H, P);
   return r;
 }
 
 // mixed addition (q affine): madd-2007-bl, 7M + 4S
 MP_NOINLINE Jac jac_madd(const Jac& p, const Aff& q, const Modulus& P) {
-  using namespace fp256;
+  using namespace F;
   if (q.inf) return p;
   if (jac_is_inf(p)) return jac_from_aff(q, P);
-  Fe Z1Z1 = sqr(p.Z, P);
-  Fe U2 = mul(q.x, Z1Z1, P), S2 = mul(mul(q.y, p.Z, P), Z1Z1, P);
+  Fe Z1Z1 = F::sqr(p.Z, P);
+  Fe U2 = F::mul(q.x, Z1Z1, P), S2 = F::mul(F::mul(q.y, p.Z, P), Z1Z1, P);
   Fe H = sub(U2, p.X, P), rr = sub(S2, p.Y, P);
   if (is_zero(H)) {
     if (is_zero(rr)) return jac_dbl(p, P);
     return jac_infinity(P);
   }
-  Fe HH = sqr(H, P), I = dbl(dbl(HH, P), P), J = mul(H, I, P), r2 = dbl(rr, P), V = mul(p.X, I, P);
+  Fe HH = F::sqr(H, P), I = dbl(dbl(HH, P), P), J = F::mul(H, I, P), r2 = dbl(rr, P), V = F::mul(p.X, I, P);
   Jac r;
-  r.X = sub(sub(sqr(r2, P), J, P), dbl(V, P), P);
-  r.Y = sub(mul(r2, sub(V, r.X, P), P), dbl(mul(p.Y, J, P), P), P);
-  r.Z = sub(sub(sqr(add(p.Z, H, P), P), Z1Z1, P), HH, P);
+  r.X = sub(sub(F::sqr(r2, P), J, P), dbl(V, P), P);
+  r.Y = sub(F::mul(r2, sub(V, r.X, P), P), dbl(F::mul(p.Y, J, P), P), P);
+  r.Z = sub(sub(F::sqr(add(p.Z, H, P), P), Z1Z1, P), HH, P);
   return r;
 }
 
 MP_NOINLINE Aff jac_to_aff(const Jac& p, const Modulus& P) {
-  using namespace fp256;
+  using namespace F;
   Aff a;
   if (jac_is_inf(p)) {
     a.x = fe_zero();
@@ -118,9 +169,9 @@ MP_NOINLINE Aff jac_to_aff(const Jac& p, const Modulus& P) {
     a.inf = 1;
     return a;
   }
-  Fe zi = inv(p.Z, P), zi2 = sqr(zi, P);
-  a.x = mul(p.X, zi2, P);
-  a.y = mul(p.Y, mul(zi2, zi, P), P);
+  Fe zi = F::inv(p.Z, P), zi2 = F::sqr(zi, P);
+  a.x = F::mul(p.X, zi2, P);
+  a.y = F::mul(p.Y, F::mul(zi2, zi, P), P);
   a.inf = 0;
   return a;
 }
@@ -132,7 +183,7 @@ MP_NOINLINE void encode(uint8_t* out, const Aff& a, const Modulus& P) {
     for (int i = 0; i < 33; ++i) out[i] = 0;
     return;
   }
-  Fe x = fp256::from_mont(a.x, P), y = fp256::from_mont(a.y, P);
+  Fe x = F::from_mont(a.x, P), y = F::from_mont(a.y, P);
   out[0] = 2 + (y.v[0] & 1u);
   for (int i = 0; i < 8; ++i) {
     uint32_t w = x.v[7 - i];
@@ -144,7 +195,7 @@ MP_NOINLINE void encode(uint8_t* out, const Aff& a, const Modulus& P) {
 }
 // returns false for an invalid encoding (reference: bytes_to_element -> None)
 MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
-  using namespace fp256;
+  using namespace F;
   const Modulus& P = C.P;
   bool all_zero = true;
   for (int i = 0; i < 33; ++i) all_zero = all_zero && in[i] == 0;
@@ -166,11 +217,11 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
 #pragma unroll
   for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(x.v[i], P.m[i]);
   if (simt::subc(0, 0) == 0) return false;
-  Fe xm = to_mont(x, P);
-  Fe y2 = add(mul(sqr(xm, P), xm, P), load(C.b7), P);
-  Fe y = pow(y2, C.sqrt_e, P);
-  if (!eq(sqr(y, P), y2)) return false;
-  Fe yn = from_mont(y, P);
+  Fe xm = F::to_mont(x, P);
+  Fe y2 = add(F::mul(F::sqr(xm, P), xm, P), load(C.b7), P);
+  Fe y = F::pow(y2, C.sqrt_e, P);
+  if (!eq(F::sqr(y, P), y2)) return false;
+  Fe yn = F::from_mont(y, P);
   if ((yn.v[0] & 1u) != (uint32_t)(in[0] & 1)) y = neg(y, P);
   a.x = xm;
   a.y = y;

@@ -74,6 +74,22 @@ int emu_ec_inv(const void* modN, const uint32_t* in, uint32_t n, uint32_t* out, 
   for (uint32_t i = 0; i < n; ++i) ec::inv_body(A, i);
   return 0;
 }
+// special-form fields: out_mul = a*b mod p, out_sqr = a*a mod p (which: 0 secp256k1, 1 curve25519)
+int emu_fpsp_ops(int which, const void* mod, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* mul,
+                 uint32_t* sqr) {
+  const fp256::Modulus& M = *(const fp256::Modulus*)mod;
+  for (uint32_t i = 0; i < n; ++i) {
+    fp256::Fe x = fp256::load(a + 8 * i), y = fp256::load(b + 8 * i);
+    if (which == 0) {
+      fp256::store(mul + 8 * i, secp::F::mul(x, y, M));
+      fp256::store(sqr + 8 * i, secp::F::sqr(x, M));
+    } else {
+      fp256::store(mul + 8 * i, rist::F::mul(x, y, M));
+      fp256::store(sqr + 8 * i, rist::F::sqr(x, M));
+    }
+  }
+  return 0;
+}
 // field-level checks: out = a*b/R, a+b, a-b, a^-1 (mod the modulus in `mod`)
 int emu_fp_ops(const void* mod, const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* mul, uint32_t* add,
                uint32_t* sub, uint32_t* inv) {

@@ -71,14 +71,15 @@ def modulus_words(m):
 def secp_consts():
     R = 1 << 256
     p = SECP_P
-    return np.concatenate([modulus_words(SECP_P), modulus_words(SECP_N), to_limbs(7 * R % p, 8),
-                           to_limbs(SECP_GX * R % p, 8), to_limbs(SECP_GY * R % p, 8), to_limbs((p + 1) // 4, 8)])
+    # base-field constants are in plain representation (fpspecial.cuh); scalar field stays Montgomery
+    return np.concatenate([modulus_words(SECP_P), modulus_words(SECP_N), to_limbs(7, 8),
+                           to_limbs(SECP_GX, 8), to_limbs(SECP_GY, 8), to_limbs((p + 1) // 4, 8)])
 
 
 def rist_consts():
     from oracle import groups as og
     R, p = 1 << 256, ED_P
-    mont = lambda v: to_limbs(v % p * R % p, 8)
+    mont = lambda v: to_limbs(v % p, 8)   # plain representation
     return np.concatenate([modulus_words(ED_P), modulus_words(ED_L), mont(og.ED_D), mont(2 * og.ED_D),
                            mont(og.ED_SQRT_M1), mont(og.ED_INVSQRT_A_MINUS_D), mont(og.ED_BX), mont(og.ED_BY),
                            to_limbs((p - 5) // 8, 8)])

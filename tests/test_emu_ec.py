@@ -39,6 +39,29 @@ def test_fp256_field_ops(L, m):
         assert eu.from_limbs(o[3][8 * i:8 * i + 8]) == (pow(A[i], -1, m) if A[i] else 0)
 
 
+@pytest.mark.parametrize("which,m", [(0, eu.SECP_P), (1, eu.ED_P)])
+def test_special_form_field(L, which, m):
+    """fpspecial.cuh: plain-representation product / square with the 2^256 = c fold, fully reduced."""
+    rng = random.Random(which + 17)
+    M = eu.modulus_words(m)
+    edge = [0, 1, 2, m - 1, m - 2, (1 << 255) - 1 if m > (1 << 255) else m - 19, (1 << 128) - 1,
+            ((1 << 256) - 1) % m, m // 2, m // 2 + 1, 0xFFFFFFFF, 0xFFFFFFFF00000000 % m]
+    A = edge + [rng.randrange(m) for _ in range(200)]
+    B = edge[::-1] + [rng.randrange(m) for _ in range(200)]
+    for k in range(40):      # structured operands: runs of all-ones / zero limbs
+        limbs = [rng.choice([0, 0xFFFFFFFF, 0xFFFFFFFE, 1, rng.getrandbits(32)]) for _ in range(8)]
+        A.append(sum(l << (32 * i) for i, l in enumerate(limbs)) % m)
+        B.append(sum(l << (32 * (7 - i)) for i, l in enumerate(limbs)) % m)
+    n = len(A)
+    a = np.concatenate([eu.to_limbs(x, 8) for x in A])
+    b = np.concatenate([eu.to_limbs(x, 8) for x in B])
+    om, osq = np.zeros(8 * n, dtype=np.uint32), np.zeros(8 * n, dtype=np.uint32)
+    L.emu_fpsp_ops(which, eu.P(M), eu.P(a), eu.P(b), n, eu.P(om), eu.P(osq))
+    for i in range(n):
+        assert eu.from_limbs(om[8 * i:8 * i + 8]) == A[i] * B[i] % m, (which, i)
+        assert eu.from_limbs(osq[8 * i:8 * i + 8]) == A[i] * A[i] % m, (which, i)
+
+
 CURVES = {
     "secp": (Secp256k1Group, eu.secp_consts, SECP_N, 33),
     "rist": (Ristretto255Group, eu.rist_consts, ED_L, 32),
