@@ -119,16 +119,26 @@ def build_box(group, n_total, t, seed):
             "group": c.name}
 
 
-def horner_macs(n0, n, t):
-    """Algorithmic MACs of the X_i kernel for positions n0+1..n0+n: per Horner step the executed
-    fixed 2-bit-window schedule is (2(d-1)+1) squarings and (d-1)+2 multiplications, d = base-4
-    digits of the position."""
-    total = 0
-    for p in range(n0 + 1, n0 + n + 1):
+def horner_macs(positions, t, tpi=8):
+    """Algorithmic MACs of the X_i kernel for the given 1-based positions, following the schedule the
+    kernel executes: per Horner step (2(d-1)+1) squarings and (d-1)+2
+    multiplications, d = base-4 digits of the position, minus the window multiplications skipped
+    because the digit is zero for every lane group of the warp (positions are dealt to warps in
+    increasing order inside each digit class, exactly as modp_api.cu::prep_positions does)."""
+    gpw = 32 // tpi
+    by = {}
+    for p in positions:
         d = 1
         while p >> (2 * d):
             d += 1
-        total += (t - 1) * ((2 * (d - 1) + 1) * SQR_MACS + ((d - 1) + 2) * MUL_MACS)
+        by.setdefault(d, []).append(p)
+    total = 0
+    for d, ps in by.items():
+        for c in range(0, len(ps), gpw):
+            chunk = ps[c:c + gpw]
+            full = chunk + [chunk[-1]] * (gpw - len(chunk))
+            skipped = sum(1 for s_ in range(d - 1) if all(((q >> (2 * s_)) & 3) == 0 for q in full))
+            total += len(chunk) * (t - 1) * ((2 * (d - 1) + 1) * SQR_MACS + ((d - 1) + 2 - skipped) * MUL_MACS)
     return total
 
 
@@ -407,9 +417,9 @@ def main():
                 "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
     }
     if args.group == "modp":
-        hm = sum(horner_macs(i, 1, t) for i in mine) if world > 1 else horner_macs(0, n, t)
+        hm = horner_macs([i + 1 for i in mine], t, args.tpi or 8)
         achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
-        dual = (args.dual != 0) and t >= 8   # library default: two half-length chunks
+        dual = (args.dual > 0) and t >= 8   # library default: single chain (modp_dual = 0)
         combine = n * (4 * 511 * SQR_MACS + (15 + 511 + 15 + 2) * MUL_MACS) if dual else 0
         total_macs = hm + combine + dleq_macs(n)
         step_timad = 2.0 * total_macs / (statistics.mean(kern_ms) * 1e-3) / 1e12
@@ -422,8 +432,8 @@ def main():
             "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
             "share_of_step_macs": hm / total_macs, "traffic": 976640,
             "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full, profiles/horner_r01_ncu.txt",
-            "note": "kernel_ms = CUDA events around the Horner launch(es): two concurrent half-polynomial launches "
-                    "of modp::horner_kernel by default (DESIGN.md section 2)",
+            "note": "kernel_ms = CUDA events around the Horner launch on the library stream; algorithmic MACs "
+                    "follow the executed fixed-window schedule, skipped zero-digit multiplications excluded",
             "whole_step": {"achieved": step_timad, "frac": step_timad / imad_lo if imad_lo else None,
                            "algorithmic_macs": total_macs, "kernel_ms": statistics.mean(kern_ms),
                            "what": "all kernels of the step (Horner + chunk combination + both DLEQ launches)"}}

@@ -66,7 +66,8 @@ struct mpvss_ctx {
   // ---- ModpGroup ----
   int modp_tpi = 8;
   int modp_overlap = 0;  // run the X-independent a2 launch on a side stream underneath the Horner kernel
-  int modp_dual = 2;  // two-chunk Horner: 0 off, 1 two interleaved chains per lane group, 2 two concurrent launches
+  int modp_dual = 0;  // two-chunk Horner: 0 off (default: fastest whole step), 1 two interleaved chains per lane
+                      // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
@@ -84,7 +85,7 @@ struct mpvss_ctx {
   std::vector<uint8_t> v_challenge, v_y_host;
   bool v_dual = false;
   DevBuf v_e, v_h;  // chunk exponents pos^B mod (q-1); H0/H1 of the two-chunk Horner
-  DevBuf v_slot, v_nd, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+  DevBuf v_slot, v_nd, v_skip, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
 
   // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call
   mpvss_ctx() : scratch(24), pinned(8) {}

@@ -11,14 +11,15 @@ __global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner_kernel(Horne
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
   horner_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>,
-                   A.nd ? A.nd[blockIdx.x] : A.ndigits);
+                   A.nd ? A.nd[blockIdx.x] : A.ndigits, A.skip ? A.skip[blockIdx.x] : 0u);
 }
 
 template <int TPI>
 __global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner2_kernel(Horner2Args A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
-  horner2_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner2_smem_words<TPI>, A.nd[blockIdx.x]);
+  horner2_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner2_smem_words<TPI>, A.nd[blockIdx.x],
+                    A.skip ? A.skip[blockIdx.x] : 0u);
 }
 
 template <int TPI>

@@ -208,7 +208,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_e, &ctx->v_h})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_e, &ctx->v_h, &ctx->v_skip})
     b->release();
 }
 
@@ -264,6 +264,7 @@ int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint
 struct PosPlan {
   std::vector<uint32_t> pos, slot;  // padded instance arrays; slot 0xffffffff = padding
   std::vector<uint32_t> nd;         // base-4 digits per CTA
+  std::vector<uint32_t> skip;       // per CTA: bit s = digit s is zero for every instance of the CTA
 };
 static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
   std::vector<std::vector<uint32_t>> by(17);
@@ -286,15 +287,27 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
     }
     plan.nd.resize(plan.pos.size() / per_cta, d);
   }
+  // consecutive positions share their high digits, so a whole CTA (one warp) often has a zero digit
+  // in common; those window multiplications (by one) are skipped block-uniformly
+  plan.skip.assign(plan.nd.size(), 0);
+  for (size_t c = 0; c < plan.nd.size(); ++c) {
+    uint32_t mask = 0;
+    for (uint32_t s = 0; s + 1 < plan.nd[c]; ++s) {   // never the top digit (it seeds the accumulator)
+      bool all_zero = true;
+      for (size_t k = 0; k < per_cta; ++k) all_zero = all_zero && ((plan.pos[c * per_cta + k] >> (2 * s)) & 3u) == 0;
+      if (all_zero) mask |= 1u << s;
+    }
+    plan.skip[c] = mask;
+  }
   return MPVSS_OK;
 }
 
 // commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
 static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
-                      const uint32_t* slot, const uint32_t* nd, size_t n_padded, uint32_t* x) {
+                      const uint32_t* slot, const uint32_t* nd, const uint32_t* skip, size_t n_padded, uint32_t* x) {
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, x, (uint32_t)t,
+  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, skip, x, (uint32_t)t,
                      (uint32_t)n_padded, 0};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
   MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
@@ -332,7 +345,8 @@ static int dev_chunk_exponents(mpvss_ctx* ctx, const int64_t* positions, size_t 
 // Two-chunk form of dev_horner: H0, H1 side by side on every lane group, then
 // X = H0 * H1^(pos^B mod (q-1)) with the exponentiation kernel.
 static int dev_horner2(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
-                       const uint32_t* slot, const uint32_t* nd, size_t n_padded, size_t n, const uint32_t* e,
+                       const uint32_t* slot, const uint32_t* nd, const uint32_t* skip, size_t n_padded, size_t n,
+                       const uint32_t* e,
                        DevBuf& h, uint32_t* x) {
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
@@ -346,15 +360,16 @@ static int dev_horner2(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t 
     // the two halves as two concurrent launches of the single-chain kernel (twice the warps)
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0));
-    modp::HornerArgs A0{K, cm.as<uint32_t>(), pos, slot, nd, h0, B, (uint32_t)n_padded, 0};
-    modp::HornerArgs A1{K, cm.as<uint32_t>() + (size_t)B * EW, pos, slot, nd, h1, (uint32_t)t - B, (uint32_t)n_padded, 0};
+    modp::HornerArgs A0{K, cm.as<uint32_t>(), pos, slot, nd, skip, h0, B, (uint32_t)n_padded, 0};
+    modp::HornerArgs A1{K, cm.as<uint32_t>() + (size_t)B * EW, pos, slot, nd, skip, h1, (uint32_t)t - B,
+                        (uint32_t)n_padded, 0};
     MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A0, ctx->stream));
     MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A1, ctx->aux[1]));
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
     timing_launch(ctx);
   } else {
-    modp::Horner2Args A{K, cm.as<uint32_t>(), pos, slot, nd, h0, h1, (uint32_t)t, (uint32_t)n_padded, B};
+    modp::Horner2Args A{K, cm.as<uint32_t>(), pos, slot, nd, skip, h0, h1, (uint32_t)t, (uint32_t)n_padded, B};
     MPVSS_CUDA(ctx, modp::launch_horner2(ctx->modp_tpi, A, ctx->stream));
   }
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
@@ -374,16 +389,18 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
   MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), np * 4));
   MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), np * 4));
   MPVSS_TRY(h2d(ctx, dnd, plan.nd.data(), plan.nd.size() * 4));
+  DevBuf& dsk = ctx->buf(8);
+  MPVSS_TRY(h2d(ctx, dsk, plan.skip.data(), plan.skip.size() * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
   const bool dual = ctx->modp_dual && t >= 8;
   if (dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->buf(6)));
   timing_begin(ctx);
   if (dual)
     MPVSS_TRY(dev_horner2(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
-                          np, n, ctx->buf(6).as<uint32_t>(), ctx->buf(7), dout.as<uint32_t>()));
+                          dsk.as<uint32_t>(), np, n, ctx->buf(6).as<uint32_t>(), ctx->buf(7), dout.as<uint32_t>()));
   else
     MPVSS_TRY(dev_horner(ctx, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
-                         np, dout.as<uint32_t>()));
+                         dsk.as<uint32_t>(), np, dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
@@ -482,6 +499,7 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), ctx->v_np * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nd.data(), plan.nd.size() * 4));
+  MPVSS_TRY(h2d(ctx, ctx->v_skip, plan.skip.data(), plan.skip.size() * 4));
   MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
@@ -518,11 +536,12 @@ static int verify_kernels(mpvss_ctx* ctx) {
   // X_i from the commitments (participant.rs:423-434)
   if (ctx->v_dual)
     MPVSS_TRY(dev_horner2(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, n,
-                          ctx->v_e.as<uint32_t>(), ctx->v_h, X));
+                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
+                          n, ctx->v_e.as<uint32_t>(), ctx->v_h, X));
   else
     MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                         ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
+                         ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
+                         X));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
   // a1 = g^r * X^c
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,

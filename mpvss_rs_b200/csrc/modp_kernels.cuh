@@ -65,6 +65,8 @@ struct HornerArgs {
   const uint32_t* nd;      // base-4 digit count per CTA (all instances of a CTA share it; the launcher
                            // passes nd[blockIdx.x] so that the schedule is provably block-uniform and
                            // ptxas needs no WARPSYNC around the shuffles); nullptr: `ndigits` everywhere
+  const uint32_t* skip;    // per CTA: bit s set = base-4 digit s is zero for every instance of the CTA, so
+                           // the window multiplication (by one) is skipped; nullptr: never skip
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
   uint32_t t, n, ndigits;
 };
@@ -75,7 +77,7 @@ constexpr int horner_smem_words = 128 + (32 / TPI) * 256;
 // X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
 // integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
 template <int TPI>
-MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits) {
+MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits, uint32_t skip) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
   Lane ln = make_lane<TPI>();
@@ -112,7 +114,7 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
       sqr_inplace<TPI>(acc, sq, M, ln);
       sqr_inplace<TPI>(acc, sq, M, ln);
       d = (pos >> (2 * s)) & 3u;
-      mont_mul<TPI>(acc, acc, d ? tbl + (d - 1) * 64 : one, M, ln);
+      if (!((skip >> s) & 1u)) mont_mul<TPI>(acc, acc, d ? tbl + (d - 1) * 64 : one, M, ln);
     }
     mont_mul<TPI>(acc, acc, cbuf, M, ln);
   }
@@ -133,6 +135,7 @@ struct Horner2Args {
   const uint32_t* pos;
   const uint32_t* slot;
   const uint32_t* nd;      // per CTA, as in HornerArgs
+  const uint32_t* skip;    // per CTA, as in HornerArgs
   uint32_t* out0;          // H0, canonical, indexed by slot
   uint32_t* out1;          // H1
   uint32_t t, n, B;        // B = ceil(t / 2) >= 2
@@ -142,7 +145,7 @@ template <int TPI>
 constexpr int horner2_smem_words = 192 + (32 / TPI) * 512;
 
 template <int TPI>
-MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits) {
+MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits, uint32_t skip) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
   Lane ln = make_lane<TPI>();
@@ -193,7 +196,8 @@ MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint3
         mont_mul2<TPI>(acc0, acc0, sq0, acc1, acc1, sq1, M, ln);
       }
       d = (pos >> (2 * s)) & 3u;
-      mont_mul2<TPI>(acc0, acc0, d ? t0 + (d - 1) * 64 : one, acc1, acc1, d ? t1 + (d - 1) * 64 : one, M, ln);
+      if (!((skip >> s) & 1u))
+        mont_mul2<TPI>(acc0, acc0, d ? t0 + (d - 1) * 64 : one, acc1, acc1, d ? t1 + (d - 1) * 64 : one, M, ln);
     }
     mont_mul2<TPI>(acc0, acc0, cbuf0, acc1, acc1, cbuf1, M, ln);
   }

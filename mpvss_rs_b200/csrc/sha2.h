@@ -8,6 +8,10 @@
 
 namespace sha2 {
 
+// sha256_ni.cpp: x86 SHA-extension block function, selected at run time
+bool cpu_has_sha_ni();
+void sha256_ni_blocks(uint32_t state[8], const uint8_t* data, size_t nblocks);
+
 struct Sha256 {
   uint32_t h[8];
   uint8_t buf[64];
@@ -61,6 +65,12 @@ struct Sha256 {
       memcpy(buf + fill, p, take);
       fill += take; p += take; n -= take;
       if (fill == 64) { block(buf); fill = 0; }
+    }
+    if (n >= 64 && cpu_has_sha_ni()) {
+      size_t nb = n / 64;
+      sha256_ni_blocks(h, p, nb);
+      p += nb * 64;
+      n -= nb * 64;
     }
     while (n >= 64) { block(p); p += 64; n -= 64; }
     if (n) { memcpy(buf, p, n); fill = n; }

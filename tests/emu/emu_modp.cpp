@@ -37,18 +37,18 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
   }
 
 extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
-                               uint32_t n, uint32_t ndigits, uint32_t* out) {
-  modp::HornerArgs A{consts, cm, pos, nullptr, nullptr, out, t, n, ndigits};
+                               uint32_t n, uint32_t ndigits, uint32_t* out, const uint32_t* skip) {
+  modp::HornerArgs A{consts, cm, pos, nullptr, nullptr, nullptr, out, t, n, ndigits};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { modp::horner_body<T>(A, w, s, ndigits); }));
+                          [&](uint32_t w, uint32_t* s) { modp::horner_body<T>(A, w, s, ndigits, skip ? skip[w] : 0u); }));
   return 0;
 }
 
 extern "C" int emu_modp_horner2(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
                                 uint32_t n, const uint32_t* nd, uint32_t* out0, uint32_t* out1) {
-  modp::Horner2Args A{consts, cm, pos, nullptr, nullptr, out0, out1, t, n, (t + 1) / 2};
+  modp::Horner2Args A{consts, cm, pos, nullptr, nullptr, nullptr, out0, out1, t, n, (t + 1) / 2};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner2_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { modp::horner2_body<T>(A, w, s, nd[0]); }));
+                          [&](uint32_t w, uint32_t* s) { modp::horner2_body<T>(A, w, s, nd[0], 0u); }));
   return 0;
 }
 

@@ -9,9 +9,12 @@ _p, _s = ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t
 
 
 def build():
-    deps = [SRC, os.path.join(CSRC, "bigint.h"), os.path.join(CSRC, "sha2.h")]
+    ni = os.path.join(CSRC, "sha256_ni.cpp")
+    deps = [SRC, ni, os.path.join(CSRC, "bigint.h"), os.path.join(CSRC, "sha2.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", SO, SRC])
+        obj = os.path.join(HERE, "sha256_ni.o")
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-msha", "-msse4.1", "-mssse3", "-c", ni, "-o", obj])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", SO, SRC, obj])
     L = ctypes.CDLL(SO)
     L.hc_divmod.argtypes = [_p, _s, _p, _s, _p, _p, _s]
     L.hc_mulmod.argtypes = [_p, _s, _p, _s, _p, _s, _p, _s]

@@ -62,7 +62,17 @@ def test_horner_kernel_equals_reference_schedule(lib, tpi):
     pos = np.array(positions, dtype=np.uint32)
     n = len(positions)
     out = np.zeros(64 * n, dtype=np.uint32)
-    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, nd, eu.P(out)) == 0
+    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, nd, eu.P(out), None) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
+    # block-uniform skipping of window multiplications whose digit is zero for the whole warp
+    gpw = 32 // tpi
+    positions = [64 + k for k in range(gpw)] + [80 + 16 * 0 + k for k in range(gpw)]   # digits (1,0,0,x), (1,1,0,x)
+    pos = np.array(positions, dtype=np.uint32)
+    n = len(positions)
+    skip = np.array([0b0110 if gpw <= 4 else 0b0100, 0b0010 if gpw <= 4 else 0b0000], dtype=np.uint32)
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, 4, eu.P(out), eu.P(skip)) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
 
