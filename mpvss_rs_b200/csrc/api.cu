@@ -122,6 +122,10 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->ec_threads = (size_t)value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "modp_comb") {
+    ctx->modp_comb = value != 0;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "modp_overlap") {
     ctx->modp_overlap = value != 0;
     return MPVSS_OK;

@@ -70,7 +70,9 @@ struct mpvss_ctx {
                       // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
-  DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4
+  DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4, [128,192) one
+  DevBuf comb[2];            // fixed-base tables of the two generators (built on first use, 16.8 MB each)
+  int modp_comb = 1;         // use them ("modp_comb")
   // ---- elliptic-curve groups ----
   size_t ec_threads = 65536;    // target thread count of the chunked Horner launch ("ec_threads")
   DevBuf ec_consts;             // secp::Consts / rist::Consts
@@ -83,6 +85,7 @@ struct mpvss_ctx {
   uint32_t v_rwin = 0, v_cwin = 0;
   size_t v_np = 0;  // padded instance count of the Horner launch
   std::vector<uint8_t> v_challenge, v_y_host;
+  const uint32_t* v_comb = nullptr;  // fixed-base table of g for a1 = g^r * X^c
   bool v_dual = false;
   DevBuf v_e, v_h;  // chunk exponents pos^B mod (q-1); H0/H1 of the two-chunk Horner
   DevBuf v_slot, v_nd, v_skip, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;

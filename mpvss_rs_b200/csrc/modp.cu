@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) exp2_kernel(Exp2Args A) {
 }
 
 template <int TPI>
+__global__ void __launch_bounds__(32) comb1_kernel(CombArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  comb1_body<TPI>(A, blockIdx.x, smem);
+}
+template <int TPI>
+__global__ void __launch_bounds__(32) comb2_kernel(CombArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  comb2_body<TPI>(A, blockIdx.x, smem);
+}
+
+template <int TPI>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) mul_kernel(MulArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
@@ -86,6 +97,15 @@ cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
     cudaError_t e = set_smem(exp2_kernel<T>, sm);
     if (e != cudaSuccess) return e;
     exp2_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s) {
+  MODP_DISPATCH(tpi, {
+    size_t sm = comb_smem_words<T> * 4;
+    comb1_kernel<T><<<1, 32, sm, s>>>(A);
+    comb2_kernel<T><<<(A.rows + 32 / T - 1) / (32 / T), 32, sm, s>>>(A);
   });
   return cudaGetLastError();
 }

@@ -114,8 +114,8 @@ int sync(mpvss_ctx* ctx) {
 // device-pointer exponentiation:  out = b1^e1 [* b2^e2]
 int dev_exp2(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s,
-             uint32_t e2w, size_t n, uint32_t* out, cudaStream_t stream = nullptr) {
-  modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w};
+             uint32_t e2w, size_t n, uint32_t* out, cudaStream_t stream = nullptr, const uint32_t* comb1 = nullptr) {
+  modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w, comb1};
   MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, stream ? stream : ctx->stream));
   timing_launch(ctx);
   return MPVSS_OK;
@@ -125,6 +125,21 @@ int dev_mul(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* a, uint32_t 
   modp::MulArgs A{consts, a, b, out, (uint32_t)n, mode, as, bs};
   MPVSS_CUDA(ctx, modp::launch_mul(ctx->modp_tpi, A, ctx->stream));
   timing_launch(ctx);
+  return MPVSS_OK;
+}
+
+// fixed-base table of generator `which` (0: G = 2, 1: g = 4), built on first use; nullptr when disabled
+int comb_table(mpvss_ctx* ctx, int which, const uint32_t** out) {
+  *out = nullptr;
+  if (!ctx->modp_comb) return MPVSS_OK;
+  DevBuf& t = ctx->comb[which];
+  if (!t.p) {
+    MPVSS_CUDA(ctx, t.ensure((size_t)256 * 256 * EB));
+    modp::CombArgs A{ctx->consts_q.as<uint32_t>(), ctx->gens.as<uint32_t>() + which * 64, t.as<uint32_t>(), 256};
+    MPVSS_CUDA(ctx, modp::launch_comb_build(ctx->modp_tpi, A, ctx->stream));
+    MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *out = t.as<uint32_t>();
   return MPVSS_OK;
 }
 
@@ -207,7 +222,7 @@ int init(mpvss_ctx* ctx) {
 }
 
 void destroy(mpvss_ctx* ctx) {
-  for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
+  for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->comb[0], &ctx->comb[1], &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
                     &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_e, &ctx->v_h, &ctx->v_skip})
     b->release();
 }
@@ -234,10 +249,12 @@ int fixed_base_exp(mpvss_ctx* ctx, int generator, const uint8_t* scalars, size_t
   DevBuf &de = ctx->buf(1), &dout = ctx->buf(2);
   MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  const uint32_t* comb;
+  MPVSS_TRY(comb_table(ctx, generator ? 1 : 0, &comb));
   timing_begin(ctx);
   MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), ctx->gens.as<uint32_t>() + (generator ? 64 : 0), 0,
                      de.as<uint32_t>(), EW, windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n,
-                     dout.as<uint32_t>()));
+                     dout.as<uint32_t>(), nullptr, comb));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
@@ -422,9 +439,15 @@ int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, con
   MPVSS_CUDA(ctx, da2.ensure(n * EB));
   uint32_t rw = windows_for(r, EB, n), cw = windows_for(c, EB, c_stride ? n : 1), cs = c_stride ? EW : 0;
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  const uint32_t* comb = nullptr;  // g1 is usually one of the two generators: use its table
+  {
+    bool rest_zero = true;
+    for (size_t i = 1; i < EB; ++i) rest_zero = rest_zero && g1[i] == 0;
+    if (rest_zero && (g1[0] == 2 || g1[0] == 4)) MPVSS_TRY(comb_table(ctx, g1[0] == 4 ? 1 : 0, &comb));
+  }
   timing_begin(ctx);
   MPVSS_TRY(dev_exp2(ctx, K, dg1.as<uint32_t>(), 0, dr.as<uint32_t>(), EW, rw, dh1.as<uint32_t>(), EW,
-                     dc.as<uint32_t>(), cs, cw, n, da1.as<uint32_t>()));
+                     dc.as<uint32_t>(), cs, cw, n, da1.as<uint32_t>(), nullptr, comb));
   MPVSS_TRY(dev_exp2(ctx, K, dg2.as<uint32_t>(), EW, dr.as<uint32_t>(), EW, rw, dh2.as<uint32_t>(), EW,
                      dc.as<uint32_t>(), cs, cw, n, da2.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
@@ -507,6 +530,7 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   MPVSS_CUDA(ctx, ctx->v_x.ensure(n * EB));
   MPVSS_CUDA(ctx, ctx->v_a1.ensure(n * EB));
   MPVSS_CUDA(ctx, ctx->v_a2.ensure(n * EB));
+  MPVSS_TRY(comb_table(ctx, 1, &ctx->v_comb));
   ctx->v_dual = ctx->modp_dual && t >= 8;
   if (ctx->v_dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->v_e));
   ctx->v_rwin = windows_for(responses, EB, n);
@@ -543,9 +567,9 @@ static int verify_kernels(mpvss_ctx* ctx) {
                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
                          X));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-  // a1 = g^r * X^c
+  // a1 = g^r * X^c  (g^r from the fixed-base table)
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
-                     ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>()));
+                     ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>(), nullptr, ctx->v_comb));
   MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // X_i (with a2 underneath)
@@ -646,22 +670,28 @@ int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t
   MPVSS_CUDA(ctx, dC.ensure(t * EB));
   MPVSS_CUDA(ctx, dGs.ensure(EB));
   uint32_t cw = windows_for(coeffs, EB, t), pw = windows_for(p.data(), EB, n), ww = windows_for(witnesses, EB, n);
+  const uint32_t *combG, *combg;
+  MPVSS_TRY(comb_table(ctx, 0, &combG));
+  MPVSS_TRY(comb_table(ctx, 1, &combg));
   timing_begin(ctx);
   // C_j = g^a_j (participant.rs:189-193)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dco.as<uint32_t>(), EW, cw, nullptr, 0, nullptr, 0, 0, t, dC.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dco.as<uint32_t>(), EW, cw, nullptr, 0, nullptr, 0, 0, t, dC.as<uint32_t>(),
+                     nullptr, combg));
   // X_i = prod_j C_j^(i^j) = g^P(i): the dealer knows P, one fixed-base exponentiation
   // gives the same group element as the reference's t-term product (participant.rs:207-215)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n, dX.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n, dX.as<uint32_t>(),
+                     nullptr, combg));
   // Y_i = y_i^P(i) (participant.rs:219)
   MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n,
                      dY.as<uint32_t>()));
   // a1 = g^w, a2 = y^w (participant.rs:236-237)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>(),
+                     nullptr, combg));
   MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
                      dA2.as<uint32_t>()));
   // G^s (participant.rs:268)
   MPVSS_TRY(dev_exp2(ctx, K, G, 0, ds.as<uint32_t>(), EW, windows_for(s_le, EB, 1), nullptr, 0, nullptr, 0, 0, 1,
-                     dGs.as<uint32_t>()));
+                     dGs.as<uint32_t>(), nullptr, combG));
   MPVSS_TRY(timing_end(ctx));
   std::vector<uint8_t> X(n * EB), A1(n * EB), A2(n * EB);
   uint8_t gs[EB];
@@ -745,14 +775,18 @@ int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const 
   }
   MPVSS_TRY(h2d(ctx, dinv, inv.data(), n * EB));
   uint32_t skw = windows_for(private_keys, EB, n), ww = windows_for(witnesses, EB, n);
+  const uint32_t* combG;
+  MPVSS_TRY(comb_table(ctx, 0, &combG));
   float ms0 = ctx->last_ms;
   int l0 = ctx->last_launches;
   timing_begin(ctx);
   // pk = G^sk (participant.rs:306), S = Y^(1/sk) (:316), a1 = G^w, a2 = S^w (:331-332)
-  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dsk.as<uint32_t>(), EW, skw, nullptr, 0, nullptr, 0, 0, n, dpk.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dsk.as<uint32_t>(), EW, skw, nullptr, 0, nullptr, 0, 0, n, dpk.as<uint32_t>(),
+                     nullptr, combG));
   MPVSS_TRY(dev_exp2(ctx, K, dY.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 512, nullptr, 0, nullptr, 0, 0, n,
                      dS.as<uint32_t>()));
-  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>()));
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>(),
+                     nullptr, combG));
   MPVSS_TRY(dev_exp2(ctx, K, dS.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
                      dA2.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));

@@ -219,6 +219,8 @@ struct Exp2Args {
   uint32_t n;
   uint32_t b1_stride, e1_stride, e1_windows;  // windows of 4 bits, counted from bit 0
   uint32_t b2_stride, e2_stride, e2_windows;
+  const uint32_t* comb1;  // optional fixed-base table for b1 (CombArgs layout): b1^e1 becomes a product of
+                          // ceil(e1_windows / 2) table entries, no squarings (b1 is then ignored)
 };
 
 template <int TPI>
@@ -255,6 +257,80 @@ MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, co
   }
 }
 
+// Fixed-base exponentiation from a precomputed table: tbl[(w * 256 + d) * 64] = base^(d * 2^(8w)) in
+// Montgomery form (d = 0: Montgomery one), so base^e = prod_w tbl[w][byte_w(e)].  Entries are staged
+// through shared memory so that the Montgomery product reads its operand from there.
+template <int TPI>
+MP_DEV void exp_comb8(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* tbl, const uint32_t* e, uint32_t nbytes,
+                      uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t d = e[0] & 0xffu;
+  load_slice<TPI>(acc, tbl + (size_t)d * 64, ln);
+  for (uint32_t w = 1; w < nbytes; ++w) {
+    d = (e[w >> 2] >> ((w & 3u) * 8)) & 0xffu;
+    uint32_t x[L];
+    load_slice<TPI>(x, tbl + ((size_t)w * 256 + d) * 64, ln);
+    stage<TPI>(sq, x, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, sq, M, ln);
+  }
+}
+
+// Table construction.  Step 1 (one lane group): tbl[w][1] = base^(2^(8w)) for w = 0..255.
+struct CombArgs {
+  const uint32_t* consts;
+  const uint32_t* base;  // 64 limbs, normal form
+  uint32_t* tbl;         // rows * 256 * 64 limbs
+  uint32_t rows;         // byte positions covered (256 for full 2048-bit exponents)
+};
+template <int TPI>
+constexpr int comb_smem_words = 64 + (32 / TPI) * 128;
+
+template <int TPI>
+MP_DEV void comb1_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* r2 = wsm;
+  uint32_t* sq = wsm + 64 + gi * 128;
+  warp_copy64(r2, A.consts + C_R2);
+  simt::syncwarp();
+  uint32_t b[L];
+  load_slice<TPI>(b, A.base, ln);
+  mont_mul<TPI>(b, b, r2, M, ln);
+  for (uint32_t w = 0; w < A.rows; ++w) {
+    if (wg == 0 && gi == 0) stage<TPI>(A.tbl + ((size_t)w * 256 + 1) * 64, b, ln);
+    for (int k = 0; k < 8; ++k) sqr_inplace<TPI>(b, sq, M, ln);
+  }
+}
+// Step 2 (lane group w): tbl[w][0] = one, tbl[w][d] = tbl[w][d-1] * tbl[w][1].
+template <int TPI>
+MP_DEV void comb2_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t w = wg * GPW + gi;
+  const bool live = w < A.rows;
+  if (!live) w = A.rows - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* b1 = wsm + 64 + gi * 128;
+  uint32_t* row = A.tbl + (size_t)w * 256 * 64;
+  uint32_t x[L];
+  load_slice<TPI>(x, A.consts + C_ONE, ln);
+  if (live) stage<TPI>(row, x, ln);
+  load_slice<TPI>(x, row + 64, ln);
+  stage<TPI>(b1, x, ln);
+  simt::syncwarp();
+  for (uint32_t d = 2; d < 256; ++d) {
+    mont_mul<TPI>(x, x, b1, M, ln);
+    if (live) stage<TPI>(row + (size_t)d * 64, x, ln);
+  }
+}
+
 // out_i = b1_i^e1_i [* b2_i^e2_i]  (fixed 4-bit windows; the window count is a launch
 // parameter, so every group of every warp runs the same schedule).
 template <int TPI>
@@ -274,8 +350,11 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
   warp_copy64(r2, A.consts + C_R2);
   simt::syncwarp();
   uint32_t acc[L];
-  exp_window4<TPI>(acc, A.b1 + (size_t)inst * A.b1_stride, A.e1 + (size_t)inst * A.e1_stride, A.e1_windows, tbl, sq,
-                   r2, A.consts, M, ln);
+  if (A.comb1)
+    exp_comb8<TPI>(acc, A.comb1, A.e1 + (size_t)inst * A.e1_stride, (A.e1_windows + 1) / 2, sq, M, ln);
+  else
+    exp_window4<TPI>(acc, A.b1 + (size_t)inst * A.b1_stride, A.e1 + (size_t)inst * A.e1_stride, A.e1_windows, tbl,
+                     sq, r2, A.consts, M, ln);
   if (A.b2 != nullptr) {
     uint32_t acc2[L];
     exp_window4<TPI>(acc2, A.b2 + (size_t)inst * A.b2_stride, A.e2 + (size_t)inst * A.e2_stride, A.e2_windows, tbl,

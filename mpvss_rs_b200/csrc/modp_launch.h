@@ -10,5 +10,6 @@ constexpr int HORNER_WARPS_PER_CTA = 1;  // Horner kernels: one warp per CTA kee
 cudaError_t launch_horner(int tpi, const HornerArgs& A, cudaStream_t s);
 cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s);
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s);
+cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s);
 cudaError_t launch_mul(int tpi, const MulArgs& A, cudaStream_t s);
 }  // namespace modp

@@ -54,8 +54,8 @@ extern "C" int emu_modp_horner2(int tpi, const uint32_t* consts, const uint32_t*
 
 extern "C" int emu_modp_exp2(int tpi, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
                              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2,
-                             uint32_t e2s, uint32_t e2w, uint32_t n, uint32_t* out) {
-  modp::Exp2Args A{consts, b1, e1, b2, e2, out, n, b1s, e1s, e1w, b2s, e2s, e2w};
+                             uint32_t e2s, uint32_t e2w, uint32_t n, uint32_t* out, const uint32_t* comb) {
+  modp::Exp2Args A{consts, b1, e1, b2, e2, out, n, b1s, e1s, e1w, b2s, e2s, e2w, comb};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::exp2_smem_words<T>,
                           [&](uint32_t w, uint32_t* s) { modp::exp2_body<T>(A, w, s); }));
   return 0;
@@ -66,5 +66,16 @@ extern "C" int emu_modp_mul(int tpi, const uint32_t* consts, const uint32_t* a, 
   modp::MulArgs A{consts, a, b, out, n, mode, as, bs};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::mul_smem_words<T>,
                           [&](uint32_t w, uint32_t* s) { modp::mul_body<T>(A, w, s); }));
+  return 0;
+}
+
+// fixed-base table: only the first `rows` byte positions are filled (step 1 is cut short by the test)
+extern "C" int emu_modp_comb_build(int tpi, const uint32_t* consts, const uint32_t* base, uint32_t* tbl,
+                                   uint32_t rows) {
+  modp::CombArgs A{consts, base, tbl, rows};
+  DISPATCH(tpi, {
+    run_warps(1, modp::comb_smem_words<T>, [&](uint32_t w, uint32_t* s) { modp::comb1_body<T>(A, w, s); });
+    run_warps(warps_for<T>(rows), modp::comb_smem_words<T>, [&](uint32_t w, uint32_t* s) { modp::comb2_body<T>(A, w, s); });
+  });
   return 0;
 }

@@ -93,10 +93,36 @@ def test_exp2_kernel(lib, tpi):
     E2 = np.concatenate([eu.to_limbs(x, 8) for x in e2])
     out = np.zeros(64 * n, dtype=np.uint32)
     assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(B1), 64, eu.P(E1), 64, 24, eu.P(B2), 64, eu.P(E2), 8, 10, n,
-                             eu.P(out)) == 0
+                             eu.P(out), None) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(b1[i], e1[i], Q) * pow(b2[i], e2[i], Q) % Q
     # single exponentiation with one shared base (stride 0)
-    assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(B1), 0, eu.P(E1), 64, 24, None, 0, None, 0, 0, n, eu.P(out)) == 0
+    assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(B1), 0, eu.P(E1), 64, 24, None, 0, None, 0, 0, n, eu.P(out), None) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(b1[0], e1[i], Q)
+
+
+def test_fixed_base_comb(lib):
+    """Fixed-base table (8-bit comb) and the exponentiation that consumes it: g^e = prod_w T[w][byte_w(e)]."""
+    C = eu.consts_block(Q)
+    rng = random.Random(12)
+    rows = 6                                        # exponents below 2^48 keep the emulated build short
+    tbl = np.zeros(rows * 256 * 64, dtype=np.uint32)
+    assert lib.emu_modp_comb_build(8, eu.P(C), eu.P(eu.to_limbs(4)), eu.P(tbl), rows) == 0
+    for w, d in [(0, 0), (0, 1), (0, 255), (1, 1), (3, 200), (5, 255)]:
+        got = eu.from_limbs(tbl[(w * 256 + d) * 64:(w * 256 + d) * 64 + 64])
+        assert got == pow(4, d << (8 * w), Q) * R % Q, (w, d)
+    n = 5
+    e1 = [rng.getrandbits(48) for _ in range(n)]
+    e1[0], e1[1], e1[2] = 0, 1, (1 << 48) - 1
+    b2 = [rng.randrange(Q) for _ in range(n)]
+    e2 = [rng.getrandbits(32) for _ in range(n)]
+    E1 = np.concatenate([eu.to_limbs(x) for x in e1])
+    B2 = np.concatenate([eu.to_limbs(x) for x in b2])
+    E2 = np.concatenate([eu.to_limbs(x, 8) for x in e2])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    for tpi in (8, 16):
+        assert lib.emu_modp_exp2(tpi, eu.P(C), eu.P(E1), 0, eu.P(E1), 64, 12, eu.P(B2), 64, eu.P(E2), 8, 8, n,
+                                 eu.P(out), eu.P(tbl)) == 0
+        for i in range(n):
+            assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(4, e1[i], Q) * pow(b2[i], e2[i], Q) % Q, (tpi, i)
