@@ -127,7 +127,7 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     return MPVSS_OK;
   }
   if (std::string(key) == "modp_overlap") {
-    ctx->modp_overlap = value != 0;
+    ctx->modp_overlap = value;
     return MPVSS_OK;
   }
   if (std::string(key) == "modp_dual") {

@@ -65,7 +65,7 @@ struct mpvss_ctx {
 
   // ---- ModpGroup ----
   int modp_tpi = 8;
-  int modp_overlap = 0;  // run the X-independent a2 launch on a side stream underneath the Horner kernel
+  int modp_overlap = 0;  // 2: issue the X-independent a2 launch on a side stream right after the Horner launch
   int modp_dual = 0;  // two-chunk Horner: 0 off (default: fastest whole step), 1 two interleaved chains per lane
                       // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
@@ -73,6 +73,7 @@ struct mpvss_ctx {
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4, [128,192) one
   DevBuf comb[2];            // fixed-base tables of the two generators (built on first use, 16.8 MB each)
   int modp_comb = 1;         // use them ("modp_comb")
+  bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----
   size_t ec_threads = 65536;    // target thread count of the chunked Horner launch ("ec_threads")
   DevBuf ec_consts;             // secp::Consts / rist::Consts

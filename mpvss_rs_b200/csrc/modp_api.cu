@@ -210,6 +210,7 @@ int init(mpvss_ctx* ctx) {
   ctx->g = big::shr1(ctx->qm1);
   std::vector<uint32_t> blk(modp::C_WORDS);
   fill_consts(ctx->q, blk.data());
+  ctx->modp_np1 = blk[modp::C_NP] == 1u;
   MPVSS_TRY(h2d(ctx, ctx->consts_q, blk.data(), blk.size() * 4));
   fill_consts(ctx->g, blk.data());
   MPVSS_TRY(h2d(ctx, ctx->consts_g, blk.data(), blk.size() * 4));
@@ -327,7 +328,7 @@ static int dev_horner(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t t
   modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, skip, x, (uint32_t)t,
                      (uint32_t)n_padded, 0};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
-  MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->stream));
+  MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A, ctx->modp_np1, ctx->stream));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
   timing_launch(ctx);
   return MPVSS_OK;
@@ -380,8 +381,8 @@ static int dev_horner2(mpvss_ctx* ctx, const uint32_t* comm, DevBuf& cm, size_t 
     modp::HornerArgs A0{K, cm.as<uint32_t>(), pos, slot, nd, skip, h0, B, (uint32_t)n_padded, 0};
     modp::HornerArgs A1{K, cm.as<uint32_t>() + (size_t)B * EW, pos, slot, nd, skip, h1, (uint32_t)t - B,
                         (uint32_t)n_padded, 0};
-    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A0, ctx->stream));
-    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A1, ctx->aux[1]));
+    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A0, ctx->modp_np1, ctx->stream));
+    MPVSS_CUDA(ctx, modp::launch_horner(ctx->modp_tpi, A1, ctx->modp_np1, ctx->aux[1]));
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
     timing_launch(ctx);
@@ -548,15 +549,18 @@ static int verify_kernels(mpvss_ctx* ctx) {
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   uint32_t* X = ctx->v_x.as<uint32_t>();
   timing_begin(ctx);
-  // a2 = y^r * Y^c does not depend on X: it runs on a side stream underneath the Horner kernel,
-  // whose lanes leave issue slots free (dleq.rs:66-84)
-  cudaStream_t side = ctx->modp_overlap ? ctx->aux[0] : ctx->stream;
+  // a2 = y^r * Y^c does not depend on X.  modp_overlap = 0: it runs first on the main stream;
+  // 2: it is issued on a side stream right AFTER the Horner launch, so its CTAs only fill what the
+  // already resident Horner warps leave idle (issuing it first lets it claim SMs and unbalances the
+  // placement of the long-running Horner CTAs -- measured 40 % slower -- hence no mode 1)
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-  MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
-  MPVSS_TRY(dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
-                     ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
-                     ctx->v_a2.as<uint32_t>(), side));
-  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+  auto launch_a2 = [&](cudaStream_t s) {
+    return dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
+                    ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
+                    ctx->v_a2.as<uint32_t>(), s);
+  };
+  const bool side = ctx->modp_overlap == 2;
+  if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
   if (ctx->v_dual)
     MPVSS_TRY(dev_horner2(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
@@ -566,11 +570,16 @@ static int verify_kernels(mpvss_ctx* ctx) {
     MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
                          X));
+  if (side) {
+    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+    MPVSS_TRY(launch_a2(ctx->aux[0]));
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+  }
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
   // a1 = g^r * X^c  (g^r from the fixed-base table)
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
                      ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>(), nullptr, ctx->v_comb));
-  MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+  if (side) MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
   MPVSS_TRY(timing_end(ctx));
   MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // X_i (with a2 underneath)
   MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));  // remaining DLEQ work

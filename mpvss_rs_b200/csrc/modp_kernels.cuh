@@ -76,7 +76,9 @@ constexpr int horner_smem_words = 128 + (32 / TPI) * 256;
 
 // X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
 // integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
-template <int TPI>
+// NP1: the modulus satisfies -q^-1 = 1 mod 2^32 (true for the RFC 3526 prime, whose low 64 bits are all
+// ones), so the Montgomery digit is the low limb itself and one multiply leaves the per-digit critical path.
+template <int TPI, bool NP1 = false>
 MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits, uint32_t skip) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
@@ -87,6 +89,7 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   if (!live) inst = A.n - 1;
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
+  if (NP1) M.np = 1u;
   uint32_t* cbuf = wsm;
   uint32_t* one = wsm + 64;
   uint32_t* tbl = wsm + 128 + gi * 256;  // tbl[0..2] = X, X^2, X^3 ; tbl + 192 = squaring stage

@@ -7,7 +7,7 @@ namespace modp {
 constexpr int WARPS_PER_CTA = 4;     // exponentiation / multiplication kernels
 constexpr int HORNER_WARPS_PER_CTA = 1;  // Horner kernels: one warp per CTA keeps the per-CTA digit classes
                                          // fine-grained and lets the block scheduler spread warps evenly
-cudaError_t launch_horner(int tpi, const HornerArgs& A, cudaStream_t s);
+cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStream_t s);
 cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s);
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s);
 cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s);

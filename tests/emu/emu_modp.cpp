@@ -38,9 +38,11 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
 
 extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
                                uint32_t n, uint32_t ndigits, uint32_t* out, const uint32_t* skip) {
+  const bool np1 = consts[modp::C_NP] == 1u;
   modp::HornerArgs A{consts, cm, pos, nullptr, nullptr, nullptr, out, t, n, ndigits};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { modp::horner_body<T>(A, w, s, ndigits, skip ? skip[w] : 0u); }));
+                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, ndigits, skip ? skip[w] : 0u);
+                            else modp::horner_body<T, false>(A, w, s, ndigits, skip ? skip[w] : 0u); }));
   return 0;
 }
 
