@@ -10,7 +10,10 @@ static inline unsigned blocks(uint32_t n) { return (n + TPB - 1) / TPB; }
 
 template <class Cv> __global__ void __launch_bounds__(TPB) exp2_kernel(Exp2Args<Cv> A) { exp2_body<Cv>(A, TID); }
 template <class Cv> __global__ void __launch_bounds__(TPB) decode_kernel(DecodeArgs<Cv> A) { decode_body<Cv>(A, TID); }
-template <class Cv> __global__ void __launch_bounds__(TPB) horner_kernel(HornerArgs<Cv> A) { horner_body<Cv>(A, TID); }
+#ifndef EC_HORNER_MIN_BLOCKS
+#define EC_HORNER_MIN_BLOCKS 4
+#endif
+template <class Cv> __global__ void __launch_bounds__(TPB, EC_HORNER_MIN_BLOCKS) horner_kernel(HornerArgs<Cv> A) { horner_body<Cv>(A, TID); }
 template <class Cv> __global__ void __launch_bounds__(TPB) sum_kernel(SumArgs<Cv> A) { sum_body<Cv>(A, TID); }
 template <class Cv> __global__ void __launch_bounds__(TPB) add_kernel(AddArgs<Cv> A) { add_body<Cv>(A, TID); }
 __global__ void __launch_bounds__(TPB) poly_kernel(PolyArgs A) { poly_body(A, TID); }

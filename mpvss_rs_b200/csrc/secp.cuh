@@ -23,12 +23,12 @@ using fp256::load;
 using fp256::neg;
 using fp256::store;
 using fp256::sub;
-MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
+MP_NOINLINE Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
   uint32_t t[16];
   fpsp::mul_wide(t, a, b);
   return fpsp::secp_reduce(t, P.m);
 }
-MP_DEV Fe sqr(const Fe& a, const Modulus& P) {
+MP_NOINLINE Fe sqr(const Fe& a, const Modulus& P) {
   uint32_t t[16];
   fpsp::sqr_wide(t, a);
   return fpsp::secp_reduce(t, P.m);
