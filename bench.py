@@ -301,6 +301,8 @@ def main():
     out_all = torch.empty((world, 3, n, eb), dtype=torch.uint8, device="cuda") if world > 1 else None
     out_host = torch.empty((world, 3, n, eb), dtype=torch.uint8).pin_memory() if world > 1 else None
     x_chk = buf(size=n * eb)
+    shares_all, chal_all = buf(box["shares"]), buf(box["challenge"])
+    import numpy as np
 
     PH = 2 if args.group == "modp" else 0   # phase index of the dominant (Horner) launch
 
@@ -322,10 +324,11 @@ def main():
         res = 1
         if rank == 0:
             out_host.copy_(out_all, non_blocking=False)
-            xs, a1s, a2s = interleave(out_host.numpy(), world, 3, n, eb)
-            group.ctx.check(lib.mpvss_transcript_check(h, n_total, ptr(buf(xs)), ptr(buf(box["shares"])),
-                                                       ptr(buf(a1s)), ptr(buf(a2s)), ptr(buf(box["challenge"])),
-                                                       ctypes.byref(ok), None))
+            # [rank, kind, j, eb] -> [kind, j, rank, eb]: participant j*N + rank, one copy, no Python bytes
+            arr = np.ascontiguousarray(out_host.numpy().reshape(world, 3, n, eb).transpose(1, 2, 0, 3))
+            u8 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+            group.ctx.check(lib.mpvss_transcript_check(h, n_total, u8(arr[0]), ptr(shares_all), u8(arr[1]), u8(arr[2]),
+                                                       ptr(chal_all), ctypes.byref(ok), None))
             res = ok.value
         return res, kms, p0
 

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) mul_kernel(MulArgs A) {
   mul_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * mul_smem_words<TPI>);
 }
 
+__global__ void __launch_bounds__(64) poly_kernel(PolyArgs A) { poly_body(A, blockIdx.x * 64 + threadIdx.x); }
+
 template <int TPI>
 static uint32_t ctas_for(uint32_t n) {
   uint32_t per_cta = WARPS_PER_CTA * (32 / TPI);
@@ -105,6 +107,12 @@ cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     exp2_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
   });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s) {
+  if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
+  poly_kernel<<<(A.n + 63) / 64, 64, 0, s>>>(A);
   return cudaGetLastError();
 }
 

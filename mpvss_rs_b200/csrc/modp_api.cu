@@ -9,7 +9,6 @@
 //   responses                     participant.rs:255-264, modp.rs:180-192
 //   U mask                        participant.rs:267-272, 512-518
 //   Lagrange exponents            participant.rs:526-561, util.rs:47-64
-#include <thread>
 #include "ctx.h"
 #include "modp_launch.h"
 #include "sha2.h"
@@ -146,58 +145,6 @@ int comb_table(mpvss_ctx* ctx, int which, const uint32_t** out) {
 int check_args(mpvss_ctx* ctx, bool ok, const char* what) {
   if (!ok) return mpvss_fail(ctx, MPVSS_ERR_ARG, what);
   return MPVSS_OK;
-}
-
-// P(x) mod (q-1) for x = first..first+count-1 by Horner with lazy reduction.  q-1 has an
-// all-ones top limb, so floor(acc / 2^2048) is the quotient estimate and
-// acc - hi*2^2048 + hi*delta (delta = 2^2048 - (q-1)) keeps acc below 2^2048 + 2^2002.
-// Equals Polynomial::get_value(x) % order (polynomial.rs:50-58, participant.rs:202).
-void poly_eval_range(const uint32_t* coeffs, size_t t, const uint32_t* order, const int64_t* positions, size_t first,
-                     size_t count, uint8_t* out) {
-  uint32_t delta[EW];
-  {
-    uint64_t br = 0;
-    for (size_t i = 0; i < EW; ++i) {  // 2^2048 - order
-      uint64_t d = (uint64_t)0 - order[i] - br;
-      delta[i] = (uint32_t)d;
-      br = (d >> 32) & 1;
-    }
-  }
-  for (size_t idx = first; idx < first + count; ++idx) {
-    uint64_t x = (uint64_t)(positions ? positions[idx] : (int64_t)idx + 1);
-    uint32_t acc[EW + 2] = {0};
-    for (size_t j = t; j-- > 0;) {
-      // acc = acc * x + a_j   (x < 2^32 assumed by the caller)
-      uint64_t c = 0;
-      const uint32_t* a = coeffs + j * EW;
-      for (size_t i = 0; i < EW; ++i) {
-        c += (uint64_t)acc[i] * x + a[i];
-        acc[i] = (uint32_t)c;
-        c >>= 32;
-      }
-      c += (uint64_t)acc[EW] * x;
-      // fold everything at or above 2^2048 back: hi * delta
-      for (int round = 0; round < 2; ++round) {
-        uint64_t hi = c;
-        if (!hi) break;
-        uint64_t cc = 0;
-        for (size_t i = 0; i < EW; ++i) {
-          unsigned __int128 p = (unsigned __int128)hi * delta[i] + acc[i] + cc;
-          acc[i] = (uint32_t)p;
-          cc = (uint64_t)(p >> 32);
-        }
-        c = cc;
-      }
-      acc[EW] = (uint32_t)c;
-    }
-    // final canonical reduction
-    big::Int v(acc, acc + EW + 1);
-    big::trim(v);
-    big::Int m(order, order + EW);
-    big::trim(m);
-    v = big::mod(v, m);
-    big::to_le(v, out + idx * EB, EB);
-  }
 }
 
 }  // namespace
@@ -644,24 +591,12 @@ int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t
                                 commitments_out && shares_out && challenge_out && responses_out && u_out &&
                                 secret_len <= EB,
                        "distribute: bad arguments (threshold <= n, participant.rs:166)"));
-  std::vector<uint32_t> order(EW, 0);
+  std::vector<uint32_t> order(EW, 0), pos(n);
   for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
-  // p_i = P(i) mod (q-1) on the host cores (participant.rs:202); index 0 of `pz` is P(0)
+  if (order[EW - 1] != 0xffffffffu)
+    return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, "distribute: scalar kernel needs an order with an all-ones top limb");
+  for (size_t i = 0; i < n; ++i) pos[i] = (uint32_t)(i + 1);
   std::vector<uint8_t> p(n * EB);
-  {
-    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-    std::vector<std::thread> th;
-    size_t chunk = (n + nt - 1) / nt;
-    for (unsigned k = 0; k < nt; ++k) {
-      size_t first = k * chunk;
-      if (first >= n) break;
-      size_t count = std::min(chunk, n - first);
-      th.emplace_back([&, first, count] {
-        poly_eval_range(reinterpret_cast<const uint32_t*>(coeffs), t, order.data(), nullptr, first, count, p.data());
-      });
-    }
-    for (auto& x : th) x.join();
-  }
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   const uint32_t* G = ctx->gens.as<uint32_t>();
   DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dw = ctx->buf(2), &dpk = ctx->buf(3), &dC = ctx->buf(4),
@@ -671,7 +606,18 @@ int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t
   big::to_le(big::mod(big::from_le(coeffs, EB), ctx->qm1), s_le, EB);
   DevBuf& ds = ctx->buf(10);
   MPVSS_TRY(h2d(ctx, dco, coeffs, t * EB));
-  MPVSS_TRY(h2d(ctx, dp, p.data(), n * EB));
+  MPVSS_CUDA(ctx, dp.ensure(n * EB));
+  {
+    // p_i = P(i) mod (q-1) (participant.rs:202), one position per thread
+    DevBuf &dord = ctx->buf(11), &dpos = ctx->buf(12);
+    MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
+    MPVSS_TRY(h2d(ctx, dpos, pos.data(), n * 4));
+    modp::PolyArgs PA{dco.as<uint32_t>(), dord.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t,
+                      (uint32_t)n};
+    MPVSS_CUDA(ctx, modp::launch_poly(PA, ctx->stream));
+    MPVSS_TRY(d2h(ctx, p.data(), dp, n * EB));
+    MPVSS_TRY(sync(ctx));
+  }
   MPVSS_TRY(h2d(ctx, dw, witnesses, n * EB));
   MPVSS_TRY(h2d(ctx, dpk, publickeys, n * EB));
   MPVSS_TRY(h2d(ctx, ds, s_le, EB));

@@ -369,6 +369,74 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
   finish_store<TPI>(acc, sq, A.out + (size_t)inst * 64, live, M, ln);
 }
 
+// ------------------------------------------------- P(i) mod order (scalars) ----
+// p_i = P(pos_i) mod order by Horner on plain integers, one position per thread, the 2048-bit
+// accumulator in registers (polynomial.rs:50-58 reduced as participant.rs:202 does).  The order q-1 is
+// even, so no Montgomery form: since its top limb is all ones, the part of acc*x + a_j above 2^2048
+// (at most x) is folded back with delta = 2^2048 - order, twice, and one conditional subtraction at the
+// end gives the canonical value.  Requires order >= 2^2048 - 2^2016 (checked by the host).
+struct PolyArgs {
+  const uint32_t* coeffs;  // t x 64 limbs
+  const uint32_t* order;   // 64 limbs
+  const uint32_t* pos;     // n positions (< 2^31)
+  uint32_t* out;           // n x 64 limbs
+  uint32_t t, n;
+};
+MP_DEV void poly_body(const PolyArgs& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  const uint64_t x = A.pos[tid];
+  uint32_t acc[64], delta[64];
+  {
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      uint64_t d = (uint64_t)0 - A.order[i] - br;
+      delta[i] = (uint32_t)d;
+      br = (d >> 32) & 1u;
+      acc[i] = 0;
+    }
+  }
+#pragma unroll 1
+  for (int j = (int)A.t - 1; j >= 0; --j) {
+    const uint32_t* a = A.coeffs + (size_t)j * 64;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      c += (uint64_t)acc[i] * x + a[i];
+      acc[i] = (uint32_t)c;
+      c >>= 32;
+    }
+    // c <= x: fold c * 2^2048 = c * delta (mod order)
+    uint64_t top = c, cc = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      cc += top * delta[i] + acc[i];
+      acc[i] = (uint32_t)cc;
+      cc >>= 32;
+    }
+    // at most one more wrap
+    uint32_t m = 0u - (uint32_t)cc;
+    uint64_t c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      c2 += (uint64_t)acc[i] + (delta[i] & m);
+      acc[i] = (uint32_t)c2;
+      c2 >>= 32;
+    }
+  }
+  // canonical: subtract the order once if acc >= order
+  uint32_t r[64];
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    uint64_t d = (uint64_t)acc[i] - A.order[i] - br;
+    r[i] = (uint32_t)d;
+    br = (d >> 32) & 1u;
+  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) A.out[(size_t)tid * 64 + i] = br ? acc[i] : r[i];
+}
+
 // ------------------------------------------------------- element-wise mul ----
 struct MulArgs {
   const uint32_t* consts;

@@ -11,5 +11,6 @@ cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStre
 cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s);
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s);
 cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s);
+cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s);
 cudaError_t launch_mul(int tpi, const MulArgs& A, cudaStream_t s);
 }  // namespace modp

@@ -81,3 +81,10 @@ extern "C" int emu_modp_comb_build(int tpi, const uint32_t* consts, const uint32
   });
   return 0;
 }
+
+extern "C" int emu_modp_poly(const uint32_t* coeffs, uint32_t t, const uint32_t* order, const uint32_t* pos, uint32_t n,
+                             uint32_t* out) {
+  modp::PolyArgs A{coeffs, order, pos, out, t, n};
+  for (uint32_t i = 0; i < n; ++i) modp::poly_body(A, i);
+  return 0;
+}

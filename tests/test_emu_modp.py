@@ -126,3 +126,19 @@ def test_fixed_base_comb(lib):
                                  eu.P(out), eu.P(tbl)) == 0
         for i in range(n):
             assert eu.from_limbs(out[64 * i:64 * i + 64]) == pow(4, e1[i], Q) * pow(b2[i], e2[i], Q) % Q, (tpi, i)
+
+
+def test_scalar_polynomial_kernel(lib):
+    """P(i) mod (q-1) kernel against Polynomial::get_value(i) % order (polynomial.rs:50-58)."""
+    rng = random.Random(21)
+    order = Q - 1
+    t = 9
+    co = [rng.randrange(order) for _ in range(t)]
+    co[0], co[1] = order - 1, (1 << 2048) - 1          # also a coefficient that is not reduced
+    positions = [1, 2, 3, 255, 4096, 65536, (1 << 31) - 1]
+    n = len(positions)
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_poly(eu.P(np.concatenate([eu.to_limbs(c) for c in co])), t, eu.P(eu.to_limbs(order)),
+                             eu.P(np.array(positions, dtype=np.uint32)), n, eu.P(out)) == 0
+    for i, x in enumerate(positions):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.poly_get_value(co, x) % order, i
