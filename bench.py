@@ -210,8 +210,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096, help="participants per GPU")
-    ap.add_argument("--t", type=int, default=0, help="threshold (default ceil(2n/3))")
+    # long spellings too: under torchrun, `--n` / `--t` collide with abbreviations of its own options
+    ap.add_argument("--n", "--participants-per-gpu", dest="n", type=int, default=4096, help="participants per GPU")
+    ap.add_argument("--t", "--threshold", dest="t", type=int, default=0, help="threshold (default ceil(2n/3))")
     ap.add_argument("--tpi", type=int, default=0, help="override lanes per 2048-bit value")
     ap.add_argument("--seed", type=int, default=0x6D70767373)
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
