@@ -421,7 +421,7 @@ def main():
                 "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
     }
     if args.group == "modp":
-        hm = horner_macs([i + 1 for i in mine], t, args.tpi or 8)
+        hm = horner_macs([i + 1 for i in mine], t, args.tpi or (4 if n >= 32768 else 8))
         achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
         dual = (args.dual > 0) and t >= 8   # library default: single chain (modp_dual = 0)
         combine = n * (4 * 511 * SQR_MACS + (15 + 511 + 15 + 2) * MUL_MACS) if dual else 0

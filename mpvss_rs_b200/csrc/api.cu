@@ -115,6 +115,7 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
   if (std::string(key) == "modp_tpi") {
     if (value != 4 && value != 8 && value != 16) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_tpi must be 4, 8 or 16");
     ctx->modp_tpi = value;
+    ctx->modp_tpi_auto = false;  // an explicit choice applies to every kernel
     return MPVSS_OK;
   }
   if (std::string(key) == "ec_threads") {

@@ -65,6 +65,8 @@ struct mpvss_ctx {
 
   // ---- ModpGroup ----
   int modp_tpi = 8;
+  bool modp_tpi_auto = true;  // Horner launches pick 4 lanes per value when a launch has >= 32768 positions
+  int v_tpi = 8;              // lanes per value of the staged Horner plan
   int modp_overlap = 0;  // 2: issue the X-independent a2 launch on a side stream right after the Horner launch
   int modp_dual = 0;  // two-chunk Horner: 0 off (default: fastest whole step), 1 two interleaved chains per lane
                       // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)

@@ -284,13 +284,25 @@ MP_DEV void canonical(uint32_t (&r)[Cfg<TPI>::L], const Mod<Cfg<TPI>::L>& M, con
   }
 }
 
-// Shared-memory staging of a group's value so that every lane can read all 64 limbs.
+// Write a group's value (64 limbs, each lane its slice) to memory: used for global stores, possibly
+// under a per-group predicate, so it contains no barrier.
 template <int TPI>
 MP_DEV void stage(uint32_t* dst64, const uint32_t (&v)[Cfg<TPI>::L], const Lane& ln) {
   constexpr int L = Cfg<TPI>::L;
   uint4* d = reinterpret_cast<uint4*>(dst64 + ln.k * L);
 #pragma unroll
   for (int i = 0; i < L; i += 4) d[i / 4] = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+
+// Shared-memory staging so that every lane can read all 64 limbs; must be called by the whole warp.
+// The leading warp barrier orders the write after the other lanes' earlier reads of the buffer (the
+// shuffles of the preceding product already serialise them in practice, but only __syncwarp is a
+// memory-ordering guarantee; compute-sanitizer racecheck is clean with it).  The caller issues the
+// trailing barrier (often once for several staged values) before anybody reads.
+template <int TPI>
+MP_DEV void stage_shared(uint32_t* dst64, const uint32_t (&v)[Cfg<TPI>::L], const Lane& ln) {
+  simt::syncwarp();
+  stage<TPI>(dst64, v, ln);
 }
 
 template <int TPI>

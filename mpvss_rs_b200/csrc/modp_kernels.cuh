@@ -29,13 +29,14 @@ MP_DEV void load_mod(Mod<Cfg<TPI>::L>& M, const uint32_t* consts, const Lane& ln
 // copy 64 limbs global -> this warp's shared buffer (lane l moves limbs 2l, 2l+1)
 MP_DEV void warp_copy64(uint32_t* dst, const uint32_t* src) {
   uint32_t l = simt::lane_id();
+  simt::syncwarp();  // earlier readers of dst are done
   dst[2 * l] = src[2 * l];
   dst[2 * l + 1] = src[2 * l + 1];
 }
 
 template <int TPI>
 MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
-  stage<TPI>(sq, acc, ln);
+  stage_shared<TPI>(sq, acc, ln);
   simt::syncwarp();
   mont_mul<TPI>(acc, acc, sq, M, ln);
 }
@@ -49,7 +50,7 @@ MP_DEV void finish_store(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, uint32_t* d
 #pragma unroll
   for (int i = 0; i < L; ++i) one[i] = 0;
   if (ln.k == 0) one[0] = 1;
-  stage<TPI>(sq, one, ln);
+  stage_shared<TPI>(sq, one, ln);
   simt::syncwarp();
   mont_mul<TPI>(acc, acc, sq, M, ln);
   canonical<TPI>(acc, M, ln);
@@ -102,14 +103,14 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   for (int j = (int)A.t - 2; j >= 0; --j) {
     warp_copy64(cbuf, A.cm + (size_t)j * 64);
     // window table X, X^2, X^3
-    stage<TPI>(tbl, acc, ln);
+    stage_shared<TPI>(tbl, acc, ln);
     simt::syncwarp();
     uint32_t x[L];
     mont_mul<TPI>(x, acc, tbl, M, ln);
-    stage<TPI>(tbl + 64, x, ln);
+    stage_shared<TPI>(tbl + 64, x, ln);
     simt::syncwarp();
     mont_mul<TPI>(x, x, tbl, M, ln);
-    stage<TPI>(tbl + 128, x, ln);
+    stage_shared<TPI>(tbl + 128, x, ln);
     simt::syncwarp();
     uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
     load_slice<TPI>(acc, d ? tbl + (d - 1) * 64 : one, ln);
@@ -175,17 +176,17 @@ MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint3
   for (int j = (int)B - 2; j >= 0; --j) {
     warp_copy64(cbuf0, A.cm + (size_t)j * 64);
     warp_copy64(cbuf1, (B + j < t) ? A.cm + (size_t)(B + j) * 64 : A.consts + C_ONE);
-    stage<TPI>(t0, acc0, ln);
-    stage<TPI>(t1, acc1, ln);
+    stage_shared<TPI>(t0, acc0, ln);
+    stage_shared<TPI>(t1, acc1, ln);
     simt::syncwarp();
     uint32_t x0[L], x1[L];
     mont_mul2<TPI>(x0, acc0, t0, x1, acc1, t1, M, ln);
-    stage<TPI>(t0 + 64, x0, ln);
-    stage<TPI>(t1 + 64, x1, ln);
+    stage_shared<TPI>(t0 + 64, x0, ln);
+    stage_shared<TPI>(t1 + 64, x1, ln);
     simt::syncwarp();
     mont_mul2<TPI>(x0, x0, t0, x1, x1, t1, M, ln);
-    stage<TPI>(t0 + 128, x0, ln);
-    stage<TPI>(t1 + 128, x1, ln);
+    stage_shared<TPI>(t0 + 128, x0, ln);
+    stage_shared<TPI>(t1 + 128, x1, ln);
     simt::syncwarp();
     uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
     load_slice<TPI>(acc0, d ? t0 + (d - 1) * 64 : one, ln);
@@ -193,8 +194,8 @@ MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint3
     for (int s = (int)ndigits - 2; s >= 0; --s) {
 #pragma unroll 1
       for (int rep = 0; rep < 2; ++rep) {
-        stage<TPI>(sq0, acc0, ln);
-        stage<TPI>(sq1, acc1, ln);
+        stage_shared<TPI>(sq0, acc0, ln);
+        stage_shared<TPI>(sq1, acc1, ln);
         simt::syncwarp();
         mont_mul2<TPI>(acc0, acc0, sq0, acc1, acc1, sq1, M, ln);
       }
@@ -237,14 +238,14 @@ MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, co
   uint32_t x[L];
   // tbl[0] = one, tbl[1] = base in Montgomery form, tbl[i] = tbl[i-1] * base
   load_slice<TPI>(x, consts + C_ONE, ln);
-  stage<TPI>(tbl, x, ln);
+  stage_shared<TPI>(tbl, x, ln);
   load_slice<TPI>(x, base64, ln);
   mont_mul<TPI>(x, x, r2, M, ln);
-  stage<TPI>(tbl + 64, x, ln);
+  stage_shared<TPI>(tbl + 64, x, ln);
   simt::syncwarp();
   for (int i = 2; i < 16; ++i) {
     mont_mul<TPI>(x, x, tbl + 64, M, ln);
-    stage<TPI>(tbl + i * 64, x, ln);
+    stage_shared<TPI>(tbl + i * 64, x, ln);
     simt::syncwarp();
   }
   uint32_t wi = windows - 1;
@@ -273,7 +274,7 @@ MP_DEV void exp_comb8(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* tbl, const u
     d = (e[w >> 2] >> ((w & 3u) * 8)) & 0xffu;
     uint32_t x[L];
     load_slice<TPI>(x, tbl + ((size_t)w * 256 + d) * 64, ln);
-    stage<TPI>(sq, x, ln);
+    stage_shared<TPI>(sq, x, ln);
     simt::syncwarp();
     mont_mul<TPI>(acc, acc, sq, M, ln);
   }
@@ -326,7 +327,7 @@ MP_DEV void comb2_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
   load_slice<TPI>(x, A.consts + C_ONE, ln);
   if (live) stage<TPI>(row, x, ln);
   load_slice<TPI>(x, row + 64, ln);
-  stage<TPI>(b1, x, ln);
+  stage_shared<TPI>(b1, x, ln);
   simt::syncwarp();
   for (uint32_t d = 2; d < 256; ++d) {
     mont_mul<TPI>(x, x, b1, M, ln);
@@ -362,7 +363,7 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
     uint32_t acc2[L];
     exp_window4<TPI>(acc2, A.b2 + (size_t)inst * A.b2_stride, A.e2 + (size_t)inst * A.e2_stride, A.e2_windows, tbl,
                      sq, r2, A.consts, M, ln);
-    stage<TPI>(sq, acc2, ln);
+    stage_shared<TPI>(sq, acc2, ln);
     simt::syncwarp();
     mont_mul<TPI>(acc, acc, sq, M, ln);
   }
@@ -472,7 +473,7 @@ MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
   if (A.mode == 0) {
     uint32_t y[L];
     load_slice<TPI>(y, A.b + (size_t)inst * A.b_stride, ln);
-    stage<TPI>(sq, y, ln);
+    stage_shared<TPI>(sq, y, ln);
     simt::syncwarp();
     mont_mul<TPI>(acc, acc, sq, M, ln);  // a*R*b/R = a*b
   }
