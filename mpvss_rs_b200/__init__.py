@@ -8,3 +8,4 @@ CUDA device every entry point raises.
 from .lib import Context, MpvssError, LIB_PATH, load  # noqa: F401
 from .participant import (DistributionSharesBox, Group, Participant, ShareBox,  # noqa: F401
                           string_from_secret, string_to_secret)
+from . import wire  # noqa: F401,E402

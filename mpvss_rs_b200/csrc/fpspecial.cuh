@@ -28,8 +28,10 @@ MP_DEV void mul_wide(uint32_t (&t)[16], const Fe& a, const Fe& b) {
         E[p + 2 * k] = simt::madc_lo_cc(a.v[ja + 2 * k], b.v[i], E[p + 2 * k]);
         E[p + 2 * k + 1] = simt::madc_hi_cc(a.v[ja + 2 * k], b.v[i], E[p + 2 * k + 1]);
       }
-      E[p + 8] = simt::addc_cc(E[p + 8], 0);
-      E[p + 9] = simt::addc(E[p + 9], 0);
+      // Column p+8 holds 0 here: the first row that reaches a new top pair adds one product to an
+      // (almost) empty pair and cannot carry out, so whatever was stored before is 0 and the carry
+      // is simply the new value (same argument for the odd accumulator below).
+      E[p + 8] = simt::addc(0, 0);
     }
     {  // limbs j = jb, jb+2, ... : odd columns, stored at index column - 1
       const int p = i + jb - 1;
@@ -40,8 +42,7 @@ MP_DEV void mul_wide(uint32_t (&t)[16], const Fe& a, const Fe& b) {
         O[p + 2 * k] = simt::madc_lo_cc(a.v[jb + 2 * k], b.v[i], O[p + 2 * k]);
         O[p + 2 * k + 1] = simt::madc_hi_cc(a.v[jb + 2 * k], b.v[i], O[p + 2 * k + 1]);
       }
-      O[p + 8] = simt::addc_cc(O[p + 8], 0);
-      O[p + 9] = simt::addc(O[p + 9], 0);
+      O[p + 8] = simt::addc(0, 0);
     }
   }
   t[0] = E[0];
