@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) mul_kernel(MulArgs A) {
 }
 
 __global__ void __launch_bounds__(64) poly_kernel(PolyArgs A) { poly_body(A, blockIdx.x * 64 + threadIdx.x); }
+__global__ void __launch_bounds__(64) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, blockIdx.x * 64 + threadIdx.x); }
 
 template <int TPI>
 static uint32_t ctas_for(uint32_t n) {
@@ -113,6 +114,12 @@ cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
 cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s) {
   if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
   poly_kernel<<<(A.n + 63) / 64, 64, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s) {
+  if (A.k == 0) return cudaErrorInvalidValue;
+  lagrange_kernel<<<(A.k + 63) / 64, 64, 0, s>>>(A);
   return cudaGetLastError();
 }
 

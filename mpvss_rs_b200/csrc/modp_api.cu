@@ -9,6 +9,7 @@
 //   responses                     participant.rs:255-264, modp.rs:180-192
 //   U mask                        participant.rs:267-272, 512-518
 //   Lagrange exponents            participant.rs:526-561, util.rs:47-64
+#include <algorithm>
 #include "ctx.h"
 #include "modp_launch.h"
 #include "sha2.h"
@@ -815,36 +816,42 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
   for (size_t i = 0; i < k; ++i)
     if (positions[i] < 1 || positions[i] > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range");
   // lambda_i = prod_{j != i} j / (j - i) mod g with the sign folded into the exponent:
-  // S^(-lambda) = S^((q-1) - lambda)  (participant.rs:535-558, element_inverse modp.rs:138-140)
-  const big::Int& g = ctx->g;
-  std::vector<big::Int> num(k), den(k);
-  std::vector<bool> neg(k);
-  for (size_t i = 0; i < k; ++i) {
-    big::Int nu = big::from_u64(1), de = big::from_u64(1);
-    bool sg = false;
-    for (size_t j = 0; j < k; ++j) {
-      if (j == i) continue;
-      if (positions[j] == positions[i]) return mpvss_fail(ctx, MPVSS_ERR_ARG, "duplicate position");
-      int64_t d = positions[j] - positions[i];
-      if (d < 0) { sg = !sg; d = -d; }
-      nu = big::mod(big::mul(nu, big::from_u64((uint64_t)positions[j])), g);
-      de = big::mod(big::mul(de, big::from_u64((uint64_t)d)), g);
-    }
-    num[i] = nu; den[i] = de; neg[i] = sg;
+  // S^(-lambda) = S^((q-1) - lambda)  (participant.rs:535-558, element_inverse modp.rs:138-140).
+  // Numerators / denominators mod q-1 on the device (one position per thread), then
+  // den^-1 = den^(g-2) mod g and lambda = num * den^-1 mod g with the kernels of modulus g.
+  std::vector<uint32_t> pos(k), order(EW, 0);
+  for (size_t i = 0; i < k; ++i) pos[i] = (uint32_t)positions[i];
+  {
+    std::vector<uint32_t> sorted(pos);
+    std::sort(sorted.begin(), sorted.end());
+    if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end())
+      return mpvss_fail(ctx, MPVSS_ERR_ARG, "duplicate position");
   }
-  // one inversion for all denominators (Montgomery's trick)
-  std::vector<big::Int> pre(k + 1);
-  pre[0] = big::from_u64(1);
-  for (size_t i = 0; i < k; ++i) pre[i + 1] = big::mulmod(pre[i], den[i], g);
-  big::Int inv_all;
-  if (!big::modinv(pre[k], g, &inv_all)) return mpvss_fail(ctx, MPVSS_ERR_NOT_INVERTIBLE, "Lagrange denominator");
-  std::vector<uint8_t> lam(k * EB);
-  for (size_t i = k; i-- > 0;) {
-    big::Int di = big::mulmod(inv_all, pre[i], g);
-    inv_all = big::mulmod(inv_all, den[i], g);
-    big::Int l = big::mulmod(num[i], di, g);
-    if (neg[i] && !big::is_zero(l)) l = big::sub(ctx->qm1, l);
-    big::to_le(l, lam.data() + i * EB, EB);
+  for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
+  std::vector<uint8_t> gm2(EB), lam(k * EB);
+  big::to_le(big::sub(ctx->g, big::from_u64(2)), gm2.data(), EB);
+  DevBuf &dpos = ctx->buf(12), &dord = ctx->buf(13), &dnum = ctx->buf(14), &dden = ctx->buf(15), &dneg = ctx->buf(16),
+         &de = ctx->buf(17), &dinv = ctx->buf(18), &dlam = ctx->buf(19);
+  MPVSS_TRY(h2d(ctx, dpos, pos.data(), k * 4));
+  MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
+  MPVSS_TRY(h2d(ctx, de, gm2.data(), EB));
+  for (DevBuf* b : {&dnum, &dden, &dinv, &dlam}) MPVSS_CUDA(ctx, b->ensure(k * EB));
+  MPVSS_CUDA(ctx, dneg.ensure(k * 4));
+  const uint32_t* Kg = ctx->consts_g.as<uint32_t>();
+  modp::LagrangeArgs LA{dord.as<uint32_t>(), dpos.as<uint32_t>(), dnum.as<uint32_t>(), dden.as<uint32_t>(),
+                        dneg.as<uint32_t>(), (uint32_t)k};
+  MPVSS_CUDA(ctx, modp::launch_lagrange(LA, ctx->stream));
+  MPVSS_TRY(dev_exp2(ctx, Kg, dden.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(gm2.data(), EB, 1), nullptr, 0,
+                     nullptr, 0, 0, k, dinv.as<uint32_t>()));
+  MPVSS_TRY(dev_mul(ctx, Kg, dnum.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 0, k, dlam.as<uint32_t>()));
+  std::vector<uint32_t> negf(k);
+  MPVSS_TRY(d2h(ctx, lam.data(), dlam, k * EB));
+  MPVSS_TRY(d2h(ctx, negf.data(), dneg, k * 4));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < k; ++i) {
+    if (!negf[i]) continue;
+    big::Int l = big::from_le(lam.data() + i * EB, EB);
+    if (!big::is_zero(l)) big::to_le(big::sub(ctx->qm1, l), lam.data() + i * EB, EB);
   }
   uint8_t gs[EB];
   MPVSS_TRY(multi_exp(ctx, shares, lam.data(), k, gs));

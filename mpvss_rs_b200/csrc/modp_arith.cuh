@@ -273,14 +273,18 @@ MP_DEV void mont_mul2(uint32_t (&r0)[Cfg<TPI>::L], const uint32_t (&a0)[Cfg<TPI>
 template <int TPI>
 MP_DEV void canonical(uint32_t (&r)[Cfg<TPI>::L], const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   constexpr int L = Cfg<TPI>::L;
-  // 2^2048 < 2q for every 2048-bit modulus, so one conditional subtraction suffices.
-  uint32_t t[L];
+  // Two conditional subtractions: one suffices when 2^2048 < 2q (the group modulus), but the subgroup
+  // order g = (q-1)/2 is just below 2^2047, so a value of [2g, 2^2048) needs the second one.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t t[L];
 #pragma unroll
-  for (int i = 0; i < L; ++i) t[i] = r[i];
-  uint32_t ge = add_resolve<TPI>(t, M.nq, 0xffffffffu, ln);  // carry <=> r >= q
-  if (ge) {
+    for (int i = 0; i < L; ++i) t[i] = r[i];
+    uint32_t ge = add_resolve<TPI>(t, M.nq, 0xffffffffu, ln);  // carry <=> r >= q
+    if (ge) {
 #pragma unroll
-    for (int i = 0; i < L; ++i) r[i] = t[i];
+      for (int i = 0; i < L; ++i) r[i] = t[i];
+    }
   }
 }
 

@@ -438,6 +438,88 @@ MP_DEV void poly_body(const PolyArgs& A, uint32_t tid) {
   for (int i = 0; i < 64; ++i) A.out[(size_t)tid * 64 + i] = br ? acc[i] : r[i];
 }
 
+// ------------------------------------------------- Lagrange numerators / denominators ----
+// For position x_i among k positions: num_i = prod_{j != i} x_j and den_i = prod_{j != i} |x_j - x_i|,
+// both modulo the order q-1 (a multiple of the subgroup order g the coefficients live in, so the host /
+// the exponentiation kernel may reduce further), and the sign of prod (x_j - x_i)
+// (util.rs:47-64 + participant.rs:535-541).  One position per thread, same lazy reduction as poly_body.
+struct LagrangeArgs {
+  const uint32_t* order;  // 64 limbs, all-ones top limb
+  const uint32_t* pos;    // k positions
+  uint32_t* num;          // k x 64 limbs
+  uint32_t* den;          // k x 64 limbs
+  uint32_t* negative;     // k flags
+  uint32_t k;
+};
+MP_DEV void lagrange_product(uint32_t* out64, const LagrangeArgs& A, uint32_t tid, bool denominator, uint32_t* neg) {
+  const uint32_t xi = A.pos[tid];
+  uint32_t acc[64], delta[64];
+  {
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      uint64_t d = (uint64_t)0 - A.order[i] - br;
+      delta[i] = (uint32_t)d;
+      br = (d >> 32) & 1u;
+      acc[i] = 0;
+    }
+    acc[0] = 1;
+  }
+  uint32_t sign = 0;
+#pragma unroll 1
+  for (uint32_t j = 0; j < A.k; ++j) {
+    if (j == tid) continue;
+    const uint32_t xj = A.pos[j];
+    uint64_t f = xj;
+    if (denominator) {
+      if (xj < xi) {
+        sign ^= 1u;
+        f = xi - xj;
+      } else {
+        f = xj - xi;
+      }
+    }
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      c += (uint64_t)acc[i] * f;
+      acc[i] = (uint32_t)c;
+      c >>= 32;
+    }
+    uint64_t top = c, cc = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      cc += top * delta[i] + acc[i];
+      acc[i] = (uint32_t)cc;
+      cc >>= 32;
+    }
+    uint32_t m = 0u - (uint32_t)cc;
+    uint64_t c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      c2 += (uint64_t)acc[i] + (delta[i] & m);
+      acc[i] = (uint32_t)c2;
+      c2 >>= 32;
+    }
+  }
+  uint64_t br = 0;
+  uint32_t r[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    uint64_t d = (uint64_t)acc[i] - A.order[i] - br;
+    r[i] = (uint32_t)d;
+    br = (d >> 32) & 1u;
+  }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) out64[i] = br ? acc[i] : r[i];
+  if (neg) *neg = sign;
+}
+MP_DEV void lagrange_body(const LagrangeArgs& A, uint32_t tid) {
+  if (tid >= A.k) return;
+  lagrange_product(A.num + (size_t)tid * 64, A, tid, false, nullptr);
+  lagrange_product(A.den + (size_t)tid * 64, A, tid, true, A.negative + tid);
+}
+
 // ------------------------------------------------------- element-wise mul ----
 struct MulArgs {
   const uint32_t* consts;

@@ -88,3 +88,10 @@ extern "C" int emu_modp_poly(const uint32_t* coeffs, uint32_t t, const uint32_t*
   for (uint32_t i = 0; i < n; ++i) modp::poly_body(A, i);
   return 0;
 }
+
+extern "C" int emu_modp_lagrange(const uint32_t* order, const uint32_t* pos, uint32_t k, uint32_t* num, uint32_t* den,
+                                 uint32_t* negative) {
+  modp::LagrangeArgs A{order, pos, num, den, negative, k};
+  for (uint32_t i = 0; i < k; ++i) modp::lagrange_body(A, i);
+  return 0;
+}

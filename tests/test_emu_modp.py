@@ -142,3 +142,20 @@ def test_scalar_polynomial_kernel(lib):
                              eu.P(np.array(positions, dtype=np.uint32)), n, eu.P(out)) == 0
     for i, x in enumerate(positions):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.poly_get_value(co, x) % order, i
+
+
+def test_lagrange_kernel(lib):
+    """num_i, den_i mod (q-1) and the sign, against util.rs:47-64 (oracle lagrange_coefficient)."""
+    from oracle.groups import lagrange_coefficient
+    order = Q - 1
+    values = [1, 3, 4, 9, 200, 4096, 65536, 7]
+    k = len(values)
+    num, den = np.zeros(64 * k, dtype=np.uint32), np.zeros(64 * k, dtype=np.uint32)
+    neg = np.zeros(k, dtype=np.uint32)
+    assert lib.emu_modp_lagrange(eu.P(eu.to_limbs(order)), eu.P(np.array(values, dtype=np.uint32)), k, eu.P(num),
+                                 eu.P(den), eu.P(neg)) == 0
+    for i, x in enumerate(values):
+        n_, d_ = lagrange_coefficient(x, values)
+        assert eu.from_limbs(num[64 * i:64 * i + 64]) == abs(n_) % order
+        assert eu.from_limbs(den[64 * i:64 * i + 64]) == abs(d_) % order
+        assert bool(neg[i]) == (n_ * d_ < 0)

@@ -1,0 +1,37 @@
+"""Wall-clock and kernel time of every PVSS phase at the BASELINE.json configurations, through the
+Python mirror of the reference API (so host-side conversion of Python ints is included in `wall_ms`;
+`kernel_ms` is the CUDA-event time of the library's launches).  Writes one JSON object."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mpvss_rs_b200 as m
+from mpvss_rs_b200 import synth
+
+CONFIGS = [("modp", 1024, 683), ("modp", 4096, 2731), ("secp256k1", 4096, 2731), ("ristretto255", 16384, 10923)]
+if len(sys.argv) > 1:
+    CONFIGS = [c for c in CONFIGS if c[0] in sys.argv[1:]]
+out = []
+for name, n, t in CONFIGS:
+    g = m.Group(name)
+    c = g.codec
+    sks = synth.private_keys(1, n, name, c.order, c.key_bound)
+    co = synth.coefficients(1, t, c.order)
+    ws = synth.witnesses(1, n, c.key_bound)
+    d = m.Participant(g)
+    row = {"group": name, "n": n, "t": t, "phases": {}}
+
+    def timed(label, fn):
+        t0 = time.perf_counter()
+        r = fn()
+        row["phases"][label] = {"wall_ms": round((time.perf_counter() - t0) * 1e3, 2),
+                                "kernel_ms": round(g.ctx.last_kernel_ms, 2)}
+        return r
+
+    pks = timed("keygen (n fixed-base exps)", lambda: g.fixed_base_exp(sks))
+    box = timed("distribute_secret", lambda: d.distribute_secret(123456789, pks, t, coeffs=co, witnesses=ws))
+    assert timed("verify_distribution_shares", lambda: d.verify_distribution_shares(box))
+    sbs = timed(f"extract_secret_share x{t}", lambda: d.extract_secret_shares(box, sks[:t], ws[:t]))
+    assert all(timed(f"verify_share x{t}", lambda: d.verify_shares(sbs, box, pks[:t])))
+    assert timed(f"reconstruct (k={t})", lambda: d.reconstruct(sbs, box)) == 123456789
+    out.append(row)
+    print(json.dumps(row), flush=True)
+json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "phases.json"), "w"), indent=1)
