@@ -9,3 +9,4 @@ from .lib import Context, MpvssError, LIB_PATH, load  # noqa: F401
 from .participant import (DistributionSharesBox, Group, Participant, ShareBox,  # noqa: F401
                           string_from_secret, string_to_secret)
 from . import wire  # noqa: F401,E402
+from .dleq import DLEQ, PVSS, hash_to_scalar  # noqa: F401,E402

@@ -140,11 +140,21 @@ MP_DEV void fold_small(uint32_t (&r)[9], const uint32_t* lo, const uint32_t* hi,
   r[8] = simt::addc(u[8], 0);
 }
 
-MP_DEV Fe cond_sub_p(const Fe& a, uint32_t carry, const uint32_t* p) {
+// The two primes as compile-time limbs: every use below unrolls to immediates, no loads.
+struct SecpP {
+  MP_DEV static constexpr uint32_t limb(int i) { return i == 0 ? 0xFFFFFC2Fu : (i == 1 ? 0xFFFFFFFEu : 0xFFFFFFFFu); }
+};
+struct EdP {
+  MP_DEV static constexpr uint32_t limb(int i) { return i == 0 ? 0xFFFFFFEDu : (i == 7 ? 0x7FFFFFFFu : 0xFFFFFFFFu); }
+};
+
+// r = a - p if a >= p (a < 2p, with an optional carry bit above the 8 limbs)
+template <class Pr>
+MP_DEV Fe cond_sub_p(const Fe& a, uint32_t carry) {
   Fe t;
-  t.v[0] = simt::sub_cc(a.v[0], p[0]);
+  t.v[0] = simt::sub_cc(a.v[0], Pr::limb(0));
 #pragma unroll
-  for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(a.v[i], p[i]);
+  for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(a.v[i], Pr::limb(i));
   uint32_t borrow = simt::subc(0, 0);
   bool take = carry || borrow == 0;
   Fe r;
@@ -152,9 +162,31 @@ MP_DEV Fe cond_sub_p(const Fe& a, uint32_t carry, const uint32_t* p) {
   for (int i = 0; i < 8; ++i) r.v[i] = take ? t.v[i] : a.v[i];
   return r;
 }
+template <class Pr>
+MP_DEV Fe add_p(const Fe& a, const Fe& b) {
+  Fe s;
+  s.v[0] = simt::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) s.v[i] = simt::addc_cc(a.v[i], b.v[i]);
+  uint32_t c = simt::addc(0, 0);
+  return cond_sub_p<Pr>(s, c);
+}
+template <class Pr>
+MP_DEV Fe sub_p(const Fe& a, const Fe& b) {
+  Fe d;
+  d.v[0] = simt::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) d.v[i] = simt::subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = simt::subc(0, 0);  // 0xffffffff when a < b
+  Fe r;
+  r.v[0] = simt::add_cc(d.v[0], Pr::limb(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) r.v[i] = simt::addc_cc(d.v[i], Pr::limb(i) & borrow);
+  return r;
+}
 
 // ---- secp256k1: 2^256 = 2^32 + 977 (mod p) -----------------------------------------------------
-MP_DEV Fe secp_reduce(const uint32_t (&t)[16], const uint32_t* p) {
+MP_DEV Fe secp_reduce(const uint32_t (&t)[16]) {
   // r = lo + hi*977 + (hi << 32)   (< 2^290)
   uint32_t r[9];
   fold_small(r, t, t + 8, 977u);
@@ -185,11 +217,11 @@ MP_DEV Fe secp_reduce(const uint32_t (&t)[16], const uint32_t* p) {
   s.v[1] = simt::addc_cc(s.v[1], 1u & m);
 #pragma unroll
   for (int x = 2; x < 8; ++x) s.v[x] = simt::addc_cc(s.v[x], 0);
-  return cond_sub_p(s, 0, p);
+  return cond_sub_p<SecpP>(s, 0);
 }
 
 // ---- curve25519: 2^256 = 38 (mod p), p = 2^255 - 19 --------------------------------------------
-MP_DEV Fe ed_reduce(const uint32_t (&t)[16], const uint32_t* p) {
+MP_DEV Fe ed_reduce(const uint32_t (&t)[16]) {
   uint32_t r[9];
   fold_small(r, t, t + 8, 38u);  // < 39 * 2^256
   // fold r[8] (< 39) and bit 255: value = low255 + 19 * (2*r[8] + bit255)
@@ -205,7 +237,7 @@ MP_DEV Fe ed_reduce(const uint32_t (&t)[16], const uint32_t* p) {
   s.v[0] = simt::add_cc(s.v[0], 19u * b);
 #pragma unroll
   for (int x = 1; x < 8; ++x) s.v[x] = simt::addc_cc(s.v[x], 0);
-  return cond_sub_p(s, 0, p);
+  return cond_sub_p<EdP>(s, 0);
 }
 
 }  // namespace fpsp

@@ -13,25 +13,32 @@ using fp256::Modulus;
 
 // Base-field arithmetic mod 2^255-19: plain representation, special-form reduction.
 namespace F {
-using fp256::add;
-using fp256::dbl;
 using fp256::eq;
 using fp256::fe_zero;
 using fp256::is_zero;
 using fp256::load;
-using fp256::neg;
 using fp256::store;
-using fp256::sub;
-MP_NOINLINE Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
+// Field constants are immediates (fpsp::EdP); the Modulus argument is kept so the curve code
+// reads the same for both fields.
+MP_DEV Fe add(const Fe& a, const Fe& b, const Modulus&) { return fpsp::add_p<fpsp::EdP>(a, b); }
+MP_DEV Fe sub(const Fe& a, const Fe& b, const Modulus&) { return fpsp::sub_p<fpsp::EdP>(a, b); }
+MP_DEV Fe neg(const Fe& a, const Modulus&) { return fpsp::sub_p<fpsp::EdP>(fe_zero(), a); }
+MP_DEV Fe dbl(const Fe& a, const Modulus&) { return fpsp::add_p<fpsp::EdP>(a, a); }
+// Operands by value: a non-inlined callee that reads its operands through references keeps ptxas
+// from pairing mad.lo.cc / madc.hi.cc into IMAD.WIDE (twice the instructions); by value they arrive
+// in registers.
+MP_NOINLINE Fe mul(Fe a, Fe b) {
   uint32_t t[16];
   fpsp::mul_wide(t, a, b);
-  return fpsp::ed_reduce(t, P.m);
+  return fpsp::ed_reduce(t);
 }
-MP_NOINLINE Fe sqr(const Fe& a, const Modulus& P) {
+MP_NOINLINE Fe sqr(Fe a) {
   uint32_t t[16];
   fpsp::sqr_wide(t, a);
-  return fpsp::ed_reduce(t, P.m);
+  return fpsp::ed_reduce(t);
 }
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus&) { return mul(a, b); }
+MP_DEV Fe sqr(const Fe& a, const Modulus&) { return sqr(a); }
 MP_DEV Fe to_mont(const Fe& a, const Modulus&) { return a; }
 MP_DEV Fe from_mont(const Fe& a, const Modulus&) { return a; }
 MP_DEV Fe mont_one(const Modulus&) {
@@ -93,11 +100,11 @@ MP_DEV Ext ext_from_aff(const Aff& a, const Modulus& P) {
 MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
   using namespace F;
   const Modulus& P = C.P;
-  Fe A = F::mul(sub(p.Y, p.X, P), sub(q.Y, q.X, P), P);
-  Fe B = F::mul(add(p.Y, p.X, P), add(q.Y, q.X, P), P);
+  Fe A = F::mul(F::sub(p.Y, p.X, P), F::sub(q.Y, q.X, P), P);
+  Fe B = F::mul(F::add(p.Y, p.X, P), F::add(q.Y, q.X, P), P);
   Fe Cc = F::mul(F::mul(p.T, load(C.d2), P), q.T, P);
-  Fe D = dbl(F::mul(p.Z, q.Z, P), P);
-  Fe E = sub(B, A, P), F = sub(D, Cc, P), G = add(D, Cc, P), H = add(B, A, P);
+  Fe D = F::dbl(F::mul(p.Z, q.Z, P), P);
+  Fe E = F::sub(B, A, P), F = F::sub(D, Cc, P), G = F::add(D, Cc, P), H = F::add(B, A, P);
   Ext r;
   r.X = F::mul(E, F, P);
   r.Y = F::mul(G, H, P);
@@ -109,10 +116,10 @@ MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
 MP_NOINLINE Ext ext_dbl(const Ext& p, const Consts& C) {
   using namespace F;
   const Modulus& P = C.P;
-  Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), Cc = dbl(F::sqr(p.Z, P), P);
-  Fe D = neg(A, P);
-  Fe E = sub(sub(F::sqr(add(p.X, p.Y, P), P), A, P), B, P);
-  Fe G = add(D, B, P), F = sub(G, Cc, P), H = sub(D, B, P);
+  Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), Cc = F::dbl(F::sqr(p.Z, P), P);
+  Fe D = F::neg(A, P);
+  Fe E = F::sub(F::sub(F::sqr(F::add(p.X, p.Y, P), P), A, P), B, P);
+  Fe G = F::add(D, B, P), F = F::sub(G, Cc, P), H = F::sub(D, B, P);
   Ext r;
   r.X = F::mul(E, F, P);
   r.Y = F::mul(G, H, P);
@@ -134,7 +141,7 @@ MP_NOINLINE bool sqrt_ratio_m1(Fe* out, const Fe& u, const Fe& v, const Consts& 
   Fe r = F::mul(F::mul(u, v3, P), F::pow(F::mul(u, v7, P), C.pm5d8, P), P);
   Fe check = F::mul(v, F::sqr(r, P), P);
   Fe sm1 = load(C.sqrt_m1);
-  Fe nu = neg(u, P);
+  Fe nu = F::neg(u, P);
   bool correct = eq(check, u);
   bool flipped = eq(check, nu);
   bool flipped_i = eq(check, F::mul(nu, sm1, P));
@@ -147,7 +154,7 @@ MP_NOINLINE bool sqrt_ratio_m1(Fe* out, const Fe& u, const Fe& v, const Consts& 
 MP_NOINLINE void encode(uint8_t* out, const Ext& p, const Consts& C) {
   using namespace F;
   const Modulus& P = C.P;
-  Fe u1 = F::mul(add(p.Z, p.Y, P), sub(p.Z, p.Y, P), P);
+  Fe u1 = F::mul(F::add(p.Z, p.Y, P), F::sub(p.Z, p.Y, P), P);
   Fe u2 = F::mul(p.X, p.Y, P);
   Fe invsqrt;
   sqrt_ratio_m1(&invsqrt, F::mont_one(P), F::mul(u1, F::sqr(u2, P), P), C);
@@ -160,8 +167,8 @@ MP_NOINLINE void encode(uint8_t* out, const Ext& p, const Consts& C) {
   Fe x = rotate ? iy0 : p.X;
   Fe y = rotate ? ix0 : p.Y;
   Fe den_inv = rotate ? enchanted : den2;
-  if (is_negative(F::mul(x, z_inv, P), P)) y = neg(y, P);
-  Fe s = F::from_mont(ct_abs(F::mul(den_inv, sub(p.Z, y, P), P), P), P);
+  if (is_negative(F::mul(x, z_inv, P), P)) y = F::neg(y, P);
+  Fe s = F::from_mont(ct_abs(F::mul(den_inv, F::sub(p.Z, y, P), P), P), P);
   for (int i = 0; i < 8; ++i) {
     out[4 * i] = (uint8_t)s.v[i];
     out[4 * i + 1] = (uint8_t)(s.v[i] >> 8);
@@ -190,14 +197,14 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
   if (s.v[0] & 1u) return false;
   Fe sm = F::to_mont(s, P), one = F::mont_one(P);
   Fe ss = F::sqr(sm, P);
-  Fe u1 = sub(one, ss, P), u2 = add(one, ss, P);
+  Fe u1 = F::sub(one, ss, P), u2 = F::add(one, ss, P);
   Fe u2_sqr = F::sqr(u2, P);
-  Fe v = sub(neg(F::mul(load(C.d), F::sqr(u1, P), P), P), u2_sqr, P);
+  Fe v = F::sub(F::neg(F::mul(load(C.d), F::sqr(u1, P), P), P), u2_sqr, P);
   Fe invsqrt;
   bool was_square = sqrt_ratio_m1(&invsqrt, one, F::mul(v, u2_sqr, P), C);
   Fe den_x = F::mul(invsqrt, u2, P);
   Fe den_y = F::mul(F::mul(invsqrt, den_x, P), v, P);
-  Fe x = ct_abs(F::mul(dbl(sm, P), den_x, P), P);
+  Fe x = ct_abs(F::mul(F::dbl(sm, P), den_x, P), P);
   Fe y = F::mul(u1, den_y, P);
   Fe tt = F::mul(x, y, P);
   if (!was_square || is_negative(tt, P) || is_zero(y)) return false;

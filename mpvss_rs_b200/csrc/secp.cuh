@@ -14,25 +14,32 @@ using fp256::Modulus;
 // Base-field arithmetic: plain representation with the special-form reduction of fpspecial.cuh
 // (the scalar field keeps the generic Montgomery code of fp256.cuh).
 namespace F {
-using fp256::add;
-using fp256::dbl;
 using fp256::eq;
 using fp256::fe_zero;
 using fp256::is_zero;
 using fp256::load;
-using fp256::neg;
 using fp256::store;
-using fp256::sub;
-MP_NOINLINE Fe mul(const Fe& a, const Fe& b, const Modulus& P) {
+// Field constants are immediates (fpsp::SecpP); the Modulus argument is kept so the curve code
+// reads the same for both fields.
+MP_DEV Fe add(const Fe& a, const Fe& b, const Modulus&) { return fpsp::add_p<fpsp::SecpP>(a, b); }
+MP_DEV Fe sub(const Fe& a, const Fe& b, const Modulus&) { return fpsp::sub_p<fpsp::SecpP>(a, b); }
+MP_DEV Fe neg(const Fe& a, const Modulus&) { return fpsp::sub_p<fpsp::SecpP>(fe_zero(), a); }
+MP_DEV Fe dbl(const Fe& a, const Modulus&) { return fpsp::add_p<fpsp::SecpP>(a, a); }
+// Operands by value: a non-inlined callee that reads its operands through references keeps ptxas
+// from pairing mad.lo.cc / madc.hi.cc into IMAD.WIDE (twice the instructions); by value they arrive
+// in registers.
+MP_NOINLINE Fe mul(Fe a, Fe b) {
   uint32_t t[16];
   fpsp::mul_wide(t, a, b);
-  return fpsp::secp_reduce(t, P.m);
+  return fpsp::secp_reduce(t);
 }
-MP_NOINLINE Fe sqr(const Fe& a, const Modulus& P) {
+MP_NOINLINE Fe sqr(Fe a) {
   uint32_t t[16];
   fpsp::sqr_wide(t, a);
-  return fpsp::secp_reduce(t, P.m);
+  return fpsp::secp_reduce(t);
 }
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus&) { return mul(a, b); }
+MP_DEV Fe sqr(const Fe& a, const Modulus&) { return sqr(a); }
 MP_DEV Fe to_mont(const Fe& a, const Modulus&) { return a; }
 MP_DEV Fe from_mont(const Fe& a, const Modulus&) { return a; }
 MP_DEV Fe mont_one(const Modulus&) {
@@ -106,15 +113,15 @@ MP_NOINLINE Jac jac_dbl(const Jac& p, const Modulus& P) {
   using namespace F;
   if (jac_is_inf(p)) return p;
   Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), C = F::sqr(B, P);
-  Fe t = add(p.X, B, P);
-  Fe D = dbl(sub(sub(F::sqr(t, P), A, P), C, P), P);
-  Fe E = add(dbl(A, P), A, P);
-  Fe F = F::sqr(E, P);
+  Fe t = F::add(p.X, B, P);
+  Fe D = F::dbl(F::sub(F::sub(F::sqr(t, P), A, P), C, P), P);
+  Fe E = F::add(F::dbl(A, P), A, P);
+  Fe E2 = F::sqr(E, P);
   Jac r;
-  r.X = sub(F, dbl(D, P), P);
-  Fe C8 = dbl(dbl(dbl(C, P), P), P);
-  r.Y = sub(F::mul(E, sub(D, r.X, P), P), C8, P);
-  r.Z = dbl(F::mul(p.Y, p.Z, P), P);
+  r.X = F::sub(E2, F::dbl(D, P), P);
+  Fe C8 = F::dbl(F::dbl(F::dbl(C, P), P), P);
+  r.Y = F::sub(F::mul(E, F::sub(D, r.X, P), P), C8, P);
+  r.Z = F::dbl(F::mul(p.Y, p.Z, P), P);
   return r;
 }
 
@@ -126,17 +133,17 @@ MP_NOINLINE Jac jac_add(const Jac& p, const Jac& q, const Modulus& P) {
   Fe Z1Z1 = F::sqr(p.Z, P), Z2Z2 = F::sqr(q.Z, P);
   Fe U1 = F::mul(p.X, Z2Z2, P), U2 = F::mul(q.X, Z1Z1, P);
   Fe S1 = F::mul(F::mul(p.Y, q.Z, P), Z2Z2, P), S2 = F::mul(F::mul(q.Y, p.Z, P), Z1Z1, P);
-  Fe H = sub(U2, U1, P), rr = sub(S2, S1, P);
+  Fe H = F::sub(U2, U1, P), rr = F::sub(S2, S1, P);
   if (is_zero(H)) {
     if (is_zero(rr)) return jac_dbl(p, P);
     return jac_infinity(P);
   }
-  Fe I = F::sqr(dbl(H, P), P), J = F::mul(H, I, P), r2 = dbl(rr, P), V = F::mul(U1, I, P);
+  Fe I = F::sqr(F::dbl(H, P), P), J = F::mul(H, I, P), r2 = F::dbl(rr, P), V = F::mul(U1, I, P);
   Jac r;
-  r.X = sub(sub(F::sqr(r2, P), J, P), dbl(V, P), P);
-  r.Y = sub(F::mul(r2, sub(V, r.X, P), P), dbl(F::mul(S1, J, P), P), P);
-  Fe zz = add(p.Z, q.Z, P);
-  r.Z = F::mul(sub(sub(F::sqr(zz, P), Z1Z1, P), Z2Z2, P), H, P);
+  r.X = F::sub(F::sub(F::sqr(r2, P), J, P), F::dbl(V, P), P);
+  r.Y = F::sub(F::mul(r2, F::sub(V, r.X, P), P), F::dbl(F::mul(S1, J, P), P), P);
+  Fe zz = F::add(p.Z, q.Z, P);
+  r.Z = F::mul(F::sub(F::sub(F::sqr(zz, P), Z1Z1, P), Z2Z2, P), H, P);
   return r;
 }
 
@@ -147,16 +154,16 @@ MP_NOINLINE Jac jac_madd(const Jac& p, const Aff& q, const Modulus& P) {
   if (jac_is_inf(p)) return jac_from_aff(q, P);
   Fe Z1Z1 = F::sqr(p.Z, P);
   Fe U2 = F::mul(q.x, Z1Z1, P), S2 = F::mul(F::mul(q.y, p.Z, P), Z1Z1, P);
-  Fe H = sub(U2, p.X, P), rr = sub(S2, p.Y, P);
+  Fe H = F::sub(U2, p.X, P), rr = F::sub(S2, p.Y, P);
   if (is_zero(H)) {
     if (is_zero(rr)) return jac_dbl(p, P);
     return jac_infinity(P);
   }
-  Fe HH = F::sqr(H, P), I = dbl(dbl(HH, P), P), J = F::mul(H, I, P), r2 = dbl(rr, P), V = F::mul(p.X, I, P);
+  Fe HH = F::sqr(H, P), I = F::dbl(F::dbl(HH, P), P), J = F::mul(H, I, P), r2 = F::dbl(rr, P), V = F::mul(p.X, I, P);
   Jac r;
-  r.X = sub(sub(F::sqr(r2, P), J, P), dbl(V, P), P);
-  r.Y = sub(F::mul(r2, sub(V, r.X, P), P), dbl(F::mul(p.Y, J, P), P), P);
-  r.Z = sub(sub(F::sqr(add(p.Z, H, P), P), Z1Z1, P), HH, P);
+  r.X = F::sub(F::sub(F::sqr(r2, P), J, P), F::dbl(V, P), P);
+  r.Y = F::sub(F::mul(r2, F::sub(V, r.X, P), P), F::dbl(F::mul(p.Y, J, P), P), P);
+  r.Z = F::sub(F::sub(F::sqr(F::add(p.Z, H, P), P), Z1Z1, P), HH, P);
   return r;
 }
 
@@ -218,11 +225,11 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
   for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(x.v[i], P.m[i]);
   if (simt::subc(0, 0) == 0) return false;
   Fe xm = F::to_mont(x, P);
-  Fe y2 = add(F::mul(F::sqr(xm, P), xm, P), load(C.b7), P);
+  Fe y2 = F::add(F::mul(F::sqr(xm, P), xm, P), load(C.b7), P);
   Fe y = F::pow(y2, C.sqrt_e, P);
   if (!eq(F::sqr(y, P), y2)) return false;
   Fe yn = F::from_mont(y, P);
-  if ((yn.v[0] & 1u) != (uint32_t)(in[0] & 1)) y = neg(y, P);
+  if ((yn.v[0] & 1u) != (uint32_t)(in[0] & 1)) y = F::neg(y, P);
   a.x = xm;
   a.y = y;
   return true;

@@ -147,3 +147,30 @@ def test_medium_box_properties(pair):
     sbs = dealer.extract_secret_shares(box, sks[5:5 + t], ws[5:5 + t])
     assert all(dealer.verify_shares(sbs, box, pks[5:5 + t]))
     assert dealer.reconstruct(sbs, box) == SECRET
+
+
+def test_dleq_wrapper_matches_reference_semantics(pair):
+    """src/dleq.rs tests restated (dleq.rs:357-441): a1/a2, r = w - alpha*c, prove -> verify round trip."""
+    import hashlib
+    g, og = pair
+    rng = random.Random(77)
+    order = og.order()
+    alpha, w = rng.randrange(1, order), rng.randrange(1, order)
+    g1 = og.generator()
+    g2 = og.exp(og.generator(), rng.randrange(1, order))
+    h1, h2 = og.exp(g1, alpha), og.exp(g2, alpha)
+    E = og.element_to_bytes
+    d = m.DLEQ(g)
+    d.init(E(g1), E(h1), E(g2), E(h2), alpha, w)
+    assert d.get_a1() == E(og.exp(g1, w)) and d.get_a2() == E(og.exp(g2, w))
+    hasher = hashlib.sha256()
+    d.update_hash(hasher)
+    d.c = m.hash_to_scalar(g, hasher.digest())
+    oh = hashlib.sha256()
+    pvss.append_transcript(og, h1, h2, og.exp(g1, w), og.exp(g2, w), oh)
+    assert d.c == pvss.challenge_from(og, oh)
+    d.r = d.get_r()
+    assert d.r == pvss.prover_response(og, w, alpha, d.c)
+    assert d.verify() is True
+    d.r = (d.r + 1) % order
+    assert d.verify() is False

@@ -208,3 +208,28 @@ def test_config2_properties(modp_group, n, t):
     sbs = dealer.extract_secret_shares(box, sks[:t], ws[:t])
     assert all(dealer.verify_shares(sbs, box, pks[:t]))
     assert dealer.reconstruct(sbs, box) == SECRET
+
+
+def test_dleq_and_pvss_wrappers(modp_group):
+    """dleq.rs:380-403 (r = w - alpha*c mod q-1) and a prove/verify round trip through the DLEQ mirror;
+    mpvss.rs:151-287 through the PVSS mirror."""
+    import hashlib
+    import mpvss_rs_b200 as m
+    d = m.DLEQ(modp_group)
+    w, alpha, c = 81647, 163027, 127997
+    d.init(4, pow(4, alpha, Q), 2, pow(2, alpha, Q), alpha, w)
+    d.c = c
+    assert d.get_r() == (w - alpha * c) % (Q - 1)
+    assert d.get_a1() == pow(4, w, Q) and d.get_a2() == pow(2, w, Q)
+    hasher = hashlib.sha256()
+    d.update_hash(hasher)
+    d.c = m.hash_to_scalar(modp_group, hasher.digest())
+    d.r = d.get_r()
+    assert d.verify() is True
+    d.c += 1
+    assert d.verify() is False
+    n, t = 4, 3
+    sks, co, ws = _setup(n, t, 321)
+    pks = modp_group.fixed_base_exp(sks)
+    box = m.Participant(modp_group).distribute_secret(SECRET, pks, t, coeffs=co, witnesses=ws)
+    assert m.PVSS(modp_group).verify_distribution_shares(box) is True

@@ -63,4 +63,7 @@ full("prof_horner_final.ncu-rep", f"horner_{RND}_ncu.txt",
 full("prof_ec_horner_secp.ncu-rep", f"ec_horner_secp256k1_{RND}_ncu.txt",
      "ncu --set full --clock-control none -k regex:horner_kernel -c 1 python bench.py --group secp256k1 --steps 1 --warmup 0\n"
      "ec::horner_kernel<secp::SecpCurve> (n = 4096, t = 2731, 16 chunks); selected raw metrics")
+full("prof_ec_horner_rist.ncu-rep", f"ec_horner_ristretto255_{RND}_ncu.txt",
+     "ncu --set full --clock-control none -k regex:horner_kernel -s 1 -c 1 python bench.py --group ristretto255 --steps 1 --warmup 1\n"
+     "ec::horner_kernel<rist::RistCurve> (n = 4096, t = 2731, 16 chunks); selected raw metrics")
 print(open(os.path.join(P, f"launches_{RND}_summary.txt")).read())
