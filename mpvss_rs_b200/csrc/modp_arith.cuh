@@ -168,8 +168,9 @@ MP_DEV void mm_digit(uint32_t (&P)[Cfg<TPI>::L + 2], uint32_t (&S)[Cfg<TPI>::L +
   }
   P[L] = simt::addc(P[L], 0);
   // P[0] is now the limb that leaves this lane's window (zero on group lane 0)
-  uint32_t out = simt::shfl(P[0], (int)simt::lane_id() + 1);
-  in = (ln.k == TPI - 1) ? 0u : out;
+  // The top lane of a group reads lane 0 of the next group (lane 31 wraps to lane 0), whose P[0] is
+  // exactly zero here (P[0] + q[0]*m = 0 mod 2^32 by the choice of m): no select needed.
+  in = simt::shfl(P[0], ((int)simt::lane_id() + 1) & 31);
 }
 
 // Fold the two accumulators of a finished digit loop (last call had P = A1, S = A0), hand the
@@ -211,21 +212,33 @@ MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L
   constexpr int L = Cfg<TPI>::L;
   uint32_t A0[L + 2], A1[L + 2];
   uint32_t in = 0;
-  const uint4* b4 = reinterpret_cast<const uint4*>(bs);
+  // Each accumulator array moves down one 64-bit pair every second digit, so the register
+  // assignment repeats after PER = L + 2 digits: a loop body of exactly PER digits closes on
+  // itself without the register moves a 4-digit body needs at its back edge (13 % of the
+  // instructions).  64 mod PER digits are peeled in front (4, 4, 10 for L = 4, 8, 16).
+  constexpr int PER = L + 2, PEEL = 64 % PER;
+  static_assert(PEEL >= 2 && PEEL % 2 == 0 && PER % 2 == 0, "digit loop layout");
+  const uint2* b2 = reinterpret_cast<const uint2*>(bs);
   {
-    uint4 bw = b4[0];
+    uint2 bw = b2[0];
     mm_digit<TPI, true>(A0, A1, a, bw.x, M, ln, in);
     mm_digit<TPI, false>(A1, A0, a, bw.y, M, ln, in);
-    mm_digit<TPI, false>(A0, A1, a, bw.z, M, ln, in);
-    mm_digit<TPI, false>(A1, A0, a, bw.w, M, ln, in);
   }
-#pragma unroll 1
-  for (int j = 1; j < 16; ++j) {
-    uint4 bw = b4[j];
+#pragma unroll
+  for (int d = 2; d < PEEL; d += 2) {
+    uint2 bw = b2[d / 2];
     mm_digit<TPI, false>(A0, A1, a, bw.x, M, ln, in);
     mm_digit<TPI, false>(A1, A0, a, bw.y, M, ln, in);
-    mm_digit<TPI, false>(A0, A1, a, bw.z, M, ln, in);
-    mm_digit<TPI, false>(A1, A0, a, bw.w, M, ln, in);
+  }
+#pragma unroll 1
+  for (int it = 0; it < (64 - PEEL) / PER; ++it) {
+    const uint2* p = b2 + (PEEL + it * PER) / 2;
+#pragma unroll
+    for (int d = 0; d < PER; d += 2) {
+      uint2 bw = p[d / 2];
+      mm_digit<TPI, false>(A0, A1, a, bw.x, M, ln, in);
+      mm_digit<TPI, false>(A1, A0, a, bw.y, M, ln, in);
+    }
   }
   mm_finish<TPI>(r, A0, A1, in, M, ln);
 }

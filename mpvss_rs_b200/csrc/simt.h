@@ -95,6 +95,9 @@ MP_DEV void syncwarp() { __syncwarp(); }
 #define MP_HOSTDEV inline
 #define MP_NOINLINE inline
 
+struct alignas(8) uint2 {
+  uint32_t x, y;
+};
 struct alignas(16) uint4 {
   uint32_t x, y, z, w;
 };
