@@ -46,12 +46,14 @@ void fill_consts(const big::Int& m, uint32_t* blk) {
   R[64] = 1;
   big::Int nq = big::sub(R, m), one = big::mod(R, m), r2 = big::mulmod(one, one, m);
   auto put = [&](const big::Int& v, int off) {
-    for (size_t i = 0; i < v.size(); ++i) blk[off + i] = v[i];
+    for (size_t i = 0; i < v.size() && i < 64; ++i) blk[off + i] = v[i];
   };
   put(m, modp::C_Q);
   put(nq, modp::C_NQ);
   put(one, modp::C_ONE);
   put(r2, modp::C_R2);
+  big::Int one1(1, 1);
+  put(big::shr1(big::add(m, one1)), modp::C_QH);
   uint32_t inv = 1, m0 = m[0];  // Newton: inv = m0^-1 mod 2^32
   for (int i = 0; i < 5; ++i) inv *= 2u - m0 * inv;
   blk[modp::C_NP] = 0u - inv;

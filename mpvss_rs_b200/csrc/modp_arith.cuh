@@ -48,6 +48,7 @@ struct Mod {
   uint32_t q[L];   // limbs [k*L, k*L+L) of q
   uint32_t nq[L];  // same slice of 2^2048 - q
   uint32_t np;     // -q^{-1} mod 2^32
+  const uint32_t* qh;  // 64 limbs of (q + 1) / 2 in global memory (mont_sqr only)
 };
 
 // Identity of a lane inside its group.
@@ -175,7 +176,7 @@ MP_DEV void mm_digit(uint32_t (&P)[Cfg<TPI>::L + 2], uint32_t (&S)[Cfg<TPI>::L +
 
 // Fold the two accumulators of a finished digit loop (last call had P = A1, S = A0), hand the
 // window overflows to the next lane, resolve carries and apply the conditional subtraction.
-template <int TPI>
+template <int TPI, bool DOUBLE = false>
 MP_DEV void mm_finish(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&A0)[Cfg<TPI>::L + 2],
                       const uint32_t (&A1)[Cfg<TPI>::L + 2], uint32_t in, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   constexpr int L = Cfg<TPI>::L;
@@ -201,7 +202,26 @@ MP_DEV void mm_finish(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&A0)[Cfg<TPI>:
   for (int i = 1; i < L; ++i) r[i] = simt::addc_cc(r[i], 0);
   // value >= 2^2048  ->  subtract q once (add 2^2048 - q, drop the carry)
   uint32_t over = ovtop + cout;
-  (void)add_resolve<TPI>(r, M.nq, 0u - over, ln);
+  if (!DOUBLE) {
+    (void)add_resolve<TPI>(r, M.nq, 0u - over, ln);
+  } else {
+    // mont_sqr: the loop produced V with 2V = a^2 / 2^2048 (mod q), V <= 2^2047 + q.  Double across
+    // the lanes (the bit leaving a lane enters the next one), then take q off at most twice:
+    // 2V <= 2^2048 + 2q, and after the first subtraction a value in [2^2048, 2^2048 + nq) is still
+    // possible, which the second round catches through the carry of the first.
+    uint32_t top = r[L - 1] >> 31;
+    uint32_t bit_in = simt::shfl(top, ((int)simt::lane_id() - 1) & 31);
+    uint32_t top_all = simt::shfl(top, ln.lane0 + TPI - 1);
+    if (ln.k == 0) bit_in = 0;
+#pragma unroll
+    for (int i = L - 1; i >= 1; --i) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+    r[0] = (r[0] << 1) | bit_in;
+    uint32_t over2 = 2u * over + top_all;                 // 0, 1 or 2
+    uint32_t m1 = over2 ? 0xffffffffu : 0u;
+    uint32_t c1 = add_resolve<TPI>(r, M.nq, m1, ln);
+    over2 = over2 - (m1 & 1u) + c1;
+    (void)add_resolve<TPI>(r, M.nq, over2 ? 0xffffffffu : 0u, ln);
+  }
 }
 
 // r = a * b * 2^-2048 mod q, result in [0, 2^2048).  `bs` points at the 64 limbs of
@@ -241,6 +261,170 @@ MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L
     }
   }
   mm_finish<TPI>(r, A0, A1, in, M, ln);
+}
+
+// ---- dedicated squaring ----------------------------------------------------------------------
+// r = a * a * 2^-2048 mod q through the same fused digit loop, issuing L/2 + 1 instead of L
+// multiply-accumulates of a per row (5 of 8 at TPI = 8; 13 instead of 16 wide MACs per row with
+// the reduction).  Every unordered pair {i, j}, i != j, of limbs is multiplied exactly once, in the
+// row of the limb the other one follows within half a period: row j (digit a_j) takes limb i when
+//     d = (i - j) mod L  is in [1, L/2 - 1]          (every lane, every row)
+//     d = L/2 or d = 0 (i != j)  and  i > j          (one MAC slot each, digit masked per lane)
+// so each lane runs the same L/2 + 1 MAC slots in every row and no lane idles.  Off-diagonal
+// products would have to be doubled; instead the loop accumulates HALF the square,
+//     T'' = (a^2 + p*q) / 2,   p = a mod 2   (a^2 + p*q is even and congruent to a^2),
+// i.e. off-diagonal products once, the squares a_i^2 halved, and p*(q+1)/2 as the start value.
+// The halved squares of a lane's own limbs form one 2L-word number h = (sum a_i^2 B^(2i)) >> 1
+// that is added to the window in two pieces (rows L*k and L*k + L - 2 of the lane's own block k);
+// the bit shifted out at the bottom belongs to column 2Lk - 1, which lane k-1 holds at offset L-1.
+// The fused reduction then yields V with 2V = a^2 * 2^-2048 (mod q); mm_finish<DOUBLE> doubles it.
+struct SqMasks {
+  uint32_t gt, ge, eq, prev;  // all-ones if this lane's index is >, >=, == the block's / == block - 1
+};
+
+template <int TPI, int RP>
+MP_DEV void sq_digit(uint32_t (&P)[Cfg<TPI>::L + 2], uint32_t (&S)[Cfg<TPI>::L + 2],
+                     const uint32_t (&a)[Cfg<TPI>::L], const uint32_t (&h)[2 * Cfg<TPI>::L], uint32_t pbn31,
+                     uint32_t b, const SqMasks& mk, const Mod<Cfg<TPI>::L>& M, const Lane& ln, uint32_t& in) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int H = L / 2;
+  // halved squares of the lane's own limbs (only the lane that owns this block adds anything)
+  if (RP == 0) {
+    P[0] = simt::add_cc(P[0], h[0] & mk.eq);
+#pragma unroll
+    for (int i = 1; i <= L + 1; ++i) {
+      uint32_t v = h[i] & mk.eq;
+      if (i == L - 1) v |= pbn31 & mk.prev;
+      P[i] = simt::addc_cc(P[i], v);
+    }
+  } else if (RP == L - 2) {
+    P[4] = simt::add_cc(P[4], h[L + 2] & mk.eq);
+#pragma unroll
+    for (int i = 5; i <= L + 1; ++i) P[i] = simt::addc_cc(P[i], h[L - 2 + i] & mk.eq);
+  }
+  const uint32_t b_tie = b & (RP < H ? mk.ge : mk.gt);
+  const uint32_t b_gt = b & mk.gt;
+  // limb shifted in from lane k+1 lands on (new) column L-1 = S[L] before the shift
+  S[L] = simt::add_cc(S[L], in);
+  S[L + 1] = simt::addc(S[L + 1], 0);
+  // stray high half of the dropped pair -> column 0; its carry feeds the odd chain
+  P[0] = simt::add_cc(P[0], S[1]);
+#pragma unroll
+  for (int x = 0; x < L; x += 2) {
+    const int sl = (x + 1 - RP + L) % L;  // slot of limb x + 1 in this row
+    if (sl <= H) {
+      const uint32_t d = sl == 0 ? b_gt : (sl == H ? b_tie : b);
+      S[x] = simt::madc_lo_cc(a[x + 1], d, S[x + 2]);
+      S[x + 1] = simt::madc_hi_cc(a[x + 1], d, S[x + 3]);
+    } else {
+      S[x] = simt::addc_cc(S[x + 2], 0);
+      S[x + 1] = simt::addc_cc(S[x + 3], 0);
+    }
+  }
+  S[L] = simt::addc(0, 0);
+  S[L + 1] = 0;
+  bool started = false;
+#pragma unroll
+  for (int i = 0; i < L; i += 2) {
+    const int sl = (i - RP + L) % L;
+    if (sl <= H) {
+      const uint32_t d = sl == 0 ? b_gt : (sl == H ? b_tie : b);
+      P[i] = started ? simt::madc_lo_cc(a[i], d, P[i]) : simt::mad_lo_cc(a[i], d, P[i]);
+      P[i + 1] = simt::madc_hi_cc(a[i], d, P[i + 1]);
+      started = true;
+    } else if (started) {
+      P[i] = simt::addc_cc(P[i], 0);
+      P[i + 1] = simt::addc_cc(P[i + 1], 0);
+    }
+  }
+  P[L] = simt::addc_cc(P[L], 0);
+  P[L + 1] = simt::addc(P[L + 1], 0);
+  // reduction half of the row: identical to mm_digit, except that the top pair of P can hold a
+  // full word right after a block addition, so its carry goes on into P[L + 1]
+  uint32_t m = simt::shfl(simt::mul_lo(P[0], M.np), ln.lane0);
+  S[0] = simt::mad_lo_cc(M.q[1], m, S[0]);
+  S[1] = simt::madc_hi_cc(M.q[1], m, S[1]);
+#pragma unroll
+  for (int i = 3; i < L; i += 2) {
+    S[i - 1] = simt::madc_lo_cc(M.q[i], m, S[i - 1]);
+    S[i] = simt::madc_hi_cc(M.q[i], m, S[i]);
+  }
+  S[L] = simt::addc(S[L], 0);
+  P[0] = simt::mad_lo_cc(M.q[0], m, P[0]);
+  P[1] = simt::madc_hi_cc(M.q[0], m, P[1]);
+#pragma unroll
+  for (int i = 2; i < L; i += 2) {
+    P[i] = simt::madc_lo_cc(M.q[i], m, P[i]);
+    P[i + 1] = simt::madc_hi_cc(M.q[i], m, P[i + 1]);
+  }
+  P[L] = simt::addc_cc(P[L], 0);
+  P[L + 1] = simt::addc(P[L + 1], 0);
+  in = simt::shfl(P[0], ((int)simt::lane_id() + 1) & 31);
+}
+
+template <int TPI, int RP, bool END = (RP >= Cfg<TPI>::L)>
+struct SqRows {
+  static MP_DEV void run(uint32_t (&A0)[Cfg<TPI>::L + 2], uint32_t (&A1)[Cfg<TPI>::L + 2],
+                         const uint32_t (&a)[Cfg<TPI>::L], const uint32_t (&h)[2 * Cfg<TPI>::L], uint32_t pbn31,
+                         const uint2* bp, const SqMasks& mk, const Mod<Cfg<TPI>::L>& M, const Lane& ln,
+                         uint32_t& in) {
+    uint2 bw = bp[RP / 2];
+    sq_digit<TPI, RP>(A0, A1, a, h, pbn31, bw.x, mk, M, ln, in);
+    sq_digit<TPI, RP + 1>(A1, A0, a, h, pbn31, bw.y, mk, M, ln, in);
+    SqRows<TPI, RP + 2>::run(A0, A1, a, h, pbn31, bp, mk, M, ln, in);
+  }
+};
+template <int TPI, int RP>
+struct SqRows<TPI, RP, true> {
+  static MP_DEV void run(uint32_t (&)[Cfg<TPI>::L + 2], uint32_t (&)[Cfg<TPI>::L + 2], const uint32_t (&)[Cfg<TPI>::L],
+                         const uint32_t (&)[2 * Cfg<TPI>::L], uint32_t, const uint2*, const SqMasks&,
+                         const Mod<Cfg<TPI>::L>&, const Lane&, uint32_t&) {}
+};
+
+// r = a^2 * 2^-2048 mod q, result in [0, 2^2048).  `as` points at the 64 limbs of a in shared
+// memory (the digits of the rows); r may alias a.
+template <int TPI>
+MP_DEV void mont_sqr(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* as,
+                     const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t h[2 * L];
+  {
+    uint32_t w[2 * L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      w[2 * i] = simt::mul_lo(a[i], a[i]);
+      w[2 * i + 1] = simt::mul_hi(a[i], a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * L - 1; ++i) h[i] = (w[i] >> 1) | (w[i + 1] << 31);
+    h[2 * L - 1] = w[2 * L - 1] >> 1;
+    h[0] |= 0;
+    // parity bit of the lane's block: to lane k-1 (column 2Lk - 1), lane 0's selects (q+1)/2
+    const uint32_t pb = w[0] & 1u;
+    const uint32_t pbn = simt::shfl(pb, ((int)simt::lane_id() + 1) & 31);
+    const uint32_t pb0 = simt::shfl(pb, ln.lane0);
+    uint32_t A0[L + 2], A1[L + 2];
+    const uint32_t m0 = 0u - pb0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      A0[i] = M.qh[ln.k * L + i] & m0;
+      A1[i] = 0;
+    }
+    A0[L] = A0[L + 1] = A1[L] = A1[L + 1] = 0;
+    uint32_t in = 0;
+    const uint32_t pbn31 = pbn << 31;
+    const uint2* b2 = reinterpret_cast<const uint2*>(as);
+#pragma unroll 1
+    for (int kp = 0; kp < TPI; ++kp) {
+      SqMasks mk;
+      mk.gt = ln.k > kp ? 0xffffffffu : 0u;
+      mk.ge = ln.k >= kp ? 0xffffffffu : 0u;
+      mk.eq = ln.k == kp ? 0xffffffffu : 0u;
+      mk.prev = ln.k + 1 == kp ? 0xffffffffu : 0u;
+      SqRows<TPI, 0>::run(A0, A1, a, h, pbn31, b2 + kp * (L / 2), mk, M, ln, in);
+    }
+    mm_finish<TPI, true>(r, A0, A1, in, M, ln);
+  }
 }
 
 // Two independent Montgomery products on the same lane group, digit loops interleaved so that

@@ -16,14 +16,15 @@ namespace modp {
 
 // Layout of the constant block (device global memory, u32 limbs):
 //   [0,64) q   [64,128) 2^2048-q   [128,192) R mod q (Montgomery one)
-//   [192,256) R^2 mod q   [256] -q^-1 mod 2^32
-enum { C_Q = 0, C_NQ = 64, C_ONE = 128, C_R2 = 192, C_NP = 256, C_WORDS = 260 };
+//   [192,256) R^2 mod q   [256] -q^-1 mod 2^32   [260,324) (q+1)/2
+enum { C_Q = 0, C_NQ = 64, C_ONE = 128, C_R2 = 192, C_NP = 256, C_QH = 260, C_WORDS = 324 };
 
 template <int TPI>
 MP_DEV void load_mod(Mod<Cfg<TPI>::L>& M, const uint32_t* consts, const Lane& ln) {
   load_slice<TPI>(M.q, consts + C_Q, ln);
   load_slice<TPI>(M.nq, consts + C_NQ, ln);
   M.np = consts[C_NP];
+  M.qh = consts + C_QH;
 }
 
 // copy 64 limbs global -> this warp's shared buffer (lane l moves limbs 2l, 2l+1)
@@ -38,7 +39,14 @@ template <int TPI>
 MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   stage_shared<TPI>(sq, acc, ln);
   simt::syncwarp();
+  // mont_sqr issues 13 instead of 16 wide MACs per row but 10 more carry/select instructions; on
+  // B200 the two cancel (Horner launch 263 ms against 255 ms), so the hot path
+  // squares through mont_mul unless MPVSS_MODP_DEDICATED_SQR is defined.
+#ifdef MPVSS_MODP_DEDICATED_SQR
+  mont_sqr<TPI>(acc, acc, sq, M, ln);
+#else
   mont_mul<TPI>(acc, acc, sq, M, ln);
+#endif
 }
 
 // Leave Montgomery form (multiply by 1), reduce below q, store 64 limbs.
@@ -528,6 +536,7 @@ struct MulArgs {
   uint32_t* out;
   uint32_t n;
   uint32_t mode;       // 0: out = a*b mod q (canonical)   1: out = a*R mod q (to Montgomery form)
+                       // 2: out = a*a/R mod q, a taken as is (any value below 2^2048; squaring test)
   uint32_t a_stride, b_stride;
 };
 
@@ -551,7 +560,13 @@ MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
   simt::syncwarp();
   uint32_t acc[L];
   load_slice<TPI>(acc, A.a + (size_t)inst * A.a_stride, ln);
-  mont_mul<TPI>(acc, acc, r2, M, ln);  // a*R
+  if (A.mode == 2) {
+    stage_shared<TPI>(sq, acc, ln);
+    simt::syncwarp();
+    mont_sqr<TPI>(acc, acc, sq, M, ln);
+  } else {
+    mont_mul<TPI>(acc, acc, r2, M, ln);  // a*R
+  }
   if (A.mode == 0) {
     uint32_t y[L];
     load_slice<TPI>(y, A.b + (size_t)inst * A.b_stride, ln);

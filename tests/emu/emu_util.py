@@ -25,12 +25,13 @@ def from_limbs(a):
 
 def consts_block(q):
     R = 1 << 2048
-    blk = np.zeros(260, dtype=np.uint32)
+    blk = np.zeros(324, dtype=np.uint32)
     blk[0:64] = to_limbs(q)
     blk[64:128] = to_limbs(R - q)
     blk[128:192] = to_limbs(R % q)
     blk[192:256] = to_limbs(R * R % q)
     blk[256] = (-pow(q, -1, 1 << 32)) % (1 << 32)
+    blk[260:324] = to_limbs((q + 1) // 2)
     return blk
 
 

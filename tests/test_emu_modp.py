@@ -51,6 +51,28 @@ def test_mont_mul_edge_patterns(lib, tpi, modulus):
 
 
 @pytest.mark.parametrize("tpi", [4, 8, 16])
+@pytest.mark.parametrize("modulus", ["q", "g"])
+def test_mont_sqr_edge_patterns(lib, tpi, modulus):
+    """Dedicated squaring (half-square accumulation + doubling): a*a/R mod m for any a < 2^2048,
+    odd and even a, saturated limbs, values at and above the modulus."""
+    m = Q if modulus == "q" else G.g
+    C = eu.consts_block(m)
+    rng = random.Random(tpi * 7 + len(modulus))
+    n = 96
+    A = [_struct(rng) for _ in range(n)]
+    A[:12] = [R - 1, 0, 1, 2, m - 1, m, m + 5, R - 2, (1 << 2047), (1 << 2047) + 1, (1 << 32) - 1, R - (1 << 31)]
+    for k in range(8):                       # a single saturated limb in every lane block, odd and even
+        A[12 + k] = 0xFFFFFFFF << (32 * (8 * k + (k % 8)))
+        A[20 + k] = (0xFFFFFFFF << (32 * (8 * k))) | 1
+    a = np.concatenate([eu.to_limbs(x) for x in A])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, None, 0, n, 2, eu.P(out)) == 0
+    rinv = pow(R, -1, m)
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * A[i] * rinv % m, (tpi, i)
+
+
+@pytest.mark.parametrize("tpi", [4, 8, 16])
 def test_horner_kernel_equals_reference_schedule(lib, tpi):
     C = eu.consts_block(Q)
     rng = random.Random(tpi)
