@@ -108,11 +108,17 @@ MP_DEV void sqr_wide(uint32_t (&t)[16], const Fe& a) {
   }
 }
 
-// r[0..8] = lo[0..7] + hi[0..7] * k   (k < 2^32)
-MP_DEV void fold_small(uint32_t (&r)[9], const uint32_t* lo, const uint32_t* hi, uint32_t k) {
-  uint32_t E[10], O[10];
+// r[0..8] + r9 * 2^288 = lo[0..7] + hi[0..7] * k (+ hi * 2^32 when SHIFTED), k < 2^32.  lo and the
+// shifted copy of hi are the start values of the even / odd column accumulators, so the whole sum
+// costs the 8 MACs and one combining pass.
+template <bool SHIFTED>
+MP_DEV void fold(uint32_t (&r)[9], uint32_t& r9, const uint32_t* lo, const uint32_t* hi, uint32_t k) {
+  uint32_t E[9], O[9];  // E[x]: column x ; O[x]: column x + 1
 #pragma unroll
-  for (int x = 0; x < 10; ++x) E[x] = O[x] = 0;
+  for (int x = 0; x < 8; ++x) {
+    E[x] = lo[x];
+    O[x] = SHIFTED ? hi[x] : 0u;
+  }
   E[0] = simt::mad_lo_cc(hi[0], k, E[0]);
   E[1] = simt::madc_hi_cc(hi[0], k, E[1]);
 #pragma unroll
@@ -120,6 +126,7 @@ MP_DEV void fold_small(uint32_t (&r)[9], const uint32_t* lo, const uint32_t* hi,
     E[j] = simt::madc_lo_cc(hi[j], k, E[j]);
     E[j + 1] = simt::madc_hi_cc(hi[j], k, E[j + 1]);
   }
+  E[8] = simt::addc(0, 0);
   O[0] = simt::mad_lo_cc(hi[1], k, O[0]);
   O[1] = simt::madc_hi_cc(hi[1], k, O[1]);
 #pragma unroll
@@ -127,17 +134,12 @@ MP_DEV void fold_small(uint32_t (&r)[9], const uint32_t* lo, const uint32_t* hi,
     O[j - 1] = simt::madc_lo_cc(hi[j], k, O[j - 1]);
     O[j] = simt::madc_hi_cc(hi[j], k, O[j]);
   }
-  // hi * k = E + (O << 32), at most 9 limbs
-  uint32_t u[9];
-  u[0] = E[0];
-  u[1] = simt::add_cc(E[1], O[0]);
+  O[8] = simt::addc(0, 0);
+  r[0] = E[0];
+  r[1] = simt::add_cc(E[1], O[0]);
 #pragma unroll
-  for (int x = 2; x < 8; ++x) u[x] = simt::addc_cc(E[x], O[x - 1]);
-  u[8] = simt::addc(0, O[7]);
-  r[0] = simt::add_cc(u[0], lo[0]);
-#pragma unroll
-  for (int x = 1; x < 8; ++x) r[x] = simt::addc_cc(u[x], lo[x]);
-  r[8] = simt::addc(u[8], 0);
+  for (int x = 2; x < 9; ++x) r[x] = simt::addc_cc(E[x], O[x - 1]);
+  r9 = simt::addc(O[8], 0);
 }
 
 // The two primes as compile-time limbs: every use below unrolls to immediates, no loads.
@@ -188,42 +190,29 @@ MP_DEV Fe sub_p(const Fe& a, const Fe& b) {
 // ---- secp256k1: 2^256 = 2^32 + 977 (mod p) -----------------------------------------------------
 MP_DEV Fe secp_reduce(const uint32_t (&t)[16]) {
   // r = lo + hi*977 + (hi << 32)   (< 2^290)
-  uint32_t r[9];
-  fold_small(r, t, t + 8, 977u);
-  uint32_t r9;
-  r[1] = simt::add_cc(r[1], t[8]);
-#pragma unroll
-  for (int x = 2; x < 8; ++x) r[x] = simt::addc_cc(r[x], t[8 + x - 1]);
-  r[8] = simt::addc_cc(r[8], t[15]);
-  r9 = simt::addc(0, 0);
-  // second fold of the part above 2^256: top = r[8] + r9 * 2^32 (< 2^34)
-  // top * (2^32 + 977) = top*977 + (top << 32)
-  uint32_t lo977 = simt::mul_lo(r[8], 977u), hi977 = simt::mul_hi(r[8], 977u) + r9 * 977u;
+  uint32_t r[9], r9;
+  fold<true>(r, r9, t, t + 8, 977u);
+  // second fold of the part above 2^256: top = r[8] + r9 * 2^32 (< 2^34),
+  // top * (2^32 + 977) = top*977 + (top << 32), three words w0..w2
+  uint32_t w0 = simt::mul_lo(r[8], 977u), w1 = simt::mul_hi(r[8], 977u) + r9 * 977u;
+  w1 = simt::add_cc(w1, r[8]);
+  uint32_t w2 = simt::addc(r9, 0);
   Fe s;
-  s.v[0] = simt::add_cc(r[0], lo977);
-  s.v[1] = simt::addc_cc(r[1], hi977);
-  s.v[2] = simt::addc_cc(r[2], 0);
+  s.v[0] = simt::add_cc(r[0], w0);
+  s.v[1] = simt::addc_cc(r[1], w1);
+  s.v[2] = simt::addc_cc(r[2], w2);
 #pragma unroll
   for (int x = 3; x < 8; ++x) s.v[x] = simt::addc_cc(r[x], 0);
   uint32_t c1 = simt::addc(0, 0);
-  s.v[1] = simt::add_cc(s.v[1], r[8]);
-  s.v[2] = simt::addc_cc(s.v[2], r9);
-#pragma unroll
-  for (int x = 3; x < 8; ++x) s.v[x] = simt::addc_cc(s.v[x], 0);
-  c1 += simt::addc(0, 0);
-  // a carry out of 2^256 is worth 2^32 + 977 again (the sum is then tiny, no further carry)
-  uint32_t m = 0u - c1;  // c1 is 0 or 1
-  s.v[0] = simt::add_cc(s.v[0], 977u & m);
-  s.v[1] = simt::addc_cc(s.v[1], 1u & m);
-#pragma unroll
-  for (int x = 2; x < 8; ++x) s.v[x] = simt::addc_cc(s.v[x], 0);
-  return cond_sub_p<SecpP>(s, 0);
+  // a carry out of 2^256 leaves a tiny s; 2^256 + s - p is what the conditional subtraction returns
+  return cond_sub_p<SecpP>(s, c1);
 }
 
 // ---- curve25519: 2^256 = 38 (mod p), p = 2^255 - 19 --------------------------------------------
 MP_DEV Fe ed_reduce(const uint32_t (&t)[16]) {
-  uint32_t r[9];
-  fold_small(r, t, t + 8, 38u);  // < 39 * 2^256
+  uint32_t r[9], r9;
+  fold<false>(r, r9, t, t + 8, 38u);  // < 39 * 2^256, r9 = 0
+  (void)r9;
   // fold r[8] (< 39) and bit 255: value = low255 + 19 * (2*r[8] + bit255)
   uint32_t top = (r[8] << 1) | (r[7] >> 31);
   Fe s;

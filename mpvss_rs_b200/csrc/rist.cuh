@@ -97,7 +97,7 @@ MP_DEV Ext ext_from_aff(const Aff& a, const Modulus& P) {
 }
 
 // add-2008-hwcd-3 (unified, complete for a = -1 and non-square d): 9M
-MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
+MP_NOINLINE Ext ext_add(Ext p, Ext q, const Consts& C) {
   using namespace F;
   const Modulus& P = C.P;
   Fe A = F::mul(F::sub(p.Y, p.X, P), F::sub(q.Y, q.X, P), P);
@@ -113,7 +113,7 @@ MP_NOINLINE Ext ext_add(const Ext& p, const Ext& q, const Consts& C) {
   return r;
 }
 // dbl-2008-hwcd with a = -1: 4M + 4S
-MP_NOINLINE Ext ext_dbl(const Ext& p, const Consts& C) {
+MP_NOINLINE Ext ext_dbl(Ext p, const Consts& C) {
   using namespace F;
   const Modulus& P = C.P;
   Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), Cc = F::dbl(F::sqr(p.Z, P), P);

@@ -109,7 +109,7 @@ MP_DEV Jac jac_neg(const Jac& p, const Modulus& P) {
 }
 
 // dbl-2009-l (a = 0): 2M + 5S
-MP_NOINLINE Jac jac_dbl(const Jac& p, const Modulus& P) {
+MP_NOINLINE Jac jac_dbl(Jac p, const Modulus& P) {
   using namespace F;
   if (jac_is_inf(p)) return p;
   Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), C = F::sqr(B, P);
@@ -126,7 +126,7 @@ MP_NOINLINE Jac jac_dbl(const Jac& p, const Modulus& P) {
 }
 
 // add-2007-bl with the exceptional cases handled: 11M + 5S
-MP_NOINLINE Jac jac_add(const Jac& p, const Jac& q, const Modulus& P) {
+MP_NOINLINE Jac jac_add(Jac p, Jac q, const Modulus& P) {
   using namespace F;
   if (jac_is_inf(p)) return q;
   if (jac_is_inf(q)) return p;
@@ -148,7 +148,7 @@ MP_NOINLINE Jac jac_add(const Jac& p, const Jac& q, const Modulus& P) {
 }
 
 // mixed addition (q affine): madd-2007-bl, 7M + 4S
-MP_NOINLINE Jac jac_madd(const Jac& p, const Aff& q, const Modulus& P) {
+MP_NOINLINE Jac jac_madd(Jac p, Aff q, const Modulus& P) {
   using namespace F;
   if (q.inf) return p;
   if (jac_is_inf(p)) return jac_from_aff(q, P);

@@ -52,6 +52,16 @@ def test_special_form_field(L, which, m):
         limbs = [rng.choice([0, 0xFFFFFFFF, 0xFFFFFFFE, 1, rng.getrandbits(32)]) for _ in range(8)]
         A.append(sum(l << (32 * i) for i, l in enumerate(limbs)) % m)
         B.append(sum(l << (32 * (7 - i)) for i, l in enumerate(limbs)) % m)
+    # products congruent to a small value v: after the first fold the 256-bit remainder sits just
+    # below 2^256, so the second fold wraps (secp: the carry handed to the conditional subtraction;
+    # 25519: the extra bit-255 wrap) -- unreachable with random operands
+    c = (1 << 256) % m
+    for v in [c - 1, c, c + 1, 2 * c, 2 * c + 1, 977 * c, (1 << 31) * c, (1 << 32) * c - 1, 19, 18, 20, 37, 38, 39,
+              (1 << 64) + c, 1, 0]:
+        for _ in range(6):
+            x = rng.randrange(1 << 200, m)
+            A.append(x)
+            B.append(v * pow(x, -1, m) % m)
     n = len(A)
     a = np.concatenate([eu.to_limbs(x, 8) for x in A])
     b = np.concatenate([eu.to_limbs(x, 8) for x in B])
