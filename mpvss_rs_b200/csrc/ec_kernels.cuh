@@ -176,7 +176,10 @@ MP_DEV void horner_body(const HornerArgs<Cv>& A, uint32_t tid) {
   Point acc = Cv::from_aff(load_aff<Cv>(A.cxy + (size_t)(hi - 1) * 16, A.cstatus[hi - 1]), C);
 #pragma unroll 1
   for (int j = (int)hi - 2; j >= (int)lo; --j) {
-    acc = small_mul<Cv>(acc, pos, nd, C);
+    if constexpr (Cv::kOwnSmallMul)
+      acc = Cv::small_mul(acc, pos, nd, C);
+    else
+      acc = small_mul<Cv>(acc, pos, nd, C);
     acc = Cv::madd(acc, load_aff<Cv>(A.cxy + (size_t)j * 16, A.cstatus[j]), C);
   }
   if (k > 0) {

@@ -219,6 +219,7 @@ struct RistCurve {
   using Point = Ext;
   using Affine = Aff;
   static constexpr int EB = 32;
+  static constexpr bool kOwnSmallMul = false;
   MP_DEV static Point infinity(const Consts& C) { return ext_identity(C.P); }
   MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return ext_from_aff(a, C.P); }
   MP_DEV static Point dbl(const Point& p, const Consts& C) { return ext_dbl(p, C); }

@@ -167,6 +167,59 @@ MP_NOINLINE Jac jac_madd(Jac p, Aff q, const Modulus& P) {
   return r;
 }
 
+// [k]p for a small scalar k < 4^nd (top base-4 digit non-zero), fixed 2-bit windows, with every
+// table entry affine.  Neither the doubling nor the addition formulas of a = 0 short Weierstrass
+// curves use b, so a Jacobian point (X : Y : Z) of y^2 = x^3 + b can be read as the *affine* point
+// (X, Y) of the isomorphic curve y^2 = x^3 + b Z^6; results computed there map back by multiplying
+// their Z by the scale.  Rescaling twice (by the Z of 2P, then by the Z of 3P) leaves P, 2P, 3P all
+// affine on one curve, so the window additions are mixed additions (7M + 4S instead of 11M + 5S).
+// The group element is the same as with the generic ladder: only the representative changes.
+MP_DEV Jac small_mul_iso(const Jac& p, uint32_t k, uint32_t nd, const Modulus& P) {
+  if (jac_is_inf(p)) return p;
+  Fe x1 = p.X, y1 = p.Y;
+  // 2P on the first curve: mdbl-2007-bl (Z1 = 1, a = 0), 1M + 5S
+  Fe XX = F::sqr(x1, P), YY = F::sqr(y1, P), YYYY = F::sqr(YY, P);
+  Fe S = F::dbl(F::sub(F::sub(F::sqr(F::add(x1, YY, P), P), XX, P), YYYY, P), P);
+  Fe M = F::add(F::dbl(XX, P), XX, P);
+  Fe X2 = F::sub(F::sqr(M, P), F::dbl(S, P), P);
+  Fe Y2 = F::sub(F::mul(M, F::sub(S, X2, P), P), F::dbl(F::dbl(F::dbl(YYYY, P), P), P), P);
+  Fe Z2 = F::dbl(y1, P);
+  // second curve: scale by Z2, 2P becomes affine
+  Fe Z2s = F::sqr(Z2, P), Z2c = F::mul(Z2s, Z2, P);
+  x1 = F::mul(x1, Z2s, P);
+  y1 = F::mul(y1, Z2c, P);
+  // 3P = P + 2P, both affine: mmadd-2007-bl, 4M + 2S (P != +-2P in a group of prime order)
+  Fe H = F::sub(X2, x1, P), HH = F::sqr(H, P), I = F::dbl(F::dbl(HH, P), P), J = F::mul(H, I, P);
+  Fe r = F::dbl(F::sub(Y2, y1, P), P), V = F::mul(x1, I, P);
+  Fe X3 = F::sub(F::sub(F::sqr(r, P), J, P), F::dbl(V, P), P);
+  Fe Y3 = F::sub(F::mul(r, F::sub(V, X3, P), P), F::dbl(F::mul(y1, J, P), P), P);
+  Fe Z3 = F::dbl(H, P);
+  // third curve: scale by Z3, all three affine
+  Fe Z3s = F::sqr(Z3, P), Z3c = F::mul(Z3s, Z3, P);
+  Aff t1, t2, t3;
+  t1.x = F::mul(x1, Z3s, P);
+  t1.y = F::mul(y1, Z3c, P);
+  t2.x = F::mul(X2, Z3s, P);
+  t2.y = F::mul(Y2, Z3c, P);
+  t3.x = X3;
+  t3.y = Y3;
+  t1.inf = t2.inf = t3.inf = 0;
+  const Fe scale = F::mul(F::mul(p.Z, Z2, P), Z3, P);
+  Jac acc = jac_infinity(P);
+#pragma unroll 1
+  for (int s = (int)nd - 1; s >= 0; --s) {
+    if (s != (int)nd - 1) {
+      acc = jac_dbl(acc, P);
+      acc = jac_dbl(acc, P);
+    }
+    uint32_t d = (k >> (2 * s)) & 3u;
+    Aff q = (d == 3) ? t3 : ((d == 2) ? t2 : t1);
+    if (d) acc = jac_madd(acc, q, P);
+  }
+  acc.Z = F::mul(acc.Z, scale, P);
+  return acc;
+}
+
 MP_NOINLINE Aff jac_to_aff(const Jac& p, const Modulus& P) {
   using namespace F;
   Aff a;
@@ -241,6 +294,10 @@ struct SecpCurve {
   using Point = Jac;
   using Affine = Aff;
   static constexpr int EB = 33;
+  static constexpr bool kOwnSmallMul = true;
+  MP_DEV static Point small_mul(const Point& p, uint32_t k, uint32_t nd, const Consts& C) {
+    return small_mul_iso(p, k, nd, C.P);
+  }
   MP_DEV static Point infinity(const Consts& C) { return jac_infinity(C.P); }
   MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return jac_from_aff(a, C.P); }
   MP_DEV static Point dbl(const Point& p, const Consts& C) { return jac_dbl(p, C.P); }
