@@ -59,26 +59,9 @@ MP_DEV typename Cv::Point scalar_mul2(const typename Cv::Point& p1, const uint32
   return acc;
 }
 
-// small-integer multiple [k]p for k < 2^(2*nd): fixed 2-bit windows
-template <class Cv>
-MP_DEV typename Cv::Point small_mul(const typename Cv::Point& p, uint32_t k, uint32_t nd,
-                                    const typename Cv::Consts& C) {
-  typename Cv::Point t2 = Cv::dbl(p, C), t3 = Cv::add(t2, p, C);
-  typename Cv::Point acc = Cv::infinity(C);
-#pragma unroll 1
-  for (int s = (int)nd - 1; s >= 0; --s) {
-    if (s != (int)nd - 1) {
-      acc = Cv::dbl(acc, C);
-      acc = Cv::dbl(acc, C);
-    }
-    // one call site for the addition: lanes pick their table entry first, so a warp whose lanes
-    // hold different digits still executes a single point addition per window
-    uint32_t d = (k >> (2 * s)) & 3u;
-    typename Cv::Point q = (d == 3) ? t3 : ((d == 2) ? t2 : p);
-    if (d) acc = Cv::add(acc, q, C);
-  }
-  return acc;
-}
+// The small-integer multiple [pos]acc of the Horner step is the curve policy's Cv::small_mul (fixed
+// 2-bit windows, one addition call site per window so that a warp whose lanes hold different digits
+// still executes a single point addition).
 
 // ------------------------------------------------------------ e1*B1 [+ e2*B2] ----
 template <class Cv>
@@ -176,10 +159,7 @@ MP_DEV void horner_body(const HornerArgs<Cv>& A, uint32_t tid) {
   Point acc = Cv::from_aff(load_aff<Cv>(A.cxy + (size_t)(hi - 1) * 16, A.cstatus[hi - 1]), C);
 #pragma unroll 1
   for (int j = (int)hi - 2; j >= (int)lo; --j) {
-    if constexpr (Cv::kOwnSmallMul)
-      acc = Cv::small_mul(acc, pos, nd, C);
-    else
-      acc = small_mul<Cv>(acc, pos, nd, C);
+    acc = Cv::small_mul(acc, pos, nd, C);
     acc = Cv::madd(acc, load_aff<Cv>(A.cxy + (size_t)j * 16, A.cstatus[j]), C);
   }
   if (k > 0) {

@@ -113,7 +113,7 @@ MP_NOINLINE Ext ext_add(Ext p, Ext q, const Consts& C) {
   return r;
 }
 // dbl-2008-hwcd with a = -1: 4M + 4S
-MP_NOINLINE Ext ext_dbl(Ext p, const Consts& C) {
+MP_NOINLINE Ext ext_dbl(Ext p, const Consts& C, bool need_t = true) {
   using namespace F;
   const Modulus& P = C.P;
   Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), Cc = F::dbl(F::sqr(p.Z, P), P);
@@ -123,9 +123,28 @@ MP_NOINLINE Ext ext_dbl(Ext p, const Consts& C) {
   Ext r;
   r.X = F::mul(E, F, P);
   r.Y = F::mul(G, H, P);
-  r.T = F::mul(E, H, P);
+  // T is only read by additions: a doubling that feeds another doubling skips it (3M + 4S)
+  r.T = need_t ? F::mul(E, H, P) : F::fe_zero();
   r.Z = F::mul(F, G, P);
   return r;
+}
+
+// [k]p for a small scalar k < 4^nd, fixed 2-bit windows (the generic ladder of ec_kernels.cuh with
+// the T coordinate skipped in the first doubling of every window)
+MP_DEV Ext small_mul_ext(const Ext& p, uint32_t k, uint32_t nd, const Consts& C) {
+  Ext t2 = ext_dbl(p, C), t3 = ext_add(t2, p, C);
+  Ext acc = ext_identity(C.P);
+#pragma unroll 1
+  for (int s = (int)nd - 1; s >= 0; --s) {
+    if (s != (int)nd - 1) {
+      acc = ext_dbl(acc, C, false);
+      acc = ext_dbl(acc, C);
+    }
+    uint32_t d = (k >> (2 * s)) & 3u;
+    Ext q = (d == 3) ? t3 : ((d == 2) ? t2 : p);
+    if (d) acc = ext_add(acc, q, C);
+  }
+  return acc;
 }
 
 // canonical-form helpers (RFC 9496 section 4.1)
@@ -219,7 +238,9 @@ struct RistCurve {
   using Point = Ext;
   using Affine = Aff;
   static constexpr int EB = 32;
-  static constexpr bool kOwnSmallMul = false;
+  MP_DEV static Point small_mul(const Point& p, uint32_t k, uint32_t nd, const Consts& C) {
+    return small_mul_ext(p, k, nd, C);
+  }
   MP_DEV static Point infinity(const Consts& C) { return ext_identity(C.P); }
   MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return ext_from_aff(a, C.P); }
   MP_DEV static Point dbl(const Point& p, const Consts& C) { return ext_dbl(p, C); }

@@ -294,7 +294,6 @@ struct SecpCurve {
   using Point = Jac;
   using Affine = Aff;
   static constexpr int EB = 33;
-  static constexpr bool kOwnSmallMul = true;
   MP_DEV static Point small_mul(const Point& p, uint32_t k, uint32_t nd, const Consts& C) {
     return small_mul_iso(p, k, nd, C.P);
   }
