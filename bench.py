@@ -324,9 +324,10 @@ def main():
         dist.all_gather_into_tensor(out_all, out_local)          # one NCCL all-gather per phase
         res = 1
         if rank == 0:
-            out_host.copy_(out_all, non_blocking=False)
-            # [rank, kind, j, eb] -> [kind, j, rank, eb]: participant j*N + rank, one copy, no Python bytes
-            arr = np.ascontiguousarray(out_host.numpy().reshape(world, 3, n, eb).transpose(1, 2, 0, 3))
+            # [rank, kind, j, eb] -> [kind, j, rank, eb] (participant j*N + rank) on the device, then one
+            # contiguous D2H copy: the re-interleave is a 25 MB permute at HBM speed instead of a host pass
+            out_host.copy_(out_all.permute(1, 2, 0, 3).contiguous().view(world, 3, n, eb), non_blocking=False)
+            arr = out_host.numpy().reshape(3, n, world, eb)
             u8 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
             group.ctx.check(lib.mpvss_transcript_check(h, n_total, u8(arr[0]), ptr(shares_all), u8(arr[1]), u8(arr[2]),
                                                        ptr(chal_all), ctypes.byref(ok), None))
