@@ -11,6 +11,7 @@
 //   mul_body     : group.mul  modp.rs:130-132
 #pragma once
 #include "modp_arith.cuh"
+#include "modp_sqr.cuh"
 
 namespace modp {
 
@@ -35,18 +36,54 @@ MP_DEV void warp_copy64(uint32_t* dst, const uint32_t* src) {
   dst[2 * l + 1] = src[2 * l + 1];
 }
 
+// Shared-memory scratch and per-lane plan of the split squaring (modp_sqr.cuh); empty unless the
+// build selects it (MPVSS_MODP_SPLIT_SQR, TPI = 8 only).
+#ifdef MPVSS_MODP_SPLIT_SQR
 template <int TPI>
-MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+constexpr int sqr_scratch_words = TPI == 8 ? SQS_WORDS : 0;
+#else
+template <int TPI>
+constexpr int sqr_scratch_words = 0;
+#endif
+struct SqrCtx {
+  uint32_t* scratch;
+  SqPlan pl;
+};
+template <int TPI>
+MP_DEV SqrCtx make_sqr_ctx(uint32_t* scratch, const Lane& ln) {
+  SqrCtx c;
+  c.scratch = scratch;
+  if (sqr_scratch_words<TPI> != 0) {
+    c.pl = make_sq_plan(ln.k);
+    scratch[SQS_ZERO + ln.k] = 0;
+  }
+  return c;
+}
+
+template <int TPI>
+MP_DEV void sqr_plain(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   stage_shared<TPI>(sq, acc, ln);
   simt::syncwarp();
-  // mont_sqr issues 13 instead of 16 wide MACs per row but 10 more carry/select instructions; on
-  // B200 the two cancel (Horner launch 263 ms against 255 ms), so the hot path
-  // squares through mont_mul unless MPVSS_MODP_DEDICATED_SQR is defined.
-#ifdef MPVSS_MODP_DEDICATED_SQR
-  mont_sqr<TPI>(acc, acc, sq, M, ln);
-#else
   mont_mul<TPI>(acc, acc, sq, M, ln);
+}
+
+template <int TPI>
+MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const SqrCtx& sc, const Mod<Cfg<TPI>::L>& M,
+                        const Lane& ln) {
+  stage_shared<TPI>(sq, acc, ln);
+  simt::syncwarp();
+  // Three squarings exist: through mont_mul (16 wide MACs per row), mont_sqr (13 MACs per row in the
+  // fused loop, but 10 more carry/select instructions: measured slower) and the
+  // split squaring of modp_sqr.cuh (thread-local block products + reduction-only loop).
+  if constexpr (sqr_scratch_words<TPI> != 0) {
+    mont_sqr_split(acc, acc, sq, sc.scratch, sc.pl, M, ln);
+  } else {
+#ifdef MPVSS_MODP_DEDICATED_SQR
+    mont_sqr<TPI>(acc, acc, sq, M, ln);
+#else
+    mont_mul<TPI>(acc, acc, sq, M, ln);
 #endif
+  }
 }
 
 // Leave Montgomery form (multiply by 1), reduce below q, store 64 limbs.
@@ -81,7 +118,7 @@ struct HornerArgs {
 };
 
 template <int TPI>
-constexpr int horner_smem_words = 128 + (32 / TPI) * 256;
+constexpr int horner_smem_words = 128 + (32 / TPI) * (256 + sqr_scratch_words<TPI>);
 
 // X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
 // integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
@@ -101,8 +138,9 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   if (NP1) M.np = 1u;
   uint32_t* cbuf = wsm;
   uint32_t* one = wsm + 64;
-  uint32_t* tbl = wsm + 128 + gi * 256;  // tbl[0..2] = X, X^2, X^3 ; tbl + 192 = squaring stage
+  uint32_t* tbl = wsm + 128 + gi * (256 + sqr_scratch_words<TPI>);  // tbl[0..2] = X, X^2, X^3 ; +192 squaring stage
   uint32_t* sq = tbl + 192;
+  const SqrCtx sc = make_sqr_ctx<TPI>(tbl + 256, ln);
   warp_copy64(one, A.consts + C_ONE);
   const uint32_t pos = A.pos[inst];
   uint32_t acc[L];
@@ -123,8 +161,8 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
     uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
     load_slice<TPI>(acc, d ? tbl + (d - 1) * 64 : one, ln);
     for (int s = (int)ndigits - 2; s >= 0; --s) {
-      sqr_inplace<TPI>(acc, sq, M, ln);
-      sqr_inplace<TPI>(acc, sq, M, ln);
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) sqr_inplace<TPI>(acc, sq, sc, M, ln);  // one code instance
       d = (pos >> (2 * s)) & 3u;
       if (!((skip >> s) & 1u)) mont_mul<TPI>(acc, acc, d ? tbl + (d - 1) * 64 : one, M, ln);
     }
@@ -236,11 +274,11 @@ struct Exp2Args {
 };
 
 template <int TPI>
-constexpr int exp2_smem_words = 64 + (32 / TPI) * (16 * 64 + 64);
+constexpr int exp2_smem_words = 64 + (32 / TPI) * (16 * 64 + 64 + sqr_scratch_words<TPI>);
 
 template <int TPI>
 MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, const uint32_t* e, uint32_t windows,
-                        uint32_t* tbl, uint32_t* sq, const uint32_t* r2, const uint32_t* consts,
+                        uint32_t* tbl, uint32_t* sq, const SqrCtx& sc, const uint32_t* r2, const uint32_t* consts,
                         const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   constexpr int L = Cfg<TPI>::L;
   uint32_t x[L];
@@ -260,10 +298,8 @@ MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, co
   uint32_t d = (e[wi >> 3] >> ((wi & 7u) * 4)) & 15u;
   load_slice<TPI>(acc, tbl + d * 64, ln);
   while (wi-- > 0) {
-    sqr_inplace<TPI>(acc, sq, M, ln);
-    sqr_inplace<TPI>(acc, sq, M, ln);
-    sqr_inplace<TPI>(acc, sq, M, ln);
-    sqr_inplace<TPI>(acc, sq, M, ln);
+#pragma unroll 1
+    for (int rep = 0; rep < 4; ++rep) sqr_inplace<TPI>(acc, sq, sc, M, ln);  // one code instance
     d = (e[wi >> 3] >> ((wi & 7u) * 4)) & 15u;
     mont_mul<TPI>(acc, acc, tbl + d * 64, M, ln);
   }
@@ -314,7 +350,7 @@ MP_DEV void comb1_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
   mont_mul<TPI>(b, b, r2, M, ln);
   for (uint32_t w = 0; w < A.rows; ++w) {
     if (wg == 0 && gi == 0) stage<TPI>(A.tbl + ((size_t)w * 256 + 1) * 64, b, ln);
-    for (int k = 0; k < 8; ++k) sqr_inplace<TPI>(b, sq, M, ln);
+    for (int k = 0; k < 8; ++k) sqr_plain<TPI>(b, sq, M, ln);
   }
 }
 // Step 2 (lane group w): tbl[w][0] = one, tbl[w][d] = tbl[w][d-1] * tbl[w][1].
@@ -357,8 +393,9 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   uint32_t* r2 = wsm;
-  uint32_t* tbl = wsm + 64 + gi * (16 * 64 + 64);
+  uint32_t* tbl = wsm + 64 + gi * (16 * 64 + 64 + sqr_scratch_words<TPI>);
   uint32_t* sq = tbl + 16 * 64;
+  const SqrCtx sc = make_sqr_ctx<TPI>(sq + 64, ln);
   warp_copy64(r2, A.consts + C_R2);
   simt::syncwarp();
   uint32_t acc[L];
@@ -366,11 +403,11 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
     exp_comb8<TPI>(acc, A.comb1, A.e1 + (size_t)inst * A.e1_stride, (A.e1_windows + 1) / 2, sq, M, ln);
   else
     exp_window4<TPI>(acc, A.b1 + (size_t)inst * A.b1_stride, A.e1 + (size_t)inst * A.e1_stride, A.e1_windows, tbl,
-                     sq, r2, A.consts, M, ln);
+                     sq, sc, r2, A.consts, M, ln);
   if (A.b2 != nullptr) {
     uint32_t acc2[L];
     exp_window4<TPI>(acc2, A.b2 + (size_t)inst * A.b2_stride, A.e2 + (size_t)inst * A.e2_stride, A.e2_windows, tbl,
-                     sq, r2, A.consts, M, ln);
+                     sq, sc, r2, A.consts, M, ln);
     stage_shared<TPI>(sq, acc2, ln);
     simt::syncwarp();
     mont_mul<TPI>(acc, acc, sq, M, ln);
@@ -573,6 +610,32 @@ MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
     stage_shared<TPI>(sq, y, ln);
     simt::syncwarp();
     mont_mul<TPI>(acc, acc, sq, M, ln);  // a*R*b/R = a*b
+  }
+  canonical<TPI>(acc, M, ln);
+  if (live) stage<TPI>(A.out + (size_t)inst * 64, acc, ln);
+}
+
+// ---- split squaring, test entry (TPI = 8): out = a*a/R mod q, a taken as is ----
+constexpr int sqrtest_smem_words = 64 + 4 * (64 + SQS_WORDS);
+MP_DEV void sqr_split_test_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int TPI = 8, L = 8, GPW = 4;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  uint32_t inst = wg * GPW + gi;
+  const bool live = inst < A.n;
+  if (!live) inst = A.n - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* sq = wsm + 64 + gi * (64 + SQS_WORDS);
+  uint32_t* scratch = sq + 64;
+  scratch[SQS_ZERO + ln.k] = 0;
+  const SqPlan pl = make_sq_plan(ln.k);
+  uint32_t acc[L];
+  load_slice<TPI>(acc, A.a + (size_t)inst * A.a_stride, ln);
+  for (uint32_t rep = 0; rep < (A.mode ? A.mode : 1u); ++rep) {  // mode = number of squarings in a row
+    stage_shared<TPI>(sq, acc, ln);
+    simt::syncwarp();
+    mont_sqr_split(acc, acc, sq, scratch, pl, M, ln);
   }
   canonical<TPI>(acc, M, ln);
   if (live) stage<TPI>(A.out + (size_t)inst * 64, acc, ln);

@@ -71,6 +71,13 @@ extern "C" int emu_modp_mul(int tpi, const uint32_t* consts, const uint32_t* a, 
   return 0;
 }
 
+// split squaring (TPI = 8): out = a^(2^reps) / R^(2^reps - 1) mod q
+extern "C" int emu_modp_sqr_split(const uint32_t* consts, const uint32_t* a, uint32_t n, uint32_t reps, uint32_t* out) {
+  modp::MulArgs A{consts, a, nullptr, out, n, reps, 64, 0};
+  run_warps((n + 3) / 4, modp::sqrtest_smem_words, [&](uint32_t w, uint32_t* s) { modp::sqr_split_test_body(A, w, s); });
+  return 0;
+}
+
 // fixed-base table: only the first `rows` byte positions are filled (step 1 is cut short by the test)
 extern "C" int emu_modp_comb_build(int tpi, const uint32_t* consts, const uint32_t* base, uint32_t* tbl,
                                    uint32_t rows) {

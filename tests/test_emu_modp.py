@@ -72,6 +72,34 @@ def test_mont_sqr_edge_patterns(lib, tpi, modulus):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * A[i] * rinv % m, (tpi, i)
 
 
+@pytest.mark.parametrize("modulus", ["q", "g"])
+def test_split_sqr_edge_patterns(lib, modulus):
+    """Split squaring (thread-local block products, column sums through shared memory, reduction-only
+    digit loop; TPI = 8): a*a/R mod m on saturated / sparse / out-of-range operands, and three squarings
+    in a row (scratch reuse)."""
+    m = Q if modulus == "q" else G.g
+    C = eu.consts_block(m)
+    rng = random.Random(99 + len(modulus))
+    n = 96
+    A = [_struct(rng) for _ in range(n)]
+    A[:12] = [R - 1, 0, 1, 2, m - 1, m, m + 5, R - 2, (1 << 2047), (1 << 2047) + 1, (1 << 32) - 1, R - (1 << 31)]
+    for k in range(8):
+        A[12 + k] = ((1 << 256) - 1) << (256 * k)          # one saturated block
+        A[20 + k] = (((1 << 256) - 1) << (256 * k)) | ((1 << 256) - 1) << (256 * ((k + 4) % 8))
+    a = np.concatenate([eu.to_limbs(x) for x in A])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    rinv = pow(R, -1, m)
+    assert lib.emu_modp_sqr_split(eu.P(C), eu.P(a), n, 1, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * A[i] * rinv % m, i
+    assert lib.emu_modp_sqr_split(eu.P(C), eu.P(a), n, 3, eu.P(out)) == 0
+    for i in range(n):
+        x = A[i]
+        for _ in range(3):
+            x = x * x * rinv % m
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == x, i
+
+
 @pytest.mark.parametrize("tpi", [4, 8, 16])
 def test_horner_kernel_equals_reference_schedule(lib, tpi):
     C = eu.consts_block(Q)
