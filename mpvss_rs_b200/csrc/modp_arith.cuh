@@ -23,14 +23,11 @@
 // subtraction only fires on overflow of 2^2048; canonical reduction below q
 // happens once, when results leave the kernel.
 //
-// Squarings run through the same fused loop (8192 MACs issued for the 6240 a symmetric product
-// needs).  Why not yet a dedicated squaring: in the digit-serial loop every lane executes the a_k*b_j
-// MACs of every row, so skipping the lower triangle saves nothing under SIMT; a product/reduction
-// split (block products A_i*A_j, i <= j, on anti-diagonals k and k+TPI per lane, then a
-// reduction-only digit loop) does save ~18 % of the MACs, but the accumulation target (low or high
-// window) of a lane's s-th block product depends on the lane, so it needs either masked adds or
-// predicated bank swaps of the window registers.  Left for the next round; it lifts the ceiling of
-// the reported IMAD fraction from 0.72 to 0.84 for the Horner schedule.
+// Squarings run through the same fused loop by default (8192 MACs issued for the 6240 a symmetric
+// product needs).  Two dedicated squarings exist and are bit-exact -- mont_sqr below (symmetric rows,
+// 13 MACs per row) and mont_sqr_split in modp_sqr.cuh (block products + reduction-only loop) -- but at
+// the benchmark's 1.74 warps per scheduler the launch is bound by dependency latency per warp, so the
+// instruction count of a product decides and both measure slower.
 #pragma once
 #include "simt.h"
 

@@ -72,9 +72,11 @@ MP_DEV void sqr_inplace(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, const SqrCtx
                         const Lane& ln) {
   stage_shared<TPI>(sq, acc, ln);
   simt::syncwarp();
-  // Three squarings exist: through mont_mul (16 wide MACs per row), mont_sqr (13 MACs per row in the
-  // fused loop, but 10 more carry/select instructions: measured slower) and the
-  // split squaring of modp_sqr.cuh (thread-local block products + reduction-only loop).
+  // Three squarings exist: through mont_mul (1696 instructions per product at TPI = 8, 1024 wide MACs),
+  // mont_sqr (symmetric rows in the fused loop: 832 MACs, 2304 instructions) and the split squaring of
+  // modp_sqr.cuh (804 MACs, ~1940 instructions).  At n = 4096 (1.74 warps per scheduler) the launch
+  // is latency-bound per warp and the instruction count decides: Horner 256 / 263 / 288 ms
+  // (DESIGN.md section 5).  The dedicated ones are compile-time options for large batches.
   if constexpr (sqr_scratch_words<TPI> != 0) {
     mont_sqr_split(acc, acc, sq, sc.scratch, sc.pl, M, ln);
   } else {
