@@ -224,8 +224,8 @@ MP_DEV void mm_finish(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&A0)[Cfg<TPI>:
 // r = a * b * 2^-2048 mod q, result in [0, 2^2048).  `bs` points at the 64 limbs of
 // b (shared memory, visible to the whole group).  r may alias a.
 template <int TPI>
-MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* bs,
-                     const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+MP_DEV void mont_mul_fused(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* bs,
+                           const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
   constexpr int L = Cfg<TPI>::L;
   uint32_t A0[L + 2], A1[L + 2];
   uint32_t in = 0;
@@ -258,6 +258,121 @@ MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L
     }
   }
   mm_finish<TPI>(r, A0, A1, in, M, ln);
+}
+
+// ---- split accumulators ----------------------------------------------------------------------
+// Same product with the a*b rows and the q*m rows kept in separate windows (AP/AS and QP/QS), so
+// that the four carry chains of a row are independent of each other and the a*b chains of row j+1
+// do not wait for the Montgomery digit of row j: the only coupling is the low word, where
+//     m_j = (AP[0] + QP[0] + stray + c) * np,   exported word = AP[0] + QP[0] + c  (carry c kept
+// for the next row's column).  Costs 6 more carry instructions per row than the fused form; meant
+// for low occupancy, where dependency latency and not issue bandwidth is the limit.
+template <int TPI>
+MP_DEV void mm_digit_il(uint32_t (&AP)[Cfg<TPI>::L + 2], uint32_t (&AS)[Cfg<TPI>::L + 2],
+                        uint32_t (&QP)[Cfg<TPI>::L + 2], uint32_t (&QS)[Cfg<TPI>::L + 2],
+                        const uint32_t (&a)[Cfg<TPI>::L], uint32_t b, const Mod<Cfg<TPI>::L>& M, const Lane& ln,
+                        uint32_t& in, uint32_t& cprev) {
+  constexpr int L = Cfg<TPI>::L;
+  // a*b half: identical to mm_digit on (AP, AS)
+  AS[L] = simt::add_cc(AS[L], in);
+  AS[L + 1] = simt::addc(AS[L + 1], 0);
+  AP[0] = simt::add_cc(AP[0], AS[1]);
+#pragma unroll
+  for (int x = 0; x < L; x += 2) {
+    AS[x] = simt::madc_lo_cc(a[x + 1], b, AS[x + 2]);
+    AS[x + 1] = simt::madc_hi_cc(a[x + 1], b, AS[x + 3]);
+  }
+  AS[L] = simt::addc(0, 0);
+  AS[L + 1] = 0;
+  AP[0] = simt::mad_lo_cc(a[0], b, AP[0]);
+  AP[1] = simt::madc_hi_cc(a[0], b, AP[1]);
+#pragma unroll
+  for (int i = 2; i < L; i += 2) {
+    AP[i] = simt::madc_lo_cc(a[i], b, AP[i]);
+    AP[i + 1] = simt::madc_hi_cc(a[i], b, AP[i + 1]);
+  }
+  AP[L] = simt::addc(AP[L], 0);
+  // Montgomery digit from the low word of the whole value (plain adds: no carry flag across the shuffle)
+  uint32_t m = simt::shfl(simt::mul_lo(AP[0] + QP[0] + QS[1] + cprev, M.np), ln.lane0);
+  // q*m half on (QP, QS); the odd window is shifted down inside its chain
+  QP[0] = simt::add_cc(QP[0], QS[1]);
+  QS[0] = simt::madc_lo_cc(M.q[1], m, QS[2]);
+  QS[1] = simt::madc_hi_cc(M.q[1], m, QS[3]);
+#pragma unroll
+  for (int i = 3; i < L; i += 2) {
+    QS[i - 1] = simt::madc_lo_cc(M.q[i], m, QS[i + 1]);
+    QS[i] = simt::madc_hi_cc(M.q[i], m, QS[i + 2]);
+  }
+  QS[L] = simt::addc(0, 0);
+  QS[L + 1] = 0;
+  QP[0] = simt::mad_lo_cc(M.q[0], m, QP[0]);
+  QP[1] = simt::madc_hi_cc(M.q[0], m, QP[1]);
+#pragma unroll
+  for (int i = 2; i < L; i += 2) {
+    QP[i] = simt::madc_lo_cc(M.q[i], m, QP[i]);
+    QP[i + 1] = simt::madc_hi_cc(M.q[i], m, QP[i + 1]);
+  }
+  QP[L] = simt::addc(QP[L], 0);
+  // word leaving the window (zero on group lane 0) and the carry of its column
+  uint32_t e = simt::add_cc(AP[0], QP[0]);
+  uint32_t c = simt::addc(0, 0);
+  e = simt::add_cc(e, cprev);
+  cprev = simt::addc(c, 0);
+  in = simt::shfl(e, ((int)simt::lane_id() + 1) & 31);
+}
+
+template <int TPI>
+MP_DEV void mont_mul_il(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* bs,
+                        const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+  constexpr int L = Cfg<TPI>::L;
+  uint32_t A0[L + 2], A1[L + 2], Q0[L + 2], Q1[L + 2];
+#pragma unroll
+  for (int i = 0; i < L + 2; ++i) A0[i] = A1[i] = Q0[i] = Q1[i] = 0;
+  uint32_t in = 0, cprev = 0;
+  constexpr int PER = L + 2, PEEL = 64 % PER;
+  const uint2* b2 = reinterpret_cast<const uint2*>(bs);
+#pragma unroll
+  for (int d = 0; d < PEEL; d += 2) {
+    uint2 bw = b2[d / 2];
+    mm_digit_il<TPI>(A0, A1, Q0, Q1, a, bw.x, M, ln, in, cprev);
+    mm_digit_il<TPI>(A1, A0, Q1, Q0, a, bw.y, M, ln, in, cprev);
+  }
+#pragma unroll 1
+  for (int it = 0; it < (64 - PEEL) / PER; ++it) {
+    const uint2* p = b2 + (PEEL + it * PER) / 2;
+#pragma unroll
+    for (int d = 0; d < PER; d += 2) {
+      uint2 bw = p[d / 2];
+      mm_digit_il<TPI>(A0, A1, Q0, Q1, a, bw.x, M, ln, in, cprev);
+      mm_digit_il<TPI>(A1, A0, Q1, Q0, a, bw.y, M, ln, in, cprev);
+    }
+  }
+  // merge the two windows (plus the pending carry of the lowest column) and finish as usual;
+  // after an even number of rows A0/Q0 hold the odd role: their word 0 is the lowest column
+  A0[0] = simt::add_cc(A0[0], cprev);
+#pragma unroll
+  for (int i = 1; i < L + 1; ++i) A0[i] = simt::addc_cc(A0[i], 0);
+  A0[L + 1] = simt::addc(A0[L + 1], 0);
+  A0[0] = simt::add_cc(A0[0], Q0[0]);
+#pragma unroll
+  for (int i = 1; i < L + 1; ++i) A0[i] = simt::addc_cc(A0[i], Q0[i]);
+  A0[L + 1] = simt::addc(A0[L + 1], Q0[L + 1]);
+  // word 0 of the even-role arrays is the exported (dropped) word: only words 1.. count
+  A1[1] = simt::add_cc(A1[1], Q1[1]);
+#pragma unroll
+  for (int i = 2; i < L + 1; ++i) A1[i] = simt::addc_cc(A1[i], Q1[i]);
+  A1[L + 1] = simt::addc(A1[L + 1], Q1[L + 1]);
+  mm_finish<TPI>(r, A0, A1, in, M, ln);
+}
+
+template <int TPI>
+MP_DEV void mont_mul(uint32_t (&r)[Cfg<TPI>::L], const uint32_t (&a)[Cfg<TPI>::L], const uint32_t* bs,
+                     const Mod<Cfg<TPI>::L>& M, const Lane& ln) {
+#ifdef MPVSS_MODP_SPLIT_ACC
+  mont_mul_il<TPI>(r, a, bs, M, ln);
+#else
+  mont_mul_fused<TPI>(r, a, bs, M, ln);
+#endif
 }
 
 // ---- dedicated squaring ----------------------------------------------------------------------

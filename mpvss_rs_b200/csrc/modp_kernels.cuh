@@ -586,6 +586,7 @@ struct MulArgs {
   uint32_t n;
   uint32_t mode;       // 0: out = a*b mod q (canonical)   1: out = a*R mod q (to Montgomery form)
                        // 2: out = a*a/R mod q, a taken as is (any value below 2^2048; squaring test)
+                       // 3: as 0, second product through mont_mul_il (split accumulators; test)
   uint32_t a_stride, b_stride;
 };
 
@@ -616,12 +617,15 @@ MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
   } else {
     mont_mul<TPI>(acc, acc, r2, M, ln);  // a*R
   }
-  if (A.mode == 0) {
+  if (A.mode == 0 || A.mode == 3) {
     uint32_t y[L];
     load_slice<TPI>(y, A.b + (size_t)inst * A.b_stride, ln);
     stage_shared<TPI>(sq, y, ln);
     simt::syncwarp();
-    mont_mul<TPI>(acc, acc, sq, M, ln);  // a*R*b/R = a*b
+    if (A.mode == 3)
+      mont_mul_il<TPI>(acc, acc, sq, M, ln);  // split-accumulator product (test entry)
+    else
+      mont_mul<TPI>(acc, acc, sq, M, ln);  // a*R*b/R = a*b
   }
   canonical<TPI>(acc, M, ln);
   if (live) stage<TPI>(A.out + (size_t)inst * 64, acc, ln);

@@ -44,6 +44,10 @@ def test_mont_mul_edge_patterns(lib, tpi, modulus):
     assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, eu.P(b), 64, n, 0, eu.P(out)) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * B[i] % m, (tpi, i)
+    # mode 3: the same product through the split-accumulator loop (mont_mul_il)
+    assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, eu.P(b), 64, n, 3, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == A[i] * B[i] % m, (tpi, i)
     # mode 1: Montgomery form a * 2^2048 mod m, canonical
     assert lib.emu_modp_mul(tpi, eu.P(C), eu.P(a), 64, None, 0, n, 1, eu.P(out)) == 0
     for i in range(n):
