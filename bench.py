@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
     ap.add_argument("--dual", type=int, default=-1, help="override modp_dual (0/1/2)")
     ap.add_argument("--ec-threads", type=int, default=0)
-    ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0/1)")
+    ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0, 2 or 3; default 3 = a2 as persistent one-warp CTAs in the idle warp slots)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary secp256k1 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

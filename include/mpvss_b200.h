@@ -59,7 +59,11 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx);
 const char* mpvss_last_error(const mpvss_ctx* ctx);
 /* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16); "modp_dual" (0/1: evaluate the
  * commitment polynomial as two half-length chunks: 1 side by side on every lane group, 2 as two
- * concurrent launches); "modp_comb" (0/1: fixed-base tables for the two generators); "ec_threads" (thread target of the chunked elliptic-curve Horner launch) */
+ * concurrent launches); "modp_comb" (0/1: fixed-base tables for the two generators); "modp_overlap"
+ * (where the X-independent a2 = y^r Y^c runs during verify_distribution: 0 before the X_i launch,
+ * 2 beside it on a side stream, 3 (default) beside it as one persistent one-warp CTA per SM, which
+ * takes the warp slot the X_i launch leaves idle); "ec_threads" (thread target of the chunked
+ * elliptic-curve Horner launch) */
 int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value);
 size_t mpvss_element_bytes(const mpvss_ctx* ctx);
 size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);

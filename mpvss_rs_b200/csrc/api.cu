@@ -72,6 +72,8 @@ int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
     return s;
   };
   if (cudaSetDevice(device) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) ctx->sm_count = sms;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->ev_mid) != cudaSuccess || cudaEventCreate(&ctx->ev_h0) != cudaSuccess ||

@@ -53,6 +53,7 @@ struct PinBuf {
 struct mpvss_ctx {
   int group = 0;
   int device = 0;
+  int sm_count = 148;  // multiprocessors of the device (read at context creation)
   cudaStream_t stream = nullptr;
   cudaStream_t aux[2] = {nullptr, nullptr};  // side streams for concurrent launches
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_h0 = nullptr, ev_h1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -67,7 +68,9 @@ struct mpvss_ctx {
   int modp_tpi = 8;
   bool modp_tpi_auto = true;  // Horner launches pick 4 lanes per value when a launch has >= 32768 positions
   int v_tpi = 8;              // lanes per value of the staged Horner plan
-  int modp_overlap = 0;  // 2: issue the X-independent a2 launch on a side stream right after the Horner launch
+  size_t exp2_filler_smem = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs
+  int modp_overlap = 3;  // a2 = y^r Y^c (independent of X): 0 before the Horner launch on the main stream; 2 regular launch on a
+                         // side stream after it; 3 (default) persistent one-warp CTAs, one per SM, on a side stream after it
   int modp_dual = 0;  // two-chunk Horner: 0 off (default: fastest whole step), 1 two interleaved chains per lane
                       // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2

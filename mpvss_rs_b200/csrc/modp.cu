@@ -29,6 +29,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) exp2_kernel(Exp2Args A) {
   exp2_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * exp2_smem_words<TPI>);
 }
 
+// Persistent one-warp CTAs, one per SM: the launch only takes the warp slot the Horner launch leaves
+// empty on every SM (7 one-warp CTAs on 4 schedulers).  Used for the X-independent a2 exponentiation
+// (modp_overlap = 3).
+template <int TPI>
+__global__ void __launch_bounds__(32) exp2_filler_kernel(Exp2Args A, uint32_t nwarps) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  for (uint32_t w = blockIdx.x; w < nwarps; w += gridDim.x) {
+    exp2_body<TPI>(A, w, smem);
+    __syncwarp();
+  }
+}
+
 template <int TPI>
 __global__ void __launch_bounds__(32) comb1_kernel(CombArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -58,6 +70,12 @@ static uint32_t ctas_for(uint32_t n) {
 
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
+  // Largest shared-memory carve-out for every MODP kernel: the kernels barely use L1, and the split of
+  // an SM cannot change while CTAs are resident, so a small carve-out chosen for the first launch would
+  // keep a second, concurrent launch (modp_overlap) from becoming resident at all.
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
@@ -107,6 +125,19 @@ cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
     cudaError_t e = set_smem(exp2_kernel<T>, sm);
     if (e != cudaSuccess) return e;
     exp2_kernel<T><<<ctas_for<T>(A.n), WARPS_PER_CTA * 32, sm, s>>>(A);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t smem_bytes, cudaStream_t s) {
+  if (A.n == 0 || A.e1_windows == 0 || (A.b2 && A.e2_windows == 0)) return cudaErrorInvalidValue;
+  MODP_DISPATCH(tpi, {
+    size_t sm = exp2_smem_words<T> * 4;
+    cudaError_t e = set_smem(exp2_filler_kernel<T>, sm);
+    if (e != cudaSuccess) return e;
+    uint32_t per_cta = 32 / T, nwarps = (A.n + per_cta - 1) / per_cta;
+    uint32_t grid = (uint32_t)smem_bytes;  // number of persistent CTAs (one per SM)
+    exp2_filler_kernel<T><<<grid < nwarps ? grid : nwarps, 32, sm, s>>>(A, nwarps);
   });
   return cudaGetLastError();
 }

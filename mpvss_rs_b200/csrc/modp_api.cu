@@ -118,7 +118,10 @@ int dev_exp2(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* b1, uint32_
              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s,
              uint32_t e2w, size_t n, uint32_t* out, cudaStream_t stream = nullptr, const uint32_t* comb1 = nullptr) {
   modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w, comb1};
-  MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, stream ? stream : ctx->stream));
+  if (ctx->exp2_filler_smem)
+    MPVSS_CUDA(ctx, modp::launch_exp2_filler(ctx->modp_tpi, A, ctx->exp2_filler_smem, stream ? stream : ctx->stream));
+  else
+    MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, stream ? stream : ctx->stream));
   timing_launch(ctx);
   return MPVSS_OK;
 }
@@ -509,17 +512,20 @@ static int verify_kernels(mpvss_ctx* ctx) {
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   uint32_t* X = ctx->v_x.as<uint32_t>();
   timing_begin(ctx);
-  // a2 = y^r * Y^c does not depend on X.  modp_overlap = 0: it runs first on the main stream;
-  // 2: it is issued on a side stream right AFTER the Horner launch, so its CTAs only fill what the
-  // already resident Horner warps leave idle (issuing it first lets it claim SMs and unbalances the
-  // placement of the long-running Horner CTAs -- measured 40 % slower -- hence no mode 1)
+  // a2 = y^r * Y^c does not depend on X.  The Horner launch puts 7 one-warp CTAs on the 4 schedulers
+  // of an SM, i.e. one warp slot per SM stays empty for the whole launch.  modp_overlap = 3 (default)
+  // issues a2 on a side stream right AFTER the Horner launch as persistent one-warp CTAs, one per SM:
+  // they take exactly that slot and a2 disappears from the step (measured: step 270.8 -> 256.5 ms,
+  // Horner launch itself 245 -> 246 ms).  2: regular a2 launch on the side stream (265.6 ms, slows
+  // the Horner warps); 0: a2 first on the main stream.  Issuing it first on a side stream lets it
+  // claim SMs and unbalances the placement of the long-running Horner CTAs (40 % slower): no mode 1.
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   auto launch_a2 = [&](cudaStream_t s) {
     return dev_exp2(ctx, K, ctx->v_pk.as<uint32_t>(), EW, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin,
                     ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
                     ctx->v_a2.as<uint32_t>(), s);
   };
-  const bool side = ctx->modp_overlap == 2;
+  const bool side = ctx->modp_overlap == 2 || ctx->modp_overlap == 3;
   if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
   if (ctx->v_dual)
@@ -532,7 +538,11 @@ static int verify_kernels(mpvss_ctx* ctx) {
                          X));
   if (side) {
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
-    MPVSS_TRY(launch_a2(ctx->aux[0]));
+    // 3: persistent one-warp CTAs, one per SM, into the warp slot the Horner CTAs leave empty
+    if (ctx->modp_overlap == 3) ctx->exp2_filler_smem = (size_t)ctx->sm_count;
+    int rc = launch_a2(ctx->aux[0]);
+    ctx->exp2_filler_smem = 0;
+    MPVSS_TRY(rc);
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
   }
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
