@@ -90,6 +90,7 @@ struct mpvss_ctx {
   size_t v_n = 0, v_t = 0;
   uint32_t v_rwin = 0, v_cwin = 0;
   size_t v_np = 0;  // padded instance count of the Horner launch
+  uint32_t v_nd_max = 1;  // base-4 digits of the largest staged position
   std::vector<uint8_t> v_challenge, v_y_host;
   const uint32_t* v_comb = nullptr;  // fixed-base table of g for a1 = g^r * X^c
   bool v_dual = false;

@@ -481,6 +481,7 @@ int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
   PosPlan plan;
   MPVSS_TRY(prep_positions(ctx, positions, n, plan));
   ctx->v_np = plan.pos.size();
+  ctx->v_nd_max = plan.nd.empty() ? 1u : plan.nd[0];  // classes are sorted longest first
   ctx->v_tpi = plan.tpi;
   MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), ctx->v_np * 4));
@@ -525,7 +526,19 @@ static int verify_kernels(mpvss_ctx* ctx) {
                     ctx->v_y.as<uint32_t>(), EW, ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n,
                     ctx->v_a2.as<uint32_t>(), s);
   };
-  const bool side = ctx->modp_overlap == 2 || ctx->modp_overlap == 3;
+  // Mode 3 only pays when the persistent CTAs finish inside the Horner launch: rounds of one
+  // exponentiation per SM (about 5 products per 4-bit window) against the t-1 Horner steps of about
+  // 3*digits+1 products; measured break-even near 0.6 (tools/overlap_sweep.sh).  Otherwise a2 goes first.
+  int overlap = ctx->modp_overlap;
+  if (overlap == 3) {
+    const size_t groups_per_warp = 32 / (size_t)ctx->modp_tpi;
+    const size_t nwarps = (n + groups_per_warp - 1) / groups_per_warp;
+    const size_t rounds = (nwarps + (size_t)ctx->sm_count - 1) / (size_t)ctx->sm_count;
+    const double filler = (double)rounds * (5.0 * (ctx->v_rwin + ctx->v_cwin) + 30.0);
+    const double horner = (double)(t > 1 ? t - 1 : 0) * (3.0 * ctx->v_nd_max + 1.0);
+    if (filler > 0.6 * horner) overlap = 0;
+  }
+  const bool side = overlap == 2 || overlap == 3;
   if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
   if (ctx->v_dual)
@@ -539,7 +552,7 @@ static int verify_kernels(mpvss_ctx* ctx) {
   if (side) {
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
     // 3: persistent one-warp CTAs, one per SM, into the warp slot the Horner CTAs leave empty
-    if (ctx->modp_overlap == 3) ctx->exp2_filler_smem = (size_t)ctx->sm_count;
+    if (overlap == 3) ctx->exp2_filler_smem = (size_t)ctx->sm_count;
     int rc = launch_a2(ctx->aux[0]);
     ctx->exp2_filler_smem = 0;
     MPVSS_TRY(rc);
