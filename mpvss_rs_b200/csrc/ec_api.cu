@@ -193,9 +193,9 @@ struct Ec {
   // device-pointer launch helpers -----------------------------------------------------------
   static int dev_exp2(mpvss_ctx* ctx, const uint8_t* b1, uint32_t b1s, const uint32_t* e1, const uint8_t* b2,
                       uint32_t b2s, const uint32_t* e2, uint32_t e2s, size_t n, uint8_t* out, Point* out_jac,
-                      uint32_t* status) {
+                      uint32_t* status, cudaStream_t stream = nullptr) {
     ec::Exp2Args<Cv> A{K(ctx), b1, e1, b2, e2, out, out_jac, status, (uint32_t)n, b1s, 8, b2s, e2s, 0};
-    MPVSS_CUDA(ctx, ec::launch_exp2<Cv>(A, ctx->stream));
+    MPVSS_CUDA(ctx, ec::launch_exp2<Cv>(A, stream ? stream : ctx->stream));
     timing_launch(ctx);
     return MPVSS_OK;
   }
@@ -408,14 +408,20 @@ struct Ec {
     uint8_t* X = ctx->v_x.as<uint8_t>();
     uint32_t* st = ctx->v_slot.as<uint32_t>();
     timing_begin(ctx);
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint8_t>(), t, ctx->v_pos.as<uint32_t>(), n, ctx->v_cm, ctx->v_nd,
                          ctx->buf(12), X));
+    // a2 = r*y + c*Y does not depend on X: a small grid (one thread per share) on a side stream, issued
+    // after the Horner launches so that it only takes CTA slots they leave free
+    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+    MPVSS_TRY(dev_exp2(ctx, ctx->v_pk.as<uint8_t>(), EB, ctx->v_r.as<uint32_t>(), ctx->v_y.as<uint8_t>(), EB,
+                       ctx->v_c.as<uint32_t>(), 0, n, ctx->v_a2.as<uint8_t>(), nullptr, st + n, ctx->aux[0]));
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
-    // a1 = r*g + c*X ; a2 = r*y + c*Y  (dleq.rs:66-84)
+    // a1 = r*g + c*X  (dleq.rs:66-84)
     MPVSS_TRY(dev_exp2(ctx, ctx->gens.as<uint8_t>(), 0, ctx->v_r.as<uint32_t>(), X, EB, ctx->v_c.as<uint32_t>(), 0, n,
                        ctx->v_a1.as<uint8_t>(), nullptr, st));
-    MPVSS_TRY(dev_exp2(ctx, ctx->v_pk.as<uint8_t>(), EB, ctx->v_r.as<uint32_t>(), ctx->v_y.as<uint8_t>(), EB,
-                       ctx->v_c.as<uint32_t>(), 0, n, ctx->v_a2.as<uint8_t>(), nullptr, st + n));
+    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
     MPVSS_TRY(timing_end(ctx));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));
