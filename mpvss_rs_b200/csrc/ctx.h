@@ -80,7 +80,7 @@ struct mpvss_ctx {
   int modp_comb = 1;         // use them ("modp_comb")
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----
-  size_t ec_threads = 65536;    // target thread count of the chunked Horner launch ("ec_threads")
+  size_t ec_threads = 131072;   // target thread count of the chunked Horner launch ("ec_threads")
   DevBuf ec_consts;             // secp::Consts / rist::Consts
   big::Int ec_order;            // group order (scalar field modulus)
   std::vector<uint8_t> ec_gen;  // encoded generator (both generators of the trait are this point)
