@@ -5,19 +5,27 @@ A "step" is one pass of Participant::verify_distribution_shares (participant.rs:
 over one synthetic DistributionSharesBox: for every participant recompute
 X_i = prod_j C_j^(i^j) from the t commitments, a1 = g^r X^c, a2 = y^r Y^c, then hash the
 framed transcript on the host and compare the challenge.  Workload at N=1: the headline
-configuration of the metric, ModpGroup n=4096 t=2731.  With N GPUs every rank verifies a
-contiguous slice of n participants of one box of N*n participants (weak scaling, t fixed);
-the X/a1/a2 rows are combined with one NCCL all-gather and rank 0 hashes them.
+configuration of the metric, ModpGroup n=4096 t=2731.  With N GPUs (one process per GPU) the
+library shards the participants of ONE box of N*4096 participants round robin over the ranks
+(rank r verifies participants r, r+N, ...; weak scaling, t fixed), gathers the transcript rows
+with one ncclAllGather issued by the library on its own stream, and every rank hashes them.
+torch.distributed is used only for the NCCL-id hand-off, the barrier and the max-over-ranks.
+
+`value`: the box is RESIDENT in HBM (staged once before the timed loop; kernels + all-gather +
+D2H + host SHA-256 are timed).  `e2e`: the full mpvss_verify_distribution call from pinned host
+buffers, host->device copies and position planning inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N] [--t T]
 
 `--impl reference` times the reference's CPU schedule (oracle/cpu_baseline.c, an OpenSSL
-proxy for num-bigint since the Rust reference cannot be built here) on all host cores.
+proxy for num-bigint since the Rust reference cannot be built here) on all host cores; it never
+touches the GPU library (its box is synthesised with OpenSSL and Python integers).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -38,15 +46,23 @@ CPU_PROXY = {"modp": "OpenSSL BN_mod_exp_mont (proxy for num-bigint 0.2)",
 DTYPE = {"modp": "u32 limbs (2048-bit integers)", "secp256k1": "u32 limbs (256-bit prime fields)",
          "ristretto255": "u32 limbs (255-bit prime field)"}
 SQR_MACS, MUL_MACS = 6240, 8256          # 2048-bit Montgomery sqr / mul, 32x32->64 MACs
-Q = None
+# 256-bit fields, plain representation with special-form reduction: 8x8 limb
+# product + fold; a squaring needs 36 distinct limb products
+EC_MUL_MACS = {"secp256k1": 64 + 8, "ristretto255": 64 + 8}
+EC_SQR_MACS = {"secp256k1": 36 + 8, "ristretto255": 36 + 8}
+SEED = 0x6D70767373
+RFC3526_2048 = int(
+    "ffffffffffffffffc90fdaa22168c234c4c6628b80dc1cd129024e088a67cc74020bbea63b139b22514a08798e3404dd"
+    "ef9519b3cd3a431b302b0a6df25f14374fe1356d6d51c245e485b576625e7ec6f44c42e9a637ed6b0bff5cb6f406b7ed"
+    "ee386bfb5a899fa5ae9f24117c4b1fe649286651ece45b3dc2007cb8a163bf0598da48361c55d39a69163fa8fd24cf5f"
+    "83655d23dca3ad961c62f356208552bb9ed529077096966d670c354e4abc9804f1746c08ca18217c32905e462e36ce3b"
+    "e39e772c180e86039b2783a2ec07a28fb5c55df06f4c52c9de2bcbf6955817183995497cea956ae515d2261898fa0510"
+    "15728e5a8aacaa68ffffffffffffffff", 16)
+SECP_N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 
 def env_int(k, d):
     return int(os.environ.get(k, d))
-
-
-def le256(x):
-    return int(x).to_bytes(256, "little")
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -97,8 +113,9 @@ class ClockSampler:
 
 # --------------------------------------------------------------- workload ----
 def build_box(group, n_total, t, seed):
-    """Synthetic DistributionSharesBox made with the library's own dealer path.
-    Returns flat boundary-encoded arrays in publickeys order."""
+    """Synthetic DistributionSharesBox made with the library's own dealer path
+    (mpvss_distribute; collective and sharded when the group's context has a communicator: every rank
+    receives the same box).  Returns flat boundary-encoded arrays in publickeys order."""
     from mpvss_rs_b200 import synth
     from mpvss_rs_b200.lib import buf, ptr
     c = group.codec
@@ -116,37 +133,75 @@ def build_box(group, n_total, t, seed):
         ptr(buf(c.enc_scalars(ws))), ptr(buf(pk_b)), ptr(comm), ptr(shares), ptr(chal), ptr(resp), ptr(u), ptr(x)))
     return {"commitments": bytes(comm), "publickeys": pk_b, "shares": bytes(shares), "responses": bytes(resp),
             "challenge": bytes(chal), "x_dealer": bytes(x), "n": n_total, "t": t, "eb": eb, "sb": sb,
-            "group": c.name}
+            "group": c.name, "U": int.from_bytes(bytes(u), "big")}
 
 
-def horner_macs(positions, t, tpi=8):
-    """Algorithmic MACs of the X_i kernel for the given 1-based positions, following the schedule the
-    kernel executes: per Horner step (2(d-1)+1) squarings and (d-1)+2
-    multiplications, d = base-4 digits of the position, minus the window multiplications skipped
-    because the digit is zero for every lane group of the warp (positions are dealt to warps in
-    increasing order inside each digit class, exactly as modp_api.cu::prep_positions does)."""
-    gpw = 32 // tpi
-    by = {}
-    for p in positions:
-        d = 1
-        while p >> (2 * d):
-            d += 1
-        by.setdefault(d, []).append(p)
-    total = 0
-    for d, ps in by.items():
-        for c in range(0, len(ps), gpw):
-            chunk = ps[c:c + gpw]
-            full = chunk + [chunk[-1]] * (gpw - len(chunk))
-            skipped = sum(1 for s_ in range(d - 1) if all(((q >> (2 * s_)) & 3) == 0 for q in full))
-            total += len(chunk) * (t - 1) * ((2 * (d - 1) + 1) * SQR_MACS + ((d - 1) + 2 - skipped) * MUL_MACS)
-    return total
+def participant_box(group, box):
+    """The flat box as the reference-shaped DistributionSharesBox (tests)."""
+    import mpvss_rs_b200 as m
+    c, n = group.codec, box["n"]
+    b = m.DistributionSharesBox()
+    b.commitments = c.dec_elems(box["commitments"], box["t"])
+    b.publickeys = c.dec_elems(box["publickeys"], n)
+    ys, rs = c.dec_elems(box["shares"], n), c.dec_scalars(box["responses"], n)
+    for i, pk in enumerate(b.publickeys):
+        k = c.key(pk)
+        b.positions[k], b.shares[k], b.responses[k] = i + 1, ys[i], rs[i]
+    b.challenge = c.dec_scalar(box["challenge"])
+    b.U = box["U"]
+    return b
+
+
+def reference_box(group_name, n_total, t, sample_idx, seed, threads):
+    """A box for the CPU reference arm, built WITHOUT the GPU library: commitments with OpenSSL
+    (oracle/cpu_baseline.c), the sampled participants' keys / shares / responses with OpenSSL and Python
+    integers.  The transcript challenge would need all n_total participants; a pseudo-challenge of the same
+    size stands in (the DLEQ relations a1 = g^w, a2 = y^w hold for any challenge and are asserted)."""
+    from mpvss_rs_b200 import synth       # pure Python (SHA-256 counter mode), no library call
+    from oracle import cpu_baseline as cb
+    from oracle import pvss
+    modp = group_name == "modp"
+    order = RFC3526_2048 - 1 if modp else SECP_N
+    bound = RFC3526_2048 if modp else SECP_N
+    sks = synth.private_keys(seed, n_total, group_name, order, bound)
+    coeffs = synth.coefficients(seed, t, order)
+    ws = synth.witnesses(seed, n_total, bound)
+    chal = int.from_bytes(hashlib.sha256(b"bench pseudo-challenge %d" % seed).digest(), "big") % \
+        ((RFC3526_2048 - 1) // 2 if modp else SECP_N)
+    ps = [pvss.poly_eval_mod(coeffs, i + 1, order) for i in sample_idx]
+    rs = [(ws[i] - p * chal) % order for i, p in zip(sample_idx, ps)]
+    if modp:
+        q = RFC3526_2048
+        comm = cb.modp_exp(q, 4, coeffs, threads)
+        pks = cb.modp_exp(q, 2, [sks[i] for i in sample_idx], threads)
+        ys = cb.modp_exp(q, pks, ps, threads)
+        a1 = cb.modp_exp(q, 4, [ws[i] for i in sample_idx], threads)
+        a2 = cb.modp_exp(q, pks, [ws[i] for i in sample_idx], threads)
+        le = lambda v: int(v).to_bytes(256, "little")
+        enc_e = enc_s = le
+    else:
+        comm = cb.secp_mul(None, coeffs)
+        pks = cb.secp_mul(None, [sks[i] for i in sample_idx])
+        ys = cb.secp_mul(pks, ps)
+        a1 = cb.secp_mul(None, [ws[i] for i in sample_idx])
+        a2 = cb.secp_mul(pks, [ws[i] for i in sample_idx])
+        enc_e = bytes
+        enc_s = lambda v: int(v).to_bytes(32, "big")
+    eb, sb = (256, 256) if modp else (33, 32)
+    rows = lambda vals, enc, w: {i: enc(v) for i, v in zip(sample_idx, vals)}
+    return {"commitments": b"".join(enc_e(v) for v in comm), "pk_rows": rows(pks, enc_e, eb), "y_rows": rows(ys, enc_e, eb),
+            "r_rows": rows(rs, enc_s, sb), "challenge": enc_s(chal), "n": n_total, "t": t, "eb": eb, "sb": sb,
+            "group": group_name, "expect_a1": [enc_e(v) for v in a1], "expect_a2": [enc_e(v) for v in a2]}
 
 
 def dleq_macs(n, rwin=512, cwin=64):
-    """Algorithmic MACs of the two DLEQ commitment launches (4-bit fixed windows)."""
-    def exp(w):
-        return 4 * (w - 1) * SQR_MACS + (15 + (w - 1)) * MUL_MACS  # 14 table mults + to-Montgomery
-    return 2 * n * (exp(rwin) + exp(cwin) + 2 * MUL_MACS)
+    """Algorithmic MACs of the two DLEQ commitment launches."""
+    def win4(w):        # variable base, fixed 4-bit windows: 14 table products + to-Montgomery, 4 sqr + 1 mul per window
+        return 4 * (w - 1) * SQR_MACS + (15 + (w - 1)) * MUL_MACS
+    comb = ((rwin + 1) // 2 - 1) * MUL_MACS            # g^r from the 8-bit fixed-base table: one product per byte
+    a1 = comb + win4(cwin) + 2 * MUL_MACS              # * X^c, leave Montgomery form
+    a2 = win4(rwin) + win4(cwin) + 2 * MUL_MACS
+    return n * (a1 + a2)
 
 
 def measure_imad_peak():
@@ -161,41 +216,63 @@ def measure_imad_peak():
         wide = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_wide"))
         return lo, wide, "measured live (tools/imad_peak)"
     except Exception:
-        try:
-            j = json.load(open(os.path.join(ROOT, "profiles", "imad_peak_r01.json")))
-            lo = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_lo_"))
-            wide = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_wide"))
-            return lo, wide, "profiles/imad_peak_r01.json (measured on this pool)"
-        except Exception:
-            return 18.4, 7.7, "fallback constant (round-1 measurement)"
+        for name in ("imad_peak_r02.json", "imad_peak_r01.json"):
+            try:
+                j = json.load(open(os.path.join(ROOT, "profiles", name)))
+                lo = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_lo_"))
+                wide = max(v["tera_per_s"] for k, v in j.items() if k.startswith("imad_wide"))
+                return lo, wide, f"profiles/{name} (measured on this pool)"
+            except Exception:
+                continue
+        return 18.4, 7.7, "fallback constant (round-1 measurement)"
 
 
 # ------------------------------------------------------------ CPU baseline ----
 def cpu_reference_step(box, sample_idx, threads, schedule=0):
-    """One bounded sample of the workload on the host cores; returns (seconds, X rows as boundary bytes)."""
+    """One bounded sample of the workload on the host cores: X_i, a1, a2 of the sampled participants
+    with the reference's loop structure, then their framed SHA-256 transcript.  Accepts the GPU arm's flat
+    box or reference_box().  Returns (seconds, X rows, a1 rows, a2 rows) as boundary bytes."""
     from oracle import cpu_baseline
     lib = cpu_baseline.load()
     s = len(sample_idx)
     t, eb, sb = box["t"], box["eb"], box["sb"]
     pos = (ctypes.c_int64 * s)(*[i + 1 for i in sample_idx])
-    row = lambda key, w: [box[key][i * w:(i + 1) * w] for i in sample_idx]
+
+    def row(key, w):
+        sparse = {"publickeys": "pk_rows", "shares": "y_rows", "responses": "r_rows"}[key]
+        if sparse in box:                                   # reference_box(): only the sampled rows exist
+            return [box[sparse][i] for i in sample_idx]
+        return [box[key][i * w:(i + 1) * w] for i in sample_idx]
     xo, a1o, a2o = (ctypes.create_string_buffer(eb * s) for _ in range(3))
     if box["group"] == "modp":
-        from mpvss_rs_b200.participant import RFC3526_2048 as q
         be = lambda b: bytes(reversed(b))
         comm = b"".join(be(box["commitments"][j * 256:(j + 1) * 256]) for j in range(t))
         sel = lambda key: b"".join(be(r) for r in row(key, 256))
+        pk, y, r, c = sel("publickeys"), sel("shares"), sel("responses"), be(box["challenge"])
+        q = RFC3526_2048.to_bytes(256, "big")
         t0 = time.perf_counter()
-        lib.cpu_modp_verify(q.to_bytes(256, "big"), comm, t, pos, sel("publickeys"), sel("shares"), sel("responses"),
-                            be(box["challenge"]), s, threads, schedule, xo, a1o, a2o)
+        lib.cpu_modp_verify(q, comm, t, pos, pk, y, r, c, s, threads, schedule, xo, a1o, a2o)
+        h = hashlib.sha256()       # dleq.rs:58-61, 87-99: len_u64_be || minimal big-endian bytes
+        for i in range(s):
+            for blob in (xo.raw, y, a1o.raw, a2o.raw):
+                e = blob[i * 256:(i + 1) * 256].lstrip(b"\0") or b"\0"
+                h.update(len(e).to_bytes(8, "big") + e)
+        h.digest()
         dt = time.perf_counter() - t0
-        return dt, [bytes(reversed(xo.raw[i * 256:(i + 1) * 256])) for i in range(s)]
+        dec = lambda o: [bytes(reversed(o.raw[i * 256:(i + 1) * 256])) for i in range(s)]
+        return dt, dec(xo), dec(a1o), dec(a2o)
     if box["group"] == "secp256k1":
+        pk, y, r = b"".join(row("publickeys", 33)), b"".join(row("shares", 33)), b"".join(row("responses", 32))
         t0 = time.perf_counter()
-        lib.cpu_secp_verify(box["commitments"], t, pos, b"".join(row("publickeys", 33)), b"".join(row("shares", 33)),
-                            b"".join(row("responses", 32)), box["challenge"], s, threads, schedule, xo, a1o, a2o)
+        lib.cpu_secp_verify(box["commitments"], t, pos, pk, y, r, box["challenge"], s, threads, schedule, xo, a1o, a2o)
+        h = hashlib.sha256()
+        for i in range(s):
+            for blob in (xo.raw, y, a1o.raw, a2o.raw):
+                h.update((33).to_bytes(8, "big") + blob[i * 33:(i + 1) * 33])
+        h.digest()
         dt = time.perf_counter() - t0
-        return dt, [xo.raw[i * 33:(i + 1) * 33] for i in range(s)]
+        dec = lambda o: [o.raw[i * 33:(i + 1) * 33] for i in range(s)]
+        return dt, dec(xo), dec(a1o), dec(a2o)
     raise ValueError("no CPU baseline for " + box["group"])
 
 
@@ -203,7 +280,139 @@ def spread_sample(n, s):
     return sorted({min(n - 1, (k * n) // s + (n // (2 * s))) for k in range(s)})
 
 
-# ------------------------------------------------------------------- main ----
+def reference_arm(args, n_total, t, config, cores):
+    """--impl reference: the reference's CPU schedule on all host cores; never loads the GPU library."""
+    sample = spread_sample(n_total, min(cores, n_total))
+    box = reference_box(args.group, n_total, t, sample, args.seed, cores)
+    _, _, a1, a2 = cpu_reference_step(box, sample, cores, schedule=1)   # correctness gate on the cheap schedule
+    if a1 != box["expect_a1"] or a2 != box["expect_a2"]:
+        raise SystemExit("CPU restatement: a1 != g^w or a2 != y^w on the synthetic box -- refusing to report")
+    for _ in range(args.warmup):
+        cpu_reference_step(box, sample[: max(1, len(sample) // 4)], cores)
+    times = [cpu_reference_step(box, sample, cores)[0] for _ in range(args.steps)]
+    per = statistics.mean(times)
+    val = len(sample) / per
+    return {"impl": "reference", "metric": METRICS[args.group], "value": val, "unit": "shares/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.group], "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": "shares/s", "cores": cores, "per_core": val / cores, "kind": "port",
+                             "sample": f"{len(sample)} participants per step at positions spread over "
+                                       f"1..{n_total}, full t={t}, reference schedule (t+4 exponentiations per "
+                                       "share, participant.rs:423-447) + framed SHA-256 of their rows, on " +
+                                       CPU_PROXY[args.group] + "; box synthesised with OpenSSL/Python, GPU library "
+                                       "not loaded"},
+            "e2e": {"value": val, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ----------------------------------------------------------------- GPU arm ----
+class Runner:
+    """One synthetic box on one group context (with or without a communicator); times resident steps and
+    full calls."""
+
+    def __init__(self, group, box, torch, dist, rank, world):
+        self.g, self.box, self.torch, self.dist, self.rank, self.world = group, box, torch, dist, rank, world
+        self.lib, self.h = group.ctx.lib, group.ctx.h
+        pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
+        self.host = {k: pin(box[k]) for k in ("commitments", "publickeys", "shares", "responses", "challenge")}
+        self.ok = ctypes.c_int(0)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.modp = box["group"] == "modp"
+
+    def P(self, key):
+        return ctypes.cast(self.host[key].data_ptr(), ctypes.POINTER(ctypes.c_uint8))
+
+    def stage(self):
+        b = self.box
+        self.g.ctx.check(self.lib.mpvss_verify_distribution_stage(
+            self.h, b["n"], b["t"], self.P("commitments"), None, self.P("publickeys"), self.P("shares"),
+            self.P("responses"), self.P("challenge")))
+
+    def run(self, x_out=None, digest=None):
+        self.g.ctx.check(self.lib.mpvss_verify_distribution_run(self.h, ctypes.byref(self.ok), x_out, None, None, digest))
+        return self.ok.value, self.g.ctx.last_kernel_ms, self.g.ctx.last_phase_ms(2 if self.modp else 0)
+
+    def full(self):
+        b = self.box
+        self.g.ctx.check(self.lib.mpvss_verify_distribution(
+            self.h, b["n"], b["t"], self.P("commitments"), None, self.P("publickeys"), self.P("shares"),
+            self.P("responses"), self.P("challenge"), ctypes.byref(self.ok), None, None, None, None))
+        return self.ok.value
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def maxr(self, x):
+        if self.dist is None:
+            return x
+        tns = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(tns, op=self.dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    def timed(self, fn, steps, warmup):
+        out = []
+        for i in range(warmup + steps):
+            self.flush.zero_()
+            self.barrier()
+            t0 = time.perf_counter()
+            r = fn()
+            self.barrier()
+            dt = self.maxr(time.perf_counter() - t0)
+            if i >= warmup:
+                out.append((dt, r))
+        return out
+
+    def measure(self, steps, warmup):
+        """resident steps, then full calls; returns a dict of means (max over ranks per step)"""
+        self.stage()
+        res = self.timed(self.run, steps, warmup)
+        assert all(r[1][0] == 1 for r in res), "synthetic box did not verify"
+        launches = self.g.ctx.last_kernel_launches * steps * self.world
+        sq, ml = self.g.ctx.last_horner_products()
+        e2e = self.timed(self.full, steps, warmup)
+        assert all(r[1] == 1 for r in e2e)
+        return {"ms": statistics.mean(r[0] for r in res) * 1e3,
+                "kernel_ms": statistics.mean(self.maxr(r[1][1]) for r in res),
+                "horner_ms": statistics.mean(self.maxr(r[1][2]) for r in res),
+                "e2e_ms": statistics.mean(r[0] for r in e2e) * 1e3, "launches": launches, "sqr": sq, "mul": ml}
+
+
+def modp_roofline(m, n_local, imad_lo, imad_wide, peak_src, traffic=None):
+    hm = m["sqr"] * SQR_MACS + m["mul"] * MUL_MACS
+    achieved = 2.0 * hm / (m["horner_ms"] * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues (SURVEY 8d)
+    total = hm + dleq_macs(n_local)
+    step = 2.0 * total / (m["kernel_ms"] * 1e-3) / 1e12
+    return {
+        "bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation, addition chains)",
+        "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
+        "peak_source": peak_src + "; 32-bit IMAD issue rate, 1 MAC (32x32->64) = 2 IMAD",
+        "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
+        "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
+        "algorithmic_macs_per_launch": hm, "modsqr_per_launch": m["sqr"], "modmul_per_launch": m["mul"],
+        "kernel_ms": m["horner_ms"], "share_of_step_macs": hm / total, "traffic": traffic,
+        "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full (profiles/)",
+        "note": "kernel_ms = CUDA events around the Horner launch on the library stream (max over ranks); "
+                "algorithmic MACs = products the executed addition chains contain (library counter, rank 0's "
+                "participants), squarings at 6240 and multiplications at 8256 MACs; padding products excluded",
+        "whole_step": {"achieved": step, "frac": step / imad_lo if imad_lo else None, "algorithmic_macs": total,
+                       "kernel_ms": m["kernel_ms"],
+                       "what": "all kernels of the step (Horner + both DLEQ launches; g^r from the fixed-base table)"}}
+
+
+def ec_roofline(m, group_name, imad_lo, imad_wide, peak_src):
+    macs = m["sqr"] * EC_SQR_MACS[group_name] + m["mul"] * EC_MUL_MACS[group_name]
+    achieved = 2.0 * macs / (m["horner_ms"] * 1e-3) / 1e12
+    return {"bound": "imad", "kernel": f"ec::horner_kernel<{group_name}> (chunked X_i Horner incl. chunk scaling)",
+            "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
+            "peak_source": peak_src, "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
+            "algorithmic_macs_per_launch": macs, "field_sqr_per_launch": m["sqr"], "field_mul_per_launch": m["mul"],
+            "kernel_ms": m["horner_ms"], "traffic": None,
+            "note": "field products executed by the Horner launches (library counter) x 72 / 44 MACs "
+                    "(8x8 limb product or 36 distinct squaring products + 8 for the special-form fold)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,248 +423,162 @@ def main():
     ap.add_argument("--n", "--participants-per-gpu", dest="n", type=int, default=4096, help="participants per GPU")
     ap.add_argument("--t", "--threshold", dest="t", type=int, default=0, help="threshold (default ceil(2n/3))")
     ap.add_argument("--tpi", type=int, default=0, help="override lanes per 2048-bit value")
-    ap.add_argument("--seed", type=int, default=0x6D70767373)
+    ap.add_argument("--seed", type=int, default=SEED)
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
-    ap.add_argument("--dual", type=int, default=-1, help="override modp_dual (0/1/2)")
     ap.add_argument("--ec-threads", type=int, default=0)
-    ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0, 2 or 3; default 3 = a2 as persistent one-warp CTAs in the idle warp slots)")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary secp256k1 measurement")
+    ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0, 2 or 3)")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c5", action="store_true", help="also time BASELINE config 5 (n=65536 t=43691) [default at 8 GPUs]")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     n = args.n
     t = args.t or -(-2 * n // 3)
     n_total = n * world
     cores = os.cpu_count() or 1
+    config = {"workload": f"{args.group} verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
+              "group": args.group, "n_per_gpu": n, "n_total": n_total, "t": t,
+              "x_schedule": "Horner in the exponent; acc^i by power-tree addition chains (DESIGN.md section 2)",
+              "residency": "value: box resident in HBM, staging excluded; e2e: host buffers, staging included",
+              "l2": "flushed between timed steps (256 MiB write)",
+              "sharding": f"participants round-robin over {world} rank(s) inside the library, one ncclAllGather of "
+                          "the framed transcript rows per step, every rank hashes"}
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(args, n_total, t, config, cores)))
+        return 0
 
     import torch
-    if args.impl == "reference" and rank != 0:
-        return 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mpvss_rs_b200 has no CPU path")
     torch.cuda.set_device(local)
     dist = None
-    if world > 1 and args.impl == "ours":
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import mpvss_rs_b200 as m
     from mpvss_rs_b200.lib import buf, ptr
-    METRIC = METRICS[args.group]
-    group = m.Group(args.group, device=local)
-    eb, sb = group.codec.eb, group.codec.sb
-    if args.tpi and args.group == "modp":
-        group.ctx.set_int("modp_tpi", args.tpi)
-    if args.ec_threads and args.group != "modp":
-        group.ctx.set_int("ec_threads", args.ec_threads)
-    if args.overlap >= 0 and args.group == "modp":
-        group.ctx.set_int("modp_overlap", args.overlap)
-    if args.dual >= 0 and args.group == "modp":
-        group.ctx.set_int("modp_dual", args.dual)
-    lib, h = group.ctx.lib, group.ctx.h
+
+    def make_group(name, joined):
+        g = m.Group(name, device=local)
+        if args.tpi and name == "modp":
+            g.ctx.set_int("modp_tpi", args.tpi)
+        if args.ec_threads and name != "modp":
+            g.ctx.set_int("ec_threads", args.ec_threads)
+        if args.overlap >= 0 and name == "modp":
+            g.ctx.set_int("modp_overlap", args.overlap)
+        if joined and world > 1:
+            g.join(rank, world, dist)           # NCCL communicator inside the library
+        return g
+
+    group = make_group(args.group, True)
+    eb = group.codec.eb
     box = build_box(group, n_total, t, args.seed)
-    config = {"workload": f"{args.group} verify_distribution_shares n={n} per GPU (box of {n_total}), t={t}",
-              "group": args.group, "n_per_gpu": n, "n_total": n_total, "t": t,
-              "x_schedule": "Horner in the exponent, fixed 2-bit windows (DESIGN.md)",
-              "l2": "flushed between timed steps (256 MiB write)", "sharding": f"participants round-robin over {world} rank(s), one NCCL all-gather per step"}
+    runner = Runner(group, box, torch, dist, rank, world)
 
-    # ---------------------------------------------------------- reference arm ----
-    if args.impl == "reference":
-        sample = spread_sample(n_total, min(cores, n_total))
-        for _ in range(args.warmup):
-            cpu_reference_step(box, sample[: max(1, len(sample) // 4)], cores)
-        times = [cpu_reference_step(box, sample, cores)[0] for _ in range(args.steps)]
-        per = statistics.mean(times)
-        val = len(sample) / per
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "shares/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.group],
-                "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "shares/s", "cores": cores, "kind": "port",
-                                 "sample": f"{len(sample)} participants per step at positions spread over "
-                                           f"1..{n_total}, full t={t}, reference schedule (t+4 exponentiations per "
-                                           "share, participant.rs:423-447) on " + CPU_PROXY[args.group]},
-                "e2e": {"value": val, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+    # correctness gates before timing: the box verifies; the verifier's X equals the dealer's g^P(i); at N>1 the
+    # sharded transcript digest equals the single-GPU digest of the same box
+    runner.stage()
+    dig = buf(size=32)
+    if world == 1:
+        x_chk = buf(size=n * eb)
+        okv, _, _ = runner.run(ptr(x_chk), ptr(dig))
+        if okv != 1:
+            raise SystemExit("verification of the synthetic box failed -- refusing to report a number")
+        if bytes(x_chk) != box["x_dealer"]:
+            raise SystemExit("verifier X_i differs from dealer X_i -- refusing to report a number")
+    else:
+        okv, _, _ = runner.run(None, ptr(dig))
+        if okv != 1:
+            raise SystemExit("sharded verification of the synthetic box failed -- refusing to report a number")
+        if rank == 0 and n_total <= 16384:
+            solo = make_group(args.group, False)
+            r1 = Runner(solo, box, torch, None, 0, 1)
+            r1.stage()
+            d1 = buf(size=32)
+            ok1, _, _ = r1.run(None, ptr(d1))
+            if ok1 != 1 or bytes(d1) != bytes(dig):
+                raise SystemExit("sharded transcript digest != single-GPU digest -- refusing to report a number")
+            config["digest_check"] = "sharded transcript digest == single-GPU digest of the same box (rank 0)"
+            solo.ctx.close()
+        runner.barrier()
 
-    # --------------------------------------------------------------- our arm ----
-    # rank r takes positions r+1, r+1+N, ... (round robin): every rank sees the same mix of small and
-    # large positions, so per-rank work is equal; the gathered rows are re-interleaved for the transcript
-    from mpvss_rs_b200.sharding import interleave, shard_indices
-    mine = shard_indices(rank, world, n_total)
-
-    def sl(key):
-        w = sb if key == "responses" else eb
-        if world == 1:
-            return box[key]
-        return b"".join(box[key][i * w:(i + 1) * w] for i in mine)
-    positions = (ctypes.c_int64 * n)(*[i + 1 for i in mine])
-    pin = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
-    host = {k: pin(v) for k, v in (("commitments", box["commitments"]), ("publickeys", sl("publickeys")),
-                                   ("shares", sl("shares")), ("responses", sl("responses")),
-                                   ("challenge", box["challenge"]))}
-    P = lambda tns: ctypes.cast(tns.data_ptr(), ctypes.POINTER(ctypes.c_uint8))
-    ok = ctypes.c_int(0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    out_local = torch.empty((3, n, eb), dtype=torch.uint8, device="cuda")
-    out_all = torch.empty((world, 3, n, eb), dtype=torch.uint8, device="cuda") if world > 1 else None
-    out_host = torch.empty((world, 3, n, eb), dtype=torch.uint8).pin_memory() if world > 1 else None
-    x_chk = buf(size=n * eb)
-    shares_all, chal_all = buf(box["shares"]), buf(box["challenge"])
-    import numpy as np
-
-    PH = 2 if args.group == "modp" else 0   # phase index of the dominant (Horner) launch
-
-    def stage():
-        group.ctx.check(lib.mpvss_verify_distribution_stage(
-            h, n, t, P(host["commitments"]), positions, P(host["publickeys"]), P(host["shares"]),
-            P(host["responses"]), P(host["challenge"])))
-
-    def run_resident(want_x=False):
-        """one step with the box resident in HBM; returns (ok, kernel_ms, Horner-launch ms)"""
-        if world == 1:
-            group.ctx.check(lib.mpvss_verify_distribution_run(h, ctypes.byref(ok), ptr(x_chk) if want_x else None,
-                                                              None, None, None))
-            return ok.value, group.ctx.last_kernel_ms, group.ctx.last_phase_ms(PH)
-        group.ctx.check(lib.mpvss_verify_distribution_compute(
-            h, out_local[0].data_ptr(), out_local[1].data_ptr(), out_local[2].data_ptr()))
-        kms, p0 = group.ctx.last_kernel_ms, group.ctx.last_phase_ms(PH)
-        dist.all_gather_into_tensor(out_all, out_local)          # one NCCL all-gather per phase
-        res = 1
-        if rank == 0:
-            # [rank, kind, j, eb] -> [kind, j, rank, eb] (participant j*N + rank) on the device, then one
-            # contiguous D2H copy: the re-interleave is a 25 MB permute at HBM speed instead of a host pass
-            out_host.copy_(out_all.permute(1, 2, 0, 3).contiguous().view(world, 3, n, eb), non_blocking=False)
-            arr = out_host.numpy().reshape(3, n, world, eb)
-            u8 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
-            group.ctx.check(lib.mpvss_transcript_check(h, n_total, u8(arr[0]), ptr(shares_all), u8(arr[1]), u8(arr[2]),
-                                                       ptr(chal_all), ctypes.byref(ok), None))
-            res = ok.value
-        return res, kms, p0
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def maxr(x):
-        if dist is None:
-            return x
-        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
-        return float(tns.item())
-
-    stage()
-    # correctness gate before timing: the box verifies and the verifier's X equals the dealer's g^P(i)
-    okv, _, _ = run_resident(want_x=(world == 1))
-    if rank == 0 and okv != 1:
-        raise SystemExit("verification of the synthetic box failed -- refusing to report a number")
-    if world == 1 and bytes(x_chk) != box["x_dealer"]:
-        raise SystemExit("verifier X_i differs from dealer X_i -- refusing to report a number")
-
-    imad_lo, imad_wide, peak_src = (measure_imad_peak() if rank == 0 and args.group == "modp" else (0, 0, ""))
-    for _ in range(args.warmup):
-        run_resident()
+    imad_lo, imad_wide, peak_src = measure_imad_peak() if rank == 0 else (0, 0, "")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    step_s, kern_ms, p0_ms, launches = [], [], [], 0
-    for _ in range(args.steps):
-        flush.zero_()
-        barrier()
-        t0 = time.perf_counter()
-        okv, kms, p0 = run_resident()
-        barrier()
-        step_s.append(maxr(time.perf_counter() - t0))
-        kern_ms.append(maxr(kms))
-        p0_ms.append(maxr(p0))
-        launches += group.ctx.last_kernel_launches
-        assert rank != 0 or okv == 1
-    # end to end through the reference-facing call, host buffers, copies inside the timed region
-    e2e_s = []
-    if world == 1:
-        for i in range(args.warmup + args.steps):
-            flush.zero_()
-            barrier()
-            t0 = time.perf_counter()
-            group.ctx.check(lib.mpvss_verify_distribution(
-                h, n, t, P(host["commitments"]), positions, P(host["publickeys"]), P(host["shares"]),
-                P(host["responses"]), P(host["challenge"]), ctypes.byref(ok), None, None, None, None))
-            barrier()
-            if i >= args.warmup:
-                e2e_s.append(time.perf_counter() - t0)
-            assert ok.value == 1
-    else:
-        for i in range(args.warmup + args.steps):
-            flush.zero_()
-            barrier()
-            t0 = time.perf_counter()
-            stage()
-            okv, _, _ = run_resident()
-            barrier()
-            if i >= args.warmup:
-                e2e_s.append(maxr(time.perf_counter() - t0))
+    meas = runner.measure(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+
+    also = {}
+    if world > 1 and not args.no_also:
+        # strong scaling: the metric's box (n = 4096 in total) split over the N GPUs
+        sg = make_group(args.group, True)
+        sbox = build_box(sg, n, t, args.seed)
+        sm = Runner(sg, sbox, torch, dist, rank, world).measure(args.steps, args.warmup)
+        also["strong"] = {"scaling": "strong", "n_total": n, "t": t, "value": n / (sm["ms"] * 1e-3), "unit": "shares/s",
+                          "ms_per_step": sm["ms"], "kernel_ms_per_step": sm["kernel_ms"],
+                          "e2e": {"value": n / (sm["e2e_ms"] * 1e-3), "unit": "shares/s"},
+                          "note": "one box of n participants in total, sharded over all ranks"}
+        sg.ctx.close()
+    if (args.c5 or world == 8) and args.group == "modp" and not args.no_also:
+        # BASELINE config 5: ModpGroup n = 65536, t = 43691, distribute + verify sharded over the ranks
+        cg = make_group("modp", True)
+        t0 = time.perf_counter()
+        cbox = build_box(cg, 65536, 43691, args.seed)
+        dist_s = runner.maxr(time.perf_counter() - t0)
+        cm = Runner(cg, cbox, torch, dist, rank, world).measure(2, 1)
+        c5 = {"workload": "modp n=65536 t=43691 (BASELINE config 5)", "n_gpus": world, "steps": 2, "warmup": 1,
+              "value": 65536 / (cm["ms"] * 1e-3), "unit": "shares/s", "ms_per_step": cm["ms"],
+              "kernel_ms_per_step": cm["kernel_ms"], "e2e": {"value": 65536 / (cm["e2e_ms"] * 1e-3), "unit": "shares/s"},
+              "distribute_wall_s": dist_s,
+              "distribute_note": "synthetic keys + mpvss_distribute (sharded dealer) incl. Python marshalling"}
+        if rank == 0:
+            c5["roofline"] = modp_roofline(cm, 65536 // world, imad_lo, imad_wide, peak_src)
+        also["c5"] = c5
+        cg.ctx.close()
     if rank != 0:
         dist.destroy_process_group()
         return 0
 
-    ms = statistics.mean(step_s) * 1e3
-    value = n_total / (ms * 1e-3)
-    e2e_ms = statistics.mean(e2e_s) * 1e3
-    h2d = t * eb + 2 * n * eb + n * sb + sb + 8 * n
-    d2h = 3 * n * eb
-    p0 = statistics.mean(p0_ms)
+    value = n_total / (meas["ms"] * 1e-3)
+    sb = group.codec.sb
+    n_loc = n_total // world
+    h2d = world * (t * eb + sb) + n_total * (2 * eb + sb)
+    d2h = world * n_total * 4 * (8 + eb)
     line = {
-        "metric": METRIC, "value": value, "unit": "shares/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRICS[args.group], "value": value, "unit": "shares/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": meas["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": DTYPE[args.group], "data": "synthetic", "config": config,
-        "timing": "per step: cuda-synchronize + barrier bracketed wall clock (kernels + D2H + host SHA-256), "
-                  "max over ranks; kernel_ms / roofline from CUDA events on the library's stream",
-        "kernel_ms_per_step": statistics.mean(kern_ms),
-        "gpu_launches": launches,
+        "timing": "per step: cuda-synchronize + barrier bracketed wall clock (kernels + all-gather + chunked D2H "
+                  "overlapped with the host SHA-256), box resident in HBM, max over ranks; kernel_ms / roofline "
+                  "from CUDA events on the library's stream",
+        "kernel_ms_per_step": meas["kernel_ms"], "host_tail_ms": meas["ms"] - meas["kernel_ms"],
+        "gpu_launches": meas["launches"],
         "clocks": clocks,
-        "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "shares/s", "ms_per_step": e2e_ms,
+        "e2e": {"value": n_total / (meas["e2e_ms"] * 1e-3), "unit": "shares/s", "ms_per_step": meas["e2e_ms"],
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "mpvss_verify_distribution (pinned host buffers in, verdict out)"},
+                "call": "mpvss_verify_distribution (pinned host buffers in, verdict out; collective at N>1)"},
     }
     if args.group == "modp":
-        hm = horner_macs([i + 1 for i in mine], t, args.tpi or (4 if n >= 32768 else 8))
-        achieved = 2.0 * hm / (p0 * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues (SURVEY 8d)
-        dual = (args.dual > 0) and t >= 8   # library default: single chain (modp_dual = 0)
-        combine = n * (4 * 511 * SQR_MACS + (15 + 511 + 15 + 2) * MUL_MACS) if dual else 0
-        total_macs = hm + combine + dleq_macs(n)
-        step_timad = 2.0 * total_macs / (statistics.mean(kern_ms) * 1e-3) / 1e12
-        line["roofline"] = {
-            "bound": "imad", "kernel": "modp::horner_kernel (X_i multi-exponentiation)",
-            "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
-            "peak_source": peak_src + "; 32-bit IMAD issue rate, 1 MAC (32x32->64) = 2 IMAD",
-            "achieved_tmac_per_s": achieved / 2, "wide_mac_peak_tmac_per_s": imad_wide,
-            "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
-            "algorithmic_macs_per_launch": hm, "kernel_ms": p0,
-            "share_of_step_macs": hm / total_macs, "traffic": 976640,
-            "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full, profiles/horner_r01_ncu.txt",
-            "note": "kernel_ms = CUDA events around the Horner launch on the library stream; algorithmic MACs "
-                    "follow the executed fixed-window schedule, skipped zero-digit multiplications excluded",
-            "whole_step": {"achieved": step_timad, "frac": step_timad / imad_lo if imad_lo else None,
-                           "algorithmic_macs": total_macs, "kernel_ms": statistics.mean(kern_ms),
-                           "what": "all kernels of the step (Horner + chunk combination + both DLEQ launches)"}}
+        line["roofline"] = modp_roofline(meas, n_loc, imad_lo, imad_wide, peak_src)
     else:
-        line["roofline"] = None
-        line["phase_ms"] = {"x_horner": p0, "dleq": statistics.mean(kern_ms) - p0}
+        line["roofline"] = ec_roofline(meas, args.group, imad_lo, imad_wide, peak_src)
+        line["phase_ms"] = {"x_horner": meas["horner_ms"], "dleq": meas["kernel_ms"] - meas["horner_ms"]}
     if not args.no_cpu_baseline and world == 1 and args.group in CPU_PROXY:
         sample = spread_sample(n_total, min(cores, n_total))
-        dt, xs = cpu_reference_step(box, sample, cores)
+        dt, xs, _, _ = cpu_reference_step(box, sample, cores)
         for i, x in zip(sample, xs):       # the CPU restatement and the GPU agree on X_i
-            assert x == bytes(x_chk)[i * eb:(i + 1) * eb], "CPU baseline X_i != GPU X_i"
-        dt_h, _ = cpu_reference_step(box, sample, cores, schedule=1)
+            assert x == box["x_dealer"][i * eb:(i + 1) * eb], "CPU baseline X_i != GPU X_i"
+        dt_h = cpu_reference_step(box, sample, cores, schedule=1)[0]
         line["cpu_baseline"] = {
-            "value": len(sample) / dt, "unit": "shares/s", "cores": cores, "kind": "port",
+            "value": len(sample) / dt, "unit": "shares/s", "cores": cores, "per_core": len(sample) / dt / cores,
+            "kind": "port",
             "sample": f"{len(sample)} participants (positions spread over 1..{n_total}), full t={t}, reference "
-                      "schedule (t+4 full exponentiations per share) on " + CPU_PROXY[args.group] +
-                      ", one participant per thread",
+                      "schedule (t+4 full exponentiations per share) + framed SHA-256 of their rows, on " +
+                      CPU_PROXY[args.group] + ", one participant per thread",
             "same_algorithm_value": len(sample) / dt_h,
             "same_algorithm_note": "CPU running the GPU's Horner schedule (baseline B, BASELINE.md section 3)"}
     if args.group == "modp" and world == 1 and not args.no_also:
@@ -466,11 +589,12 @@ def main():
                                  (["--no-cpu-baseline"] if args.no_cpu_baseline else []),
                                  capture_output=True, text=True, timeout=900)
             sec = json.loads(out.stdout.strip().splitlines()[-1])
-            line["also"] = {"secp256k1": {k: sec.get(k) for k in ("metric", "value", "unit", "ms_per_step",
-                                                                 "kernel_ms_per_step", "e2e", "cpu_baseline",
-                                                                 "phase_ms", "gpu_launches")}}
+            also["secp256k1"] = {k: sec.get(k) for k in ("metric", "value", "unit", "ms_per_step", "kernel_ms_per_step",
+                                                        "e2e", "roofline", "cpu_baseline", "phase_ms", "gpu_launches")}
         except Exception as ex:  # the primary line stands on its own
-            line["also"] = {"secp256k1": {"error": str(ex)[:200]}}
+            also["secp256k1"] = {"error": str(ex)[:200]}
+    if also:
+        line["also"] = also
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

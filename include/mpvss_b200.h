@@ -18,8 +18,19 @@
  *
  * Every function returns MPVSS_OK (0) or a negative status; mpvss_last_error()
  * gives the text.  Nothing panics or throws across the boundary.  A context may
- * be used from any thread, one call at a time (calls are serialised internally).
+ * be used from any thread, one call at a time: every entry point holds the
+ * context's lock for its whole duration (the fused calls for all their steps).  The
+ * two-step pair mpvss_verify_distribution_stage / _run shares staged state between
+ * two calls and must be serialised by the caller as a pair.
  * There is no CPU fallback: without a CUDA device mpvss_ctx_create fails.
+ *
+ * Multi-GPU: one context per GPU (one process or thread each), joined by
+ * mpvss_comm_init.  Participants are independent, so the fused phase calls
+ * (mpvss_verify_distribution, mpvss_distribute) shard them inside the call --
+ * rank r takes participants r, r + N, ... -- and exchange the results with one
+ * NCCL all-gather per phase on the library's stream.  Such
+ * calls are collective: every rank makes the same call with the same arguments
+ * and every rank receives the full result.
  */
 #ifndef MPVSS_B200_H
 #define MPVSS_B200_H
@@ -45,7 +56,8 @@ enum mpvss_status {
   MPVSS_ERR_ARG = -2,         /* null pointer, zero count, threshold > n, ... */
   MPVSS_ERR_ENCODING = -3,    /* invalid element / scalar encoding (reference: None / false) */
   MPVSS_ERR_UNSUPPORTED = -4, /* operation not available for this group */
-  MPVSS_ERR_NOT_INVERTIBLE = -5 /* scalar without inverse (reference: extract_secret_share -> None) */
+  MPVSS_ERR_NOT_INVERTIBLE = -5, /* scalar without inverse (reference: extract_secret_share -> None) */
+  MPVSS_ERR_COMM = -6          /* NCCL missing or a collective failed */
 };
 
 enum mpvss_generator {
@@ -57,13 +69,14 @@ enum mpvss_generator {
 int mpvss_ctx_create(int group, int device, mpvss_ctx** out);
 void mpvss_ctx_destroy(mpvss_ctx* ctx);
 const char* mpvss_last_error(const mpvss_ctx* ctx);
-/* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16); "modp_dual" (0/1: evaluate the
- * commitment polynomial as two half-length chunks: 1 side by side on every lane group, 2 as two
- * concurrent launches); "modp_comb" (0/1: fixed-base tables for the two generators); "modp_overlap"
- * (where the X-independent a2 = y^r Y^c runs during verify_distribution: 0 before the X_i launch,
- * 2 beside it on a side stream, 3 (default) beside it as one persistent one-warp CTA per SM, which
- * takes the warp slot the X_i launch leaves idle); "ec_threads" (thread target of the chunked
- * elliptic-curve Horner launch) */
+/* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16); "modp_comb" (0/1: fixed-base tables for
+ * the two generators); "modp_overlap" (where the X-independent a2 = y^r Y^c runs during
+ * verify_distribution: 0 before the X_i launch, 2 beside it on a side stream, 3 (default) beside it as
+ * one persistent one-warp CTA per SM, which takes the warp slot the X_i launch leaves idle);
+ * "ec_threads" (thread target of the chunked elliptic-curve Horner launch); "validate" (0/1, default 0:
+ * ModpGroup elements entering verify_distribution / verify_shares are checked for range 0 < x < q and
+ * subgroup membership x^g = 1 -- the reference's bytes_to_element accepts anything, modp.rs:154-156;
+ * a box that fails verifies as false) */
 int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value);
 size_t mpvss_element_bytes(const mpvss_ctx* ctx);
 size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);
@@ -71,6 +84,10 @@ size_t mpvss_scalar_bytes(const mpvss_ctx* ctx);
  * and the number of kernel launches it made */
 float mpvss_last_kernel_ms(const mpvss_ctx* ctx);
 int mpvss_last_kernel_launches(const mpvss_ctx* ctx);
+/* modular squarings (which = 0) and multiplications (which = 1) executed by the last X_i launch of a
+ * ModpGroup context (summed over this rank's participants): the algorithmic work behind the roofline
+ * figure bench.py reports.  EC contexts: field squarings / multiplications of the last Horner launch. */
+uint64_t mpvss_last_horner_products(const mpvss_ctx* ctx, int which);
 /* kernel time (ms) of one phase of the last fused call.  verify_distribution: phase 0 = X_i
  * (Montgomery conversion + Horner multi-exponentiation [+ chunk combination]; a2 runs underneath on
  * a side stream), phase 1 = remaining DLEQ commitments, phase 2 = the Horner launch alone (MODP). */
@@ -90,6 +107,11 @@ int mpvss_batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n
  * 1-based positions (NULL = 1..n). */
 int mpvss_poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
                         uint8_t* out);
+/* Polynomial::get_value reduced as its callers do (polynomial.rs:50-58; participant.rs:202, 1155-1157,
+ * 1619-1621): out[i] = sum_j coeffs[j] * positions[i]^j mod order, order = q-1 / n / l.
+ * positions NULL = 1..n. */
+int mpvss_scalar_poly_eval(mpvss_ctx* ctx, const uint8_t* coeffs, size_t t, const int64_t* positions, size_t n,
+                           uint8_t* out);
 /* Verifier::commitments (dleq.rs:66-84): a1[i] = g1^r[i] * h1[i]^c[i], a2[i] = g2[i]^r[i] * h2[i]^c[i].
  * g1 is one element (a generator); c_stride = 0 means one shared challenge. */
 int mpvss_dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2,
@@ -111,21 +133,13 @@ int mpvss_verify_distribution(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t*
                               const uint8_t* responses, const uint8_t* challenge, int* ok, uint8_t* x_out,
                               uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out);
 /* Two-step form for callers that keep the box resident on the device (used by bench.py to
- * time the path without the host->device copies): stage copies the inputs, run verifies. */
+ * time the path without the host->device copies): stage copies the inputs, run verifies.  With a
+ * communicator both are collective like mpvss_verify_distribution; x/a1/a2 outputs must then be NULL. */
 int mpvss_verify_distribution_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
                                     const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,
                                     const uint8_t* responses, const uint8_t* challenge);
 int mpvss_verify_distribution_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out,
                                   uint8_t* digest_out);
-
-/* Sharded form (one process per GPU, each holding a contiguous slice of the participants):
- * compute runs the kernels for the staged slice and copies X, a1, a2 (n elements each) to the
- * caller's DEVICE buffers (e.g. torch tensors that are then all-gathered with NCCL);
- * transcript_check hashes the gathered HOST rows in index order and compares the challenge
- * (participant.rs:438-454).  Together they equal mpvss_verify_distribution_run. */
-int mpvss_verify_distribution_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev);
-int mpvss_transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
-                           const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out);
 
 /* Participant::distribute_secret (participant.rs:160-286 / 1094-1274 / 1573-1717) with the
  * randomness injected: `coeffs` (t scalars) replaces Polynomial::init (polynomial.rs:34-47),
@@ -155,6 +169,24 @@ int mpvss_verify_shares(mpvss_ctx* ctx, size_t n, const uint8_t* publickeys, con
  * left-padded).  gs_out (optional) receives G^s. */
 int mpvss_reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_t* shares, const uint8_t* u,
                       uint8_t* secret_out, uint8_t* gs_out);
+
+/* ---- multi-GPU --------------------------------------------------------------------- */
+/* One context per GPU.  Rank 0 obtains an id (ncclGetUniqueId), the caller distributes its
+ * MPVSS_COMM_ID_BYTES bytes to the other ranks by any means, then every rank calls mpvss_comm_init
+ * (ncclCommInitRank on the context's device).  Afterwards mpvss_verify_distribution[_stage/_run] and
+ * mpvss_distribute on these contexts are collective calls that shard the participants round robin and
+ * all-gather the transcript rows over NVLink.  libnccl.so.2 is loaded on first use. */
+#define MPVSS_COMM_ID_BYTES 128
+int mpvss_comm_unique_id(uint8_t* id_out, size_t id_len);
+int mpvss_comm_init(mpvss_ctx* ctx, const uint8_t* id, size_t id_len, int nranks, int rank);
+int mpvss_comm_destroy(mpvss_ctx* ctx);
+int mpvss_comm_size(const mpvss_ctx* ctx);
+int mpvss_comm_rank(const mpvss_ctx* ctx);
+/* Host-only half of the sharded transcript, exposed for tests of the gather layout: SHA-256 over the
+ * framed rows of n_total participants laid out [rank][ceil(n_total / nranks)][4 frames of 8 + element
+ * bytes] as the all-gather delivers them, in participant order (participant i = rank i % nranks, row
+ * i / nranks).  Needs no device. */
+int mpvss_transcript_digest(int group, const uint8_t* gathered_rows, size_t n_total, int nranks, uint8_t* digest_out);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 // extern "C" surface of libmpvss_b200.so (declared in include/mpvss_b200.h): context
 // management, error reporting and dispatch to the per-group implementations.
 #include "ctx.h"
+#include "transcript.h"
 
 int mpvss_fail(mpvss_ctx* ctx, int status, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -84,6 +85,8 @@ int mpvss_ctx_create(int group, int device, mpvss_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming) != cudaSuccess)
       return bail(MPVSS_ERR_CUDA);
+  for (cudaEvent_t& e : ctx->ev_chunk)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(MPVSS_ERR_CUDA);
   int s = MPVSS_OK;
   if (group == MPVSS_GROUP_MODP) s = modp_api::init(ctx);
   if (group == MPVSS_GROUP_SECP256K1) s = secp_api::init(ctx);
@@ -97,7 +100,16 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  comm_release(ctx);
+  // scratch and pinned buffers may have held secrets (private keys, witnesses, coefficients)
+  for (auto& b : ctx->scratch)
+    if (b.p) cudaMemset(b.p, 0, b.cap);
+  for (auto& b : ctx->pinned)
+    if (b.p) memset(b.p, 0, b.cap);
   modp_api::destroy(ctx);
+  ctx->h_frames.release();
+  for (cudaEvent_t e : ctx->ev_chunk)
+    if (e) cudaEventDestroy(e);
   ctx->ec_consts.release();
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
@@ -133,8 +145,8 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->modp_overlap = value;
     return MPVSS_OK;
   }
-  if (std::string(key) == "modp_dual") {
-    ctx->modp_dual = value;  // 0: one chain, 1: two interleaved chains per lane group, 2: two launches
+  if (std::string(key) == "validate") {
+    ctx->validate = value != 0;
     return MPVSS_OK;
   }
   return mpvss_fail(ctx, MPVSS_ERR_ARG, std::string("unknown tunable: ") + key);
@@ -150,6 +162,9 @@ size_t mpvss_scalar_bytes(const mpvss_ctx* ctx) {
 }
 float mpvss_last_kernel_ms(const mpvss_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
 int mpvss_last_kernel_launches(const mpvss_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+uint64_t mpvss_last_horner_products(const mpvss_ctx* ctx, int which) {
+  return !ctx ? 0 : which == 0 ? ctx->horner_sqr : ctx->horner_mul;
+}
 float mpvss_last_phase_ms(const mpvss_ctx* ctx, int phase) {
   return (ctx && phase >= 0 && phase < 4) ? ctx->phase_ms[phase] : 0.f;
 }
@@ -189,20 +204,39 @@ int mpvss_verify_distribution_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8
                                   uint8_t* digest_out) {
   DISPATCH(ctx, verify_run, ok, x_out, a1_out, a2_out, digest_out);
 }
-int mpvss_verify_distribution_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev) {
-  DISPATCH(ctx, verify_compute, x_dev, a1_dev, a2_dev);
-}
-int mpvss_transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
-                           const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out) {
-  DISPATCH(ctx, transcript_check, n, x, y, a1, a2, challenge, ok, digest_out);
+// Box contents that do not decode (bad point, non-canonical scalar, position out of range) make the
+// reference return false (participant.rs:415-420, bytes_to_element -> None), not fail: only caller
+// or CUDA faults are reported as errors.
+static int box_verdict(int status, int* ok) {
+  if (status == MPVSS_ERR_ENCODING && ok) {
+    *ok = 0;
+    return MPVSS_OK;
+  }
+  return status;
 }
 int mpvss_verify_distribution(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments,
                               const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,
                               const uint8_t* responses, const uint8_t* challenge, int* ok, uint8_t* x_out,
                               uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
+  if (!ctx || !ok) return MPVSS_ERR_ARG;
+  Guard hold(ctx);  // one lock across both steps: no other thread can stage a different box in between
   int s = mpvss_verify_distribution_stage(ctx, n, t, commitments, positions, publickeys, shares, responses, challenge);
-  if (s != MPVSS_OK) return s;
-  return mpvss_verify_distribution_run(ctx, ok, x_out, a1_out, a2_out, digest_out);
+  if (s != MPVSS_OK) return box_verdict(s, ok);
+  return box_verdict(mpvss_verify_distribution_run(ctx, ok, x_out, a1_out, a2_out, digest_out), ok);
+}
+int mpvss_scalar_poly_eval(mpvss_ctx* ctx, const uint8_t* coeffs, size_t t, const int64_t* positions, size_t n,
+                           uint8_t* out) {
+  DISPATCH(ctx, scalar_poly_eval, coeffs, t, positions, n, out);
+}
+int mpvss_transcript_digest(int group, const uint8_t* rows, size_t n_total, int nranks, uint8_t* digest_out) {
+  if (!rows || !digest_out || n_total == 0 || nranks < 1 || group < MPVSS_GROUP_MODP || group > MPVSS_GROUP_RISTRETTO255)
+    return MPVSS_ERR_ARG;
+  const transcript::Geom g{group == MPVSS_GROUP_MODP ? (size_t)256 : group == MPVSS_GROUP_SECP256K1 ? (size_t)33 : (size_t)32,
+                           group == MPVSS_GROUP_MODP};
+  sha2::Sha256 h;
+  transcript::hash_range(h, rows, 0, n_total, nranks, transcript::rows_per_rank(n_total, nranks), g);
+  h.finalize(digest_out);
+  return MPVSS_OK;
 }
 int mpvss_distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t secret_len,
                      const uint8_t* coeffs, const uint8_t* witnesses, const uint8_t* publickeys,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <mutex>
+#include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/mpvss_b200.h"
@@ -58,7 +60,7 @@ struct mpvss_ctx {
   cudaStream_t aux[2] = {nullptr, nullptr};  // side streams for concurrent launches
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr, ev_h0 = nullptr, ev_h1 = nullptr, ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   float phase_ms[4] = {0, 0, 0, 0};  // per-phase kernel time of the last fused call
-  std::mutex mu;
+  std::recursive_mutex mu;  // one lock per public call; fused calls re-enter it for their steps
   std::string err;
   float last_ms = 0.f;
   int last_launches = 0;
@@ -68,16 +70,15 @@ struct mpvss_ctx {
   int modp_tpi = 8;
   bool modp_tpi_auto = true;  // Horner launches pick 4 lanes per value when a launch has >= 32768 positions
   int v_tpi = 8;              // lanes per value of the staged Horner plan
-  size_t exp2_filler_smem = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs
+  size_t exp2_filler_ctas = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs
   int modp_overlap = 3;  // a2 = y^r Y^c (independent of X): 0 before the Horner launch on the main stream; 2 regular launch on a
                          // side stream after it; 3 (default) persistent one-warp CTAs, one per SM, on a side stream after it
-  int modp_dual = 0;  // two-chunk Horner: 0 off (default: fastest whole step), 1 two interleaved chains per lane
-                      // group, 2 two concurrent half-polynomial launches (+ one combining exponentiation)
   big::Int q, qm1, g;        // modulus, order q-1, subgroup order g = (q-1)/2
   DevBuf consts_q, consts_g; // modp::C_WORDS words each (Montgomery constants for q and for g)
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4, [128,192) one
   DevBuf comb[2];            // fixed-base tables of the two generators (built on first use, 16.8 MB each)
   int modp_comb = 1;         // use them ("modp_comb")
+  bool validate = false;     // range / subgroup check of ModpGroup elements entering the verify calls
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----
   size_t ec_threads = 131072;   // target thread count of the chunked Horner launch ("ec_threads")
@@ -90,12 +91,20 @@ struct mpvss_ctx {
   size_t v_n = 0, v_t = 0;
   uint32_t v_rwin = 0, v_cwin = 0;
   size_t v_np = 0;  // padded instance count of the Horner launch
-  uint32_t v_nd_max = 1;  // base-4 digits of the largest staged position
+  uint32_t v_nops_max = 1;  // products per Horner step of the longest staged addition chain
   std::vector<uint8_t> v_challenge, v_y_host;
   const uint32_t* v_comb = nullptr;  // fixed-base table of g for a1 = g^r * X^c
-  bool v_dual = false;
-  DevBuf v_e, v_h;  // chunk exponents pos^B mod (q-1); H0/H1 of the two-chunk Horner
-  DevBuf v_slot, v_nd, v_skip, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+  DevBuf v_slot, v_nd, v_ops, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2, v_st;
+  // framed transcript rows (dleq.rs:58-61, 87-99): per participant 4 x (u64 BE length || bytes), written by the
+  // device in the rank's local order; v_gather holds the rows of all ranks after the all-gather
+  DevBuf v_frames, v_gather;
+  PinBuf h_frames;
+  size_t v_n_total = 0;          // participants of the whole box (== v_n without a communicator)
+  uint64_t horner_sqr = 0, horner_mul = 0;  // modular squarings / multiplications of the last X_i launch
+  // ---- multi-GPU (one context per GPU, one process or thread per context) ----
+  void* comm = nullptr;          // ncclComm_t
+  int nranks = 1, rank = 0;
+  cudaEvent_t ev_chunk[16] = {};
 
   // fixed-size pools: references handed out by buf()/pin() stay valid for the whole call
   mpvss_ctx() : scratch(24), pinned(8) {}
@@ -137,9 +146,7 @@ int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
 int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
                  const uint8_t*, const uint8_t*);
 int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
-int verify_compute(mpvss_ctx*, void*, void*, void*);
-int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
-                     int*, uint8_t*);
+int scalar_poly_eval(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
 int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
                uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
 int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,
@@ -161,9 +168,7 @@ int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
 int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
                  const uint8_t*, const uint8_t*);
 int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
-int verify_compute(mpvss_ctx*, void*, void*, void*);
-int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
-                     int*, uint8_t*);
+int scalar_poly_eval(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
 int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
                uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
 int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,
@@ -185,9 +190,7 @@ int multi_exp(mpvss_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);
 int verify_stage(mpvss_ctx*, size_t, size_t, const uint8_t*, const int64_t*, const uint8_t*, const uint8_t*,
                  const uint8_t*, const uint8_t*);
 int verify_run(mpvss_ctx*, int*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
-int verify_compute(mpvss_ctx*, void*, void*, void*);
-int transcript_check(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*,
-                     int*, uint8_t*);
+int scalar_poly_eval(mpvss_ctx*, const uint8_t*, size_t, const int64_t*, size_t, uint8_t*);
 int distribute(mpvss_ctx*, size_t, size_t, const uint8_t*, size_t, const uint8_t*, const uint8_t*, const uint8_t*,
                uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*, uint8_t*);
 int extract_shares(mpvss_ctx*, size_t, const uint8_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*, uint8_t*,

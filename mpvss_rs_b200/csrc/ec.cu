@@ -16,6 +16,7 @@ template <class Cv> __global__ void __launch_bounds__(TPB) decode_kernel(DecodeA
 template <class Cv> __global__ void __launch_bounds__(TPB, EC_HORNER_MIN_BLOCKS) horner_kernel(HornerArgs<Cv> A) { horner_body<Cv>(A, TID); }
 template <class Cv> __global__ void __launch_bounds__(TPB) sum_kernel(SumArgs<Cv> A) { sum_body<Cv>(A, TID); }
 template <class Cv> __global__ void __launch_bounds__(TPB) add_kernel(AddArgs<Cv> A) { add_body<Cv>(A, TID); }
+__global__ void __launch_bounds__(TPB) frame_kernel(FrameArgs A) { frame_body(A, TID); }
 __global__ void __launch_bounds__(TPB) poly_kernel(PolyArgs A) { poly_body(A, TID); }
 __global__ void __launch_bounds__(TPB) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, TID); }
 __global__ void __launch_bounds__(TPB) inv_kernel(InvArgs A) { inv_body(A, TID); }
@@ -43,6 +44,11 @@ template <class Cv> cudaError_t launch_sum(const SumArgs<Cv>& A, cudaStream_t s)
 template <class Cv> cudaError_t launch_add(const AddArgs<Cv>& A, cudaStream_t s) {
   if (A.n == 0) return cudaErrorInvalidValue;
   add_kernel<Cv><<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_frames(const FrameArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  frame_kernel<<<blocks(A.n * 4), TPB, 0, s>>>(A);
   return cudaGetLastError();
 }
 cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s) {

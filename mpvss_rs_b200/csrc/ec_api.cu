@@ -12,6 +12,7 @@
 #include "ctx.h"
 #include "ec_launch.h"
 #include "sha2.h"
+#include "transcript.h"
 
 namespace {
 
@@ -380,34 +381,70 @@ struct Ec {
   }
 
   // ---- verify_distribution_shares --------------------------------------------------------------
-  static int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments, const int64_t* positions,
-                          const uint8_t* publickeys, const uint8_t* shares, const uint8_t* responses,
-                          const uint8_t* challenge) {
-    MPVSS_TRY(bad(ctx, n > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
+  static transcript::Geom geom() { return transcript::Geom{EB, false}; }
+  static const uint8_t* slice_rows(const mpvss_ctx* ctx, const uint8_t* all, size_t n_total, size_t width,
+                                   std::vector<uint8_t>& tmp) {
+    if (ctx->nranks <= 1) return all;
+    tmp.clear();
+    for (size_t i = (size_t)ctx->rank; i < n_total; i += (size_t)ctx->nranks)
+      tmp.insert(tmp.end(), all + i * width, all + (i + 1) * width);
+    return tmp.data();
+  }
+  static int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commitments,
+                          const int64_t* positions, const uint8_t* publickeys, const uint8_t* shares,
+                          const uint8_t* responses, const uint8_t* challenge) {
+    ctx->v_n_total = 0;
+    MPVSS_TRY(bad(ctx, n_total > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
                   "verify_distribution: bad arguments"));
-    std::vector<uint32_t> pos, rl, cl;
-    MPVSS_TRY(positions_u32(ctx, positions, n, pos));
-    MPVSS_TRY(scalars_in(ctx, responses, n, rl));
+    // every rank checks ALL positions and scalars, so that a malformed box is rejected by all ranks alike
+    std::vector<uint32_t> pos_all, rl_all, cl;
+    MPVSS_TRY(positions_u32(ctx, positions, n_total, pos_all));
+    MPVSS_TRY(scalars_in(ctx, responses, n_total, rl_all));
     MPVSS_TRY(scalars_in(ctx, challenge, 1, cl));
+    const size_t n = transcript::local_count(n_total, ctx->nranks, ctx->rank), N = (size_t)ctx->nranks;
+    std::vector<uint32_t> pos(n), rl(n * 8);
+    for (size_t j = 0; j < n; ++j) {
+      const size_t i = (size_t)ctx->rank + j * N;
+      pos[j] = pos_all[i];
+      memcpy(&rl[j * 8], &rl_all[i * 8], 32);
+    }
+    std::vector<uint8_t> tpk, ty;
+    const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
+    const uint8_t* y = slice_rows(ctx, shares, n_total, EB, ty);
     MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
-    MPVSS_TRY(h2d(ctx, ctx->v_pos, pos.data(), n * 4));
-    MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
-    MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
-    MPVSS_TRY(h2d(ctx, ctx->v_r, rl.data(), n * 32));
     MPVSS_TRY(h2d(ctx, ctx->v_c, cl.data(), 32));
-    for (DevBuf* b : {&ctx->v_x, &ctx->v_a1, &ctx->v_a2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
-    MPVSS_CUDA(ctx, ctx->v_slot.ensure(2 * n * 4));  // status of the two DLEQ launches
+    if (n) {
+      MPVSS_TRY(h2d(ctx, ctx->v_pos, pos.data(), n * 4));
+      MPVSS_TRY(h2d(ctx, ctx->v_pk, pk, n * EB));
+      MPVSS_TRY(h2d(ctx, ctx->v_y, y, n * EB));
+      MPVSS_TRY(h2d(ctx, ctx->v_r, rl.data(), n * 32));
+      for (DevBuf* b : {&ctx->v_x, &ctx->v_a1, &ctx->v_a2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
+      MPVSS_CUDA(ctx, ctx->v_st.ensure(2 * n * 4));  // status of the two DLEQ launches
+    }
+    const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks), row = geom().row();
+    MPVSS_CUDA(ctx, ctx->v_frames.ensure(rpr * row));
+    MPVSS_CUDA(ctx, cudaMemsetAsync(ctx->v_frames.p, 0, rpr * row, ctx->stream));
+    if (ctx->nranks > 1) MPVSS_CUDA(ctx, ctx->v_gather.ensure(N * rpr * row));
     ctx->v_challenge.assign(challenge, challenge + SB);
-    ctx->v_y_host.assign(shares, shares + n * EB);
     ctx->v_n = n;
     ctx->v_t = t;
-    return sync(ctx);
+    MPVSS_TRY(sync(ctx));
+    ctx->v_n_total = n_total;
+    return MPVSS_OK;
   }
-  static int verify_kernels(mpvss_ctx* ctx) {
+  // X (chunked Horner), a1 = r*g + c*X, a2 = r*y + c*Y, framed rows.  *decoded = false if an element of the
+  // box is not a valid encoding (the rows are then marked instead of failing: the all-gather must still run)
+  static int verify_kernels(mpvss_ctx* ctx, bool* decoded) {
     const size_t n = ctx->v_n, t = ctx->v_t;
-    uint8_t* X = ctx->v_x.as<uint8_t>();
-    uint32_t* st = ctx->v_slot.as<uint32_t>();
+    *decoded = true;
     timing_begin(ctx);
+    if (n == 0) {
+      MPVSS_TRY(timing_end(ctx));
+      ctx->phase_ms[0] = ctx->phase_ms[1] = 0.f;
+      return MPVSS_OK;
+    }
+    uint8_t* X = ctx->v_x.as<uint8_t>();
+    uint32_t* st = ctx->v_st.as<uint32_t>();
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint8_t>(), t, ctx->v_pos.as<uint32_t>(), n, ctx->v_cm, ctx->v_nd,
                          ctx->buf(12), X));
@@ -422,12 +459,23 @@ struct Ec {
     MPVSS_TRY(dev_exp2(ctx, ctx->gens.as<uint8_t>(), 0, ctx->v_r.as<uint32_t>(), X, EB, ctx->v_c.as<uint32_t>(), 0, n,
                        ctx->v_a1.as<uint8_t>(), nullptr, st));
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+    ec::FrameArgs FA{X, ctx->v_y.as<uint8_t>(), ctx->v_a1.as<uint8_t>(), ctx->v_a2.as<uint8_t>(),
+                     ctx->v_frames.as<uint8_t>(), (uint32_t)n, (uint32_t)EB};
+    MPVSS_CUDA(ctx, ec::launch_frames(FA, ctx->stream));
+    timing_launch(ctx);
     MPVSS_TRY(timing_end(ctx));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));
-    MPVSS_TRY(check_status(ctx, ctx->v_nd, t, "verify_distribution (commitments)"));
-    MPVSS_TRY(check_status(ctx, ctx->v_slot, 2 * n, "verify_distribution (public keys / shares)"));
-    return MPVSS_OK;
+    int s1 = check_status(ctx, ctx->v_nd, t, "verify_distribution (commitments)");
+    int s2 = s1 == MPVSS_OK ? check_status(ctx, ctx->v_st, 2 * n, "verify_distribution (public keys / shares)") : s1;
+    if (s2 == MPVSS_ERR_ENCODING) {
+      *decoded = false;
+      const uint8_t mark = 0xff;
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->v_frames.p, &mark, 1, cudaMemcpyHostToDevice, ctx->stream));
+      MPVSS_TRY(sync(ctx));
+      return MPVSS_OK;
+    }
+    return s2;
   }
   static void framed(sha2::Sha256& h, const uint8_t* e) {  // dleq.rs:58-61
     uint8_t len8[8] = {0, 0, 0, 0, 0, 0, 0, (uint8_t)EB};
@@ -440,46 +488,58 @@ struct Ec {
     if (digest_out) memcpy(digest_out, digest, 32);
     return T::hash_to_scalar(digest, 32, ctx->ec_order);  // the digest is hashed again (participant.rs:1217-1218)
   }
-  static int transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
-                              const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out) {
-    MPVSS_TRY(bad(ctx, n > 0 && x && y && a1 && a2 && challenge && ok, "transcript_check: bad arguments"));
-    sha2::Sha256 h;
-    for (size_t i = 0; i < n; ++i) {
-      framed(h, x + i * EB);
-      framed(h, y + i * EB);
-      framed(h, a1 + i * EB);
-      framed(h, a2 + i * EB);
-    }
-    big::Int c = challenge_of(ctx, h, digest_out);
-    *ok = big::cmp(c, scalar_big(challenge)) == 0;
-    return MPVSS_OK;
-  }
-  static int verify_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev) {
-    MPVSS_TRY(bad(ctx, x_dev && a1_dev && a2_dev && ctx->v_n > 0, "verify_distribution_compute: nothing staged"));
-    MPVSS_TRY(verify_kernels(ctx));
-    const size_t bytes = ctx->v_n * EB;
-    MPVSS_CUDA(ctx, cudaMemcpyAsync(x_dev, ctx->v_x.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    MPVSS_CUDA(ctx, cudaMemcpyAsync(a1_dev, ctx->v_a1.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    MPVSS_CUDA(ctx, cudaMemcpyAsync(a2_dev, ctx->v_a2.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    return sync(ctx);
-  }
   static int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out,
                         uint8_t* digest_out) {
-    MPVSS_TRY(bad(ctx, ok && ctx->v_n > 0, "verify_distribution_run: nothing staged"));
-    const size_t n = ctx->v_n;
-    MPVSS_TRY(verify_kernels(ctx));
-    PinBuf &hx = ctx->pin(0), &ha1 = ctx->pin(1), &ha2 = ctx->pin(2);
-    for (PinBuf* b : {&hx, &ha1, &ha2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
-    MPVSS_TRY(d2h(ctx, hx.p, ctx->v_x, n * EB));
-    MPVSS_TRY(d2h(ctx, ha1.p, ctx->v_a1, n * EB));
-    MPVSS_TRY(d2h(ctx, ha2.p, ctx->v_a2, n * EB));
+    MPVSS_TRY(bad(ctx, ok && ctx->v_n_total > 0, "verify_distribution_run: nothing staged"));
+    MPVSS_TRY(bad(ctx, ctx->nranks <= 1 || (!x_out && !a1_out && !a2_out),
+                  "verify_distribution: x/a1/a2 outputs are not available with a communicator"));
+    const size_t n = ctx->v_n, n_total = ctx->v_n_total;
+    bool decoded = true;
+    MPVSS_TRY(verify_kernels(ctx, &decoded));
+    const transcript::Geom g = geom();
+    const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks);
+    const uint8_t* rows = ctx->v_frames.as<uint8_t>();
+    if (ctx->nranks > 1) {
+      MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * g.row()));
+      rows = ctx->v_gather.as<uint8_t>();
+    }
+    sha2::Sha256 h;
+    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h));
+    big::Int c = challenge_of(ctx, h, digest_out);
+    *ok = big::cmp(c, scalar_big(ctx->v_challenge.data())) == 0;
+    for (int r = 0; r < ctx->nranks; ++r)  // a rank whose slice did not decode marked its first row
+      if (ctx->h_frames.as<uint8_t>()[(size_t)r * rpr * g.row()] == 0xff) *ok = 0;
+    if (!decoded) *ok = 0;
+    if (x_out) MPVSS_TRY(d2h(ctx, x_out, ctx->v_x, n * EB));
+    if (a1_out) MPVSS_TRY(d2h(ctx, a1_out, ctx->v_a1, n * EB));
+    if (a2_out) MPVSS_TRY(d2h(ctx, a2_out, ctx->v_a2, n * EB));
+    return sync(ctx);
+  }
+
+  static int scalar_poly_eval(mpvss_ctx* ctx, const uint8_t* coeffs, size_t t, const int64_t* positions, size_t n,
+                              uint8_t* out) {
+    MPVSS_TRY(bad(ctx, coeffs && out && n > 0 && t > 0, "scalar_poly_eval: bad arguments"));
+    std::vector<uint32_t> co, pos, p(n * 8);
+    MPVSS_TRY(scalars_in(ctx, coeffs, t, co));
+    MPVSS_TRY(positions_u32(ctx, positions, n, pos));
+    DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dpos = ctx->buf(9);
+    MPVSS_TRY(h2d(ctx, dco, co.data(), t * 32));
+    MPVSS_TRY(h2d(ctx, dpos, pos.data(), n * 4));
+    MPVSS_CUDA(ctx, dp.ensure(n * 32));
+    timing_begin(ctx);
+    ec::PolyArgs PA{KN(ctx), dco.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t, (uint32_t)n};
+    MPVSS_CUDA(ctx, ec::launch_poly(PA, ctx->stream));
+    timing_launch(ctx);
+    MPVSS_TRY(timing_end(ctx));
+    MPVSS_TRY(d2h(ctx, p.data(), dp, n * 32));
     MPVSS_TRY(sync(ctx));
-    MPVSS_TRY(transcript_check(ctx, n, hx.as<uint8_t>(), ctx->v_y_host.data(), ha1.as<uint8_t>(), ha2.as<uint8_t>(),
-                               ctx->v_challenge.data(), ok, digest_out));
-    if (x_out) memcpy(x_out, hx.p, n * EB);
-    if (a1_out) memcpy(a1_out, ha1.p, n * EB);
-    if (a2_out) memcpy(a2_out, ha2.p, n * EB);
-    return MPVSS_OK;
+    for (size_t i = 0; i < n; ++i) {
+      big::Int v(p.begin() + i * 8, p.begin() + i * 8 + 8);
+      big::trim(v);
+      scalar_out(v, out + i * SB);
+    }
+    MPVSS_CUDA(ctx, cudaMemsetAsync(dco.p, 0, dco.cap, ctx->stream));  // coefficients are secret
+    return sync(ctx);
   }
 
   // ---- distribute_secret -------------------------------------------------------------------------
@@ -690,10 +750,8 @@ struct Ec {
   int verify_run(mpvss_ctx* c, int* ok, uint8_t* x, uint8_t* a1, uint8_t* a2, uint8_t* d) {                          \
     return Ec<Traits>::verify_run(c, ok, x, a1, a2, d);                                                              \
   }                                                                                                                  \
-  int verify_compute(mpvss_ctx* c, void* x, void* a1, void* a2) { return Ec<Traits>::verify_compute(c, x, a1, a2); } \
-  int transcript_check(mpvss_ctx* c, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,                \
-                       const uint8_t* a2, const uint8_t* ch, int* ok, uint8_t* d) {                                  \
-    return Ec<Traits>::transcript_check(c, n, x, y, a1, a2, ch, ok, d);                                              \
+  int scalar_poly_eval(mpvss_ctx* c, const uint8_t* co, size_t t, const int64_t* p, size_t n, uint8_t* o) {        \
+    return Ec<Traits>::scalar_poly_eval(c, co, t, p, n, o);                                                          \
   }                                                                                                                  \
   int distribute(mpvss_ctx* c, size_t n, size_t t, const uint8_t* s, size_t sl, const uint8_t* co, const uint8_t* w, \
                  const uint8_t* pk, uint8_t* cm, uint8_t* sh, uint8_t* ch, uint8_t* r, uint8_t* u, uint8_t* x) {     \

@@ -231,6 +231,27 @@ MP_DEV void add_body(const AddArgs<Cv>& A, uint32_t tid) {
   Cv::encode(A.out + (size_t)tid * Cv::EB, r, C);
 }
 
+// ------------------------------------------------------- transcript frames ----
+// Row j of the Fiat-Shamir transcript (dleq.rs:58-61, 87-99): F(X_j) F(Y_j) F(a1_j) F(a2_j) with
+// F(e) = len_u64_be || encoding; the curves' encodings have fixed length eb (33 / 32), so a row is
+// 4 * (8 + eb) bytes.  One thread per frame.  `bad` marks a row set whose inputs did not decode: the
+// first byte of the rank's first row becomes 0xff (never part of a valid length), which every rank sees
+// after the all-gather.
+struct FrameArgs {
+  const uint8_t *x, *y, *a1, *a2;  // n encodings each
+  uint8_t* out;
+  uint32_t n, eb;
+};
+MP_DEV void frame_body(const FrameArgs& A, uint32_t tid) {
+  const uint32_t j = tid >> 2, e = tid & 3u;
+  if (j >= A.n) return;
+  const uint8_t* src = (e == 0 ? A.x : e == 1 ? A.y : e == 2 ? A.a1 : A.a2) + (size_t)j * A.eb;
+  uint8_t* dst = A.out + ((size_t)j * 4 + e) * (8 + A.eb);
+  for (int k = 0; k < 7; ++k) dst[k] = 0;
+  dst[7] = (uint8_t)A.eb;
+  for (uint32_t k = 0; k < A.eb; ++k) dst[8 + k] = src[k];
+}
+
 // ---------------------------------------------------------- scalar kernels ----
 // p_i = P(pos_i) mod n by Horner in the scalar field (coefficients: 8 LE limbs, < n)
 struct PolyArgs {

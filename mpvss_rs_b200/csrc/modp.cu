@@ -11,15 +11,7 @@ __global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner_kernel(Horne
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
   horner_body<TPI, NP1>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>,
-                   A.nd ? A.nd[blockIdx.x] : A.ndigits, A.skip ? A.skip[blockIdx.x] : 0u);
-}
-
-template <int TPI>
-__global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner2_kernel(Horner2Args A) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t w = threadIdx.x >> 5;
-  horner2_body<TPI>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner2_smem_words<TPI>, A.nd[blockIdx.x],
-                    A.skip ? A.skip[blockIdx.x] : 0u);
+                        A.nops ? A.nops[blockIdx.x] : A.nops_all);
 }
 
 template <int TPI>
@@ -59,6 +51,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) mul_kernel(MulArgs A) {
   mul_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * mul_smem_words<TPI>);
 }
 
+__global__ void __launch_bounds__(128) frame_kernel(FrameArgs A) { frame_body(A, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(64) resp_kernel(RespArgs A) { resp_body(A, blockIdx.x * 64 + threadIdx.x); }
 __global__ void __launch_bounds__(64) poly_kernel(PolyArgs A) { poly_body(A, blockIdx.x * 64 + threadIdx.x); }
 __global__ void __launch_bounds__(64) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, blockIdx.x * 64 + threadIdx.x); }
 
@@ -106,18 +100,6 @@ cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStre
   return cudaGetLastError();
 }
 
-cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s) {
-  if (A.n == 0 || A.t < 4 || A.B < 2) return cudaErrorInvalidValue;
-  MODP_DISPATCH(tpi, {
-    size_t sm = HORNER_WARPS_PER_CTA * horner2_smem_words<T> * 4;
-    cudaError_t e = set_smem(horner2_kernel<T>, sm);
-    if (e != cudaSuccess) return e;
-    uint32_t per_cta = HORNER_WARPS_PER_CTA * (32 / T);
-    horner2_kernel<T><<<(A.n + per_cta - 1) / per_cta, HORNER_WARPS_PER_CTA * 32, sm, s>>>(A);
-  });
-  return cudaGetLastError();
-}
-
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
   if (A.n == 0 || A.e1_windows == 0 || (A.b2 && A.e2_windows == 0)) return cudaErrorInvalidValue;
   MODP_DISPATCH(tpi, {
@@ -129,16 +111,28 @@ cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t smem_bytes, cudaStream_t s) {
+cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t ctas, cudaStream_t s) {
   if (A.n == 0 || A.e1_windows == 0 || (A.b2 && A.e2_windows == 0)) return cudaErrorInvalidValue;
   MODP_DISPATCH(tpi, {
     size_t sm = exp2_smem_words<T> * 4;
     cudaError_t e = set_smem(exp2_filler_kernel<T>, sm);
     if (e != cudaSuccess) return e;
     uint32_t per_cta = 32 / T, nwarps = (A.n + per_cta - 1) / per_cta;
-    uint32_t grid = (uint32_t)smem_bytes;  // number of persistent CTAs (one per SM)
+    uint32_t grid = (uint32_t)ctas;  // number of persistent CTAs (one per SM)
     exp2_filler_kernel<T><<<grid < nwarps ? grid : nwarps, 32, sm, s>>>(A, nwarps);
   });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_frames(const FrameArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  frame_kernel<<<(A.n * 4 + 127) / 128, 128, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resp(const RespArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  resp_kernel<<<(A.n + 63) / 64, 64, 0, s>>>(A);
   return cudaGetLastError();
 }
 

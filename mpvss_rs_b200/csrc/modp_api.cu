@@ -11,8 +11,10 @@
 //   Lagrange exponents            participant.rs:526-561, util.rs:47-64
 #include <algorithm>
 #include "ctx.h"
+#include "modp_chain.h"
 #include "modp_launch.h"
 #include "sha2.h"
+#include "transcript.h"
 
 namespace {
 
@@ -118,8 +120,8 @@ int dev_exp2(mpvss_ctx* ctx, const uint32_t* consts, const uint32_t* b1, uint32_
              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s,
              uint32_t e2w, size_t n, uint32_t* out, cudaStream_t stream = nullptr, const uint32_t* comb1 = nullptr) {
   modp::Exp2Args A{consts, b1, e1, b2, e2, out, (uint32_t)n, b1s, e1s, e1w, b2s, e2s, e2w, comb1};
-  if (ctx->exp2_filler_smem)
-    MPVSS_CUDA(ctx, modp::launch_exp2_filler(ctx->modp_tpi, A, ctx->exp2_filler_smem, stream ? stream : ctx->stream));
+  if (ctx->exp2_filler_ctas)
+    MPVSS_CUDA(ctx, modp::launch_exp2_filler(ctx->modp_tpi, A, ctx->exp2_filler_ctas, stream ? stream : ctx->stream));
   else
     MPVSS_CUDA(ctx, modp::launch_exp2(ctx->modp_tpi, A, stream ? stream : ctx->stream));
   timing_launch(ctx);
@@ -177,7 +179,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->comb[0], &ctx->comb[1], &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_e, &ctx->v_h, &ctx->v_skip})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_st})
     b->release();
 }
 
@@ -241,53 +243,66 @@ static int horner_tpi(const mpvss_ctx* ctx, size_t n) {
 
 struct PosPlan {
   int tpi = 8;
-  std::vector<uint32_t> pos, slot;  // padded instance arrays; slot 0xffffffff = padding
-  std::vector<uint32_t> nd;         // base-4 digits per CTA
-  std::vector<uint32_t> skip;       // per CTA: bit s = digit s is zero for every instance of the CTA
+  std::vector<uint32_t> slot;   // padded instance array: output row of the instance, 0xffffffff = padding
+  std::vector<uint16_t> ops;    // HC_OPS ops per instance: one Horner step (modp_chain.h)
+  std::vector<uint32_t> nops;   // ops per step, per CTA
+  uint64_t sqr = 0, mul = 0;    // products per Horner step summed over the live instances (roofline accounting)
+  uint32_t nops_max = 1;
 };
+static modp_chain::PowerTree g_tree;  // shared by all contexts; grown under g_tree_mu
+static std::mutex g_tree_mu;
+
+// Positions are sorted by the length of their op list (longest first) and every length class is padded to
+// a whole number of CTAs, so all lane groups of a CTA run the same number of products per step while
+// one launch covers every class; shorter lists inside a class do not occur, padding instances repeat
+// the last live one.
 static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
-  std::vector<std::vector<uint32_t>> by(17);
+  static_assert(modp_chain::SLOTS == modp::HC_SLOTS && modp_chain::OPS_MAX == modp::HC_OPS, "kernel / host op format");
+  uint32_t maxp = 1;
   for (size_t i = 0; i < n; ++i) {
     int64_t p = positions ? positions[i] : (int64_t)i + 1;
     if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
-    by[ndigits_for((uint64_t)p)].push_back((uint32_t)i);
+    maxp = std::max<uint32_t>(maxp, (uint32_t)p);
+  }
+  std::lock_guard<std::mutex> lk(g_tree_mu);
+  g_tree.build(std::min<uint32_t>(maxp, modp_chain::TREE_LIMIT));
+  std::vector<std::vector<uint16_t>> ops(n);
+  std::vector<std::vector<uint32_t>> by(modp_chain::OPS_MAX + 1);
+  plan.sqr = plan.mul = 0;
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t sq, ml;
+    if (!modp_chain::step_ops((uint32_t)(positions ? positions[i] : (int64_t)i + 1), g_tree, ops[i], &sq, &ml))
+      return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, "no addition chain within the kernel's slot budget");
+    plan.sqr += sq;
+    plan.mul += ml;
+    by[ops[i].size()].push_back((uint32_t)i);
   }
   plan.tpi = horner_tpi(ctx, n);
   const size_t per_cta = modp::HORNER_WARPS_PER_CTA * (32 / plan.tpi);
-  plan.pos.clear(); plan.slot.clear(); plan.nd.clear();
-  for (uint32_t d = 16; d >= 1; --d) {
-    if (by[d].empty()) continue;
-    for (uint32_t i : by[d]) {
-      plan.slot.push_back(i);
-      plan.pos.push_back((uint32_t)(positions ? positions[i] : (int64_t)i + 1));
-    }
-    while (plan.pos.size() % per_cta) {
-      plan.slot.push_back(0xffffffffu);
-      plan.pos.push_back(plan.pos.back());
-    }
-    plan.nd.resize(plan.pos.size() / per_cta, d);
-  }
-  // consecutive positions share their high digits, so a whole CTA (one warp) often has a zero digit
-  // in common; those window multiplications (by one) are skipped block-uniformly
-  plan.skip.assign(plan.nd.size(), 0);
-  for (size_t c = 0; c < plan.nd.size(); ++c) {
-    uint32_t mask = 0;
-    for (uint32_t s = 0; s + 1 < plan.nd[c]; ++s) {   // never the top digit (it seeds the accumulator)
-      bool all_zero = true;
-      for (size_t k = 0; k < per_cta; ++k) all_zero = all_zero && ((plan.pos[c * per_cta + k] >> (2 * s)) & 3u) == 0;
-      if (all_zero) mask |= 1u << s;
-    }
-    plan.skip[c] = mask;
+  plan.slot.clear(); plan.ops.clear(); plan.nops.clear();
+  plan.nops_max = 1;
+  for (uint32_t len = modp_chain::OPS_MAX; len >= 1; --len) {
+    if (by[len].empty()) continue;
+    plan.nops_max = std::max(plan.nops_max, len);
+    auto emit = [&](uint32_t i, uint32_t slot) {
+      plan.slot.push_back(slot);
+      size_t base = plan.ops.size();
+      plan.ops.resize(base + modp_chain::OPS_MAX, (uint16_t)modp_chain::B_ONE);
+      std::copy(ops[i].begin(), ops[i].end(), plan.ops.begin() + base);
+    };
+    for (uint32_t i : by[len]) emit(i, i);
+    while (plan.slot.size() % per_cta) emit(by[len].back(), 0xffffffffu);
+    plan.nops.resize(plan.slot.size() / per_cta, len);
   }
   return MPVSS_OK;
 }
 
 // commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
-static int dev_horner(mpvss_ctx* ctx, int tpi, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
-                      const uint32_t* slot, const uint32_t* nd, const uint32_t* skip, size_t n_padded, uint32_t* x) {
+static int dev_horner(mpvss_ctx* ctx, int tpi, const uint32_t* comm, DevBuf& cm, size_t t, const uint16_t* ops,
+                      const uint32_t* slot, const uint32_t* nops, size_t n_padded, uint32_t* x) {
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), pos, slot, nd, skip, x, (uint32_t)t,
+  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), ops, slot, nops, x, (uint32_t)t,
                      (uint32_t)n_padded, 0};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
   MPVSS_CUDA(ctx, modp::launch_horner(tpi, A, ctx->modp_np1, ctx->stream));
@@ -296,92 +311,25 @@ static int dev_horner(mpvss_ctx* ctx, int tpi, const uint32_t* comm, DevBuf& cm,
   return MPVSS_OK;
 }
 
-// e_i = pos_i^B mod (q-1) for the two-chunk Horner: q-1 = 2g, so by CRT e_i is the representative
-// of pos_i^B mod g (device modexp with the constants of modulus g) that has the parity of pos_i.
-static int dev_chunk_exponents(mpvss_ctx* ctx, const int64_t* positions, size_t n, uint32_t B, DevBuf& e_out) {
-  std::vector<uint8_t> base(n * EB, 0), bexp(EB, 0), e(n * EB);
-  for (size_t i = 0; i < n; ++i) {
-    uint32_t p = (uint32_t)(positions ? positions[i] : (int64_t)i + 1);
-    memcpy(base.data() + i * EB, &p, 4);
-  }
-  memcpy(bexp.data(), &B, 4);
-  DevBuf &db = ctx->buf(20), &dx = ctx->buf(21);
-  MPVSS_TRY(h2d(ctx, db, base.data(), n * EB));
-  MPVSS_TRY(h2d(ctx, dx, bexp.data(), EB));
-  MPVSS_CUDA(ctx, e_out.ensure(n * EB));
-  MPVSS_TRY(dev_exp2(ctx, ctx->consts_g.as<uint32_t>(), db.as<uint32_t>(), EW, dx.as<uint32_t>(), 0,
-                     windows_for(bexp.data(), EB, 1), nullptr, 0, nullptr, 0, 0, n, e_out.as<uint32_t>()));
-  MPVSS_TRY(d2h(ctx, e.data(), e_out, n * EB));
-  MPVSS_TRY(sync(ctx));
-  for (size_t i = 0; i < n; ++i) {
-    if ((e[i * EB] & 1u) != (base[i * EB] & 1u)) {
-      big::Int v = big::add(big::from_le(e.data() + i * EB, EB), ctx->g);
-      big::to_le(v, e.data() + i * EB, EB);
-    }
-  }
-  return h2d(ctx, e_out, e.data(), n * EB);
-}
-
-// Two-chunk form of dev_horner: H0, H1 side by side on every lane group, then
-// X = H0 * H1^(pos^B mod (q-1)) with the exponentiation kernel.
-static int dev_horner2(mpvss_ctx* ctx, int tpi, const uint32_t* comm, DevBuf& cm, size_t t, const uint32_t* pos,
-                       const uint32_t* slot, const uint32_t* nd, const uint32_t* skip, size_t n_padded, size_t n,
-                       const uint32_t* e,
-                       DevBuf& h, uint32_t* x) {
-  const uint32_t* K = ctx->consts_q.as<uint32_t>();
-  MPVSS_CUDA(ctx, cm.ensure(t * EB));
-  MPVSS_CUDA(ctx, h.ensure(2 * n * EB));
-  MPVSS_TRY(dev_mul(ctx, K, comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  uint32_t* h0 = h.as<uint32_t>();
-  uint32_t* h1 = h0 + n * EW;
-  const uint32_t B = (uint32_t)((t + 1) / 2);
-  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
-  if (ctx->modp_dual == 2) {
-    // the two halves as two concurrent launches of the single-chain kernel (twice the warps)
-    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0));
-    modp::HornerArgs A0{K, cm.as<uint32_t>(), pos, slot, nd, skip, h0, B, (uint32_t)n_padded, 0};
-    modp::HornerArgs A1{K, cm.as<uint32_t>() + (size_t)B * EW, pos, slot, nd, skip, h1, (uint32_t)t - B,
-                        (uint32_t)n_padded, 0};
-    MPVSS_CUDA(ctx, modp::launch_horner(tpi, A0, ctx->modp_np1, ctx->stream));
-    MPVSS_CUDA(ctx, modp::launch_horner(tpi, A1, ctx->modp_np1, ctx->aux[1]));
-    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[1], ctx->aux[1]));
-    MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
-    timing_launch(ctx);
-  } else {
-    modp::Horner2Args A{K, cm.as<uint32_t>(), pos, slot, nd, skip, h0, h1, (uint32_t)t, (uint32_t)n_padded, B};
-    MPVSS_CUDA(ctx, modp::launch_horner2(tpi, A, ctx->stream));
-  }
-  MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
-  timing_launch(ctx);
-  return dev_exp2(ctx, K, h1, EW, e, EW, 512, h0, EW, ctx->gens.as<uint32_t>() + 128, 0, 1, n, x);
-}
-
 int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const int64_t* positions, size_t n,
                   uint8_t* out) {
   MPVSS_TRY(check_args(ctx, commitments && out && n > 0 && t > 0, "poly_eval_exp: bad arguments"));
   PosPlan plan;
   MPVSS_TRY(prep_positions(ctx, positions, n, plan));
-  DevBuf &dc = ctx->buf(0), &dp = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4),
-         &dnd = ctx->buf(5);
-  const size_t np = plan.pos.size();
+  DevBuf &dc = ctx->buf(0), &dops = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4),
+         &dno = ctx->buf(5);
+  const size_t np = plan.slot.size();
   MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, dp, plan.pos.data(), np * 4));
+  MPVSS_TRY(h2d(ctx, dops, plan.ops.data(), plan.ops.size() * 2));
   MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), np * 4));
-  MPVSS_TRY(h2d(ctx, dnd, plan.nd.data(), plan.nd.size() * 4));
-  DevBuf& dsk = ctx->buf(8);
-  MPVSS_TRY(h2d(ctx, dsk, plan.skip.data(), plan.skip.size() * 4));
+  MPVSS_TRY(h2d(ctx, dno, plan.nops.data(), plan.nops.size() * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
-  const bool dual = ctx->modp_dual && t >= 8;
-  if (dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->buf(6)));
   timing_begin(ctx);
-  if (dual)
-    MPVSS_TRY(dev_horner2(ctx, plan.tpi, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
-                          dsk.as<uint32_t>(), np, n, ctx->buf(6).as<uint32_t>(), ctx->buf(7), dout.as<uint32_t>()));
-  else
-    MPVSS_TRY(dev_horner(ctx, plan.tpi, dc.as<uint32_t>(), dcm, t, dp.as<uint32_t>(), dsl.as<uint32_t>(), dnd.as<uint32_t>(),
-                         dsk.as<uint32_t>(), np, dout.as<uint32_t>()));
+  MPVSS_TRY(dev_horner(ctx, plan.tpi, dc.as<uint32_t>(), dcm, t, dops.as<uint16_t>(), dsl.as<uint32_t>(),
+                       dno.as<uint32_t>(), np, dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
+  ctx->horner_sqr = plan.sqr * (t - 1);
+  ctx->horner_mul = plan.mul * (t - 1);
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
 }
@@ -473,46 +421,134 @@ int multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size
   return sync(ctx);
 }
 
-// ------------------------------------------------------------------- verify ----
-int verify_stage(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* commitments, const int64_t* positions,
-                 const uint8_t* publickeys, const uint8_t* shares, const uint8_t* responses, const uint8_t* challenge) {
-  MPVSS_TRY(check_args(ctx, n > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
-                       "verify_distribution: bad arguments"));
-  PosPlan plan;
-  MPVSS_TRY(prep_positions(ctx, positions, n, plan));
-  ctx->v_np = plan.pos.size();
-  ctx->v_nd_max = plan.nd.empty() ? 1u : plan.nd[0];  // classes are sorted longest first
-  ctx->v_tpi = plan.tpi;
-  MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_pos, plan.pos.data(), ctx->v_np * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nd.data(), plan.nd.size() * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_skip, plan.skip.data(), plan.skip.size() * 4));
-  MPVSS_TRY(h2d(ctx, ctx->v_pk, publickeys, n * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_y, shares, n * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_r, responses, n * EB));
-  MPVSS_TRY(h2d(ctx, ctx->v_c, challenge, EB));
-  MPVSS_CUDA(ctx, ctx->v_x.ensure(n * EB));
-  MPVSS_CUDA(ctx, ctx->v_a1.ensure(n * EB));
-  MPVSS_CUDA(ctx, ctx->v_a2.ensure(n * EB));
-  MPVSS_TRY(comb_table(ctx, 1, &ctx->v_comb));
-  ctx->v_dual = ctx->modp_dual && t >= 8;
-  if (ctx->v_dual) MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, (uint32_t)((t + 1) / 2), ctx->v_e));
-  ctx->v_rwin = windows_for(responses, EB, n);
-  ctx->v_cwin = windows_for(challenge, EB, 1);
-  ctx->v_challenge.assign(challenge, challenge + EB);
-  ctx->v_y_host.assign(shares, shares + n * EB);
-  ctx->v_n = n;
-  ctx->v_t = t;
-  return sync(ctx);  // the host buffers may be released by the caller after return
+// P(i) mod (q-1) for the given positions (polynomial.rs:50-58 reduced as participant.rs:202 does)
+int scalar_poly_eval(mpvss_ctx* ctx, const uint8_t* coeffs, size_t t, const int64_t* positions, size_t n, uint8_t* out) {
+  MPVSS_TRY(check_args(ctx, coeffs && out && n > 0 && t > 0, "scalar_poly_eval: bad arguments"));
+  std::vector<uint32_t> order(EW, 0), pos(n);
+  for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
+  for (size_t i = 0; i < n; ++i) {
+    int64_t p = positions ? positions[i] : (int64_t)i + 1;
+    if (p < 1 || p > 0x7fffffff) return mpvss_fail(ctx, MPVSS_ERR_ARG, "position out of range [1, 2^31)");
+    pos[i] = (uint32_t)p;
+  }
+  // the kernel wants coefficients below 2^2048 and reduces lazily; bring them below the order first
+  std::vector<uint8_t> co(t * EB);
+  for (size_t j = 0; j < t; ++j) big::to_le(big::mod(big::from_le(coeffs + j * EB, EB), ctx->qm1), co.data() + j * EB, EB);
+  DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dord = ctx->buf(11), &dpos = ctx->buf(12);
+  MPVSS_TRY(h2d(ctx, dco, co.data(), t * EB));
+  MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
+  MPVSS_TRY(h2d(ctx, dpos, pos.data(), n * 4));
+  MPVSS_CUDA(ctx, dp.ensure(n * EB));
+  timing_begin(ctx);
+  modp::PolyArgs PA{dco.as<uint32_t>(), dord.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t,
+                    (uint32_t)n};
+  MPVSS_CUDA(ctx, modp::launch_poly(PA, ctx->stream));
+  timing_launch(ctx);
+  MPVSS_TRY(timing_end(ctx));
+  MPVSS_TRY(d2h(ctx, out, dp, n * EB));
+  MPVSS_CUDA(ctx, cudaMemsetAsync(dco.p, 0, dco.cap, ctx->stream));  // coefficients are secret
+  return sync(ctx);
 }
 
-// kernels of the staged verification: X (Horner), then a1 = g^r * X^c, a2 = y^r * Y^c
+// Optional input validation ("validate" tunable): the reference's bytes_to_element accepts any
+// integer (modp.rs:154-156).  Elements must satisfy 0 < x < q and lie in the subgroup of order g the
+// protocol works in: x^g = 1 (one exponentiation each, with the kernels of modulus q).  *valid = false
+// if any of the `count` device-resident elements fails.
+static int validate_elements(mpvss_ctx* ctx, const uint32_t* dev, size_t count, bool* valid) {
+  std::vector<uint8_t> gexp(EB), res(count * EB), in(count * EB);
+  big::to_le(ctx->g, gexp.data(), EB);
+  DevBuf &de = ctx->buf(20), &dout = ctx->buf(21);
+  MPVSS_TRY(h2d(ctx, de, gexp.data(), EB));
+  MPVSS_CUDA(ctx, dout.ensure(count * EB));
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), dev, EW, de.as<uint32_t>(), 0, 512, nullptr, 0, nullptr, 0, 0,
+                     count, dout.as<uint32_t>()));
+  MPVSS_TRY(d2h(ctx, res.data(), dout, count * EB));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(in.data(), dev, count * EB, cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < count && *valid; ++i) {
+    big::Int x = big::from_le(in.data() + i * EB, EB);
+    bool one = res[i * EB] == 1;
+    for (size_t k = 1; k < EB && one; ++k) one = res[i * EB + k] == 0;
+    if (big::is_zero(x) || big::cmp(x, ctx->q) >= 0 || !one) *valid = false;
+  }
+  return MPVSS_OK;
+}
+
+// ------------------------------------------------------------------- verify ----
+static const transcript::Geom GEOM{EB, true};
+
+// rows `rank, rank + nranks, ...` of a host array of n_total rows (the whole array without a communicator)
+static const uint8_t* slice_rows(const mpvss_ctx* ctx, const uint8_t* all, size_t n_total, size_t width,
+                                 std::vector<uint8_t>& tmp) {
+  if (ctx->nranks <= 1) return all;
+  tmp.clear();
+  for (size_t i = (size_t)ctx->rank; i < n_total; i += (size_t)ctx->nranks)
+    tmp.insert(tmp.end(), all + i * width, all + (i + 1) * width);
+  return tmp.data();
+}
+
+int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commitments, const int64_t* positions,
+                 const uint8_t* publickeys, const uint8_t* shares, const uint8_t* responses, const uint8_t* challenge) {
+  ctx->v_n_total = 0;
+  MPVSS_TRY(check_args(ctx, n_total > 0 && t > 0 && commitments && publickeys && shares && responses && challenge,
+                       "verify_distribution: bad arguments"));
+  // this rank's participants: rank, rank + N, ... (every rank gets the same mix of short and long chains)
+  const size_t n = transcript::local_count(n_total, ctx->nranks, ctx->rank);
+  std::vector<int64_t> pos(n);
+  for (size_t j = 0; j < n; ++j) {
+    const size_t i = (size_t)ctx->rank + j * (size_t)ctx->nranks;
+    pos[j] = positions ? positions[i] : (int64_t)i + 1;
+  }
+  PosPlan plan;
+  if (n) MPVSS_TRY(prep_positions(ctx, pos.data(), n, plan));
+  ctx->v_np = plan.slot.size();
+  ctx->v_nops_max = plan.nops_max;
+  ctx->v_tpi = plan.tpi;
+  ctx->horner_sqr = plan.sqr * (t - 1);
+  ctx->horner_mul = plan.mul * (t - 1);
+  std::vector<uint8_t> tpk, ty, tr;
+  const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
+  const uint8_t* y = slice_rows(ctx, shares, n_total, EB, ty);
+  const uint8_t* r = slice_rows(ctx, responses, n_total, EB, tr);
+  MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
+  MPVSS_TRY(h2d(ctx, ctx->v_c, challenge, EB));
+  if (n) {
+    MPVSS_TRY(h2d(ctx, ctx->v_ops, plan.ops.data(), plan.ops.size() * 2));
+    MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
+    MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nops.data(), plan.nops.size() * 4));
+    MPVSS_TRY(h2d(ctx, ctx->v_pk, pk, n * EB));
+    MPVSS_TRY(h2d(ctx, ctx->v_y, y, n * EB));
+    MPVSS_TRY(h2d(ctx, ctx->v_r, r, n * EB));
+    MPVSS_CUDA(ctx, ctx->v_x.ensure(n * EB));
+    MPVSS_CUDA(ctx, ctx->v_a1.ensure(n * EB));
+    MPVSS_CUDA(ctx, ctx->v_a2.ensure(n * EB));
+  }
+  const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks);
+  MPVSS_CUDA(ctx, ctx->v_frames.ensure(rpr * GEOM.row()));
+  MPVSS_CUDA(ctx, cudaMemsetAsync(ctx->v_frames.p, 0, rpr * GEOM.row(), ctx->stream));
+  if (ctx->nranks > 1) MPVSS_CUDA(ctx, ctx->v_gather.ensure((size_t)ctx->nranks * rpr * GEOM.row()));
+  MPVSS_TRY(comb_table(ctx, 1, &ctx->v_comb));
+  ctx->v_rwin = n ? windows_for(r, EB, n) : 1;
+  ctx->v_cwin = windows_for(challenge, EB, 1);
+  ctx->v_challenge.assign(challenge, challenge + EB);
+  ctx->v_n = n;
+  ctx->v_t = t;
+  MPVSS_TRY(sync(ctx));  // the host buffers may be released by the caller after return
+  ctx->v_n_total = n_total;
+  return MPVSS_OK;
+}
+
+// kernels of the staged verification: X (Horner), a1 = g^r * X^c, a2 = y^r * Y^c, then the framed rows
 static int verify_kernels(mpvss_ctx* ctx) {
   const size_t n = ctx->v_n, t = ctx->v_t;
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   uint32_t* X = ctx->v_x.as<uint32_t>();
   timing_begin(ctx);
+  if (n == 0) {  // more ranks than participants: this rank only takes part in the all-gather
+    MPVSS_TRY(timing_end(ctx));
+    ctx->phase_ms[0] = ctx->phase_ms[1] = ctx->phase_ms[2] = 0.f;
+    return MPVSS_OK;
+  }
   // a2 = y^r * Y^c does not depend on X.  The Horner launch puts 7 one-warp CTAs on the 4 schedulers
   // of an SM, i.e. one warp slot per SM stays empty for the whole launch.  modp_overlap = 3 (default)
   // issues a2 on a side stream right AFTER the Horner launch as persistent one-warp CTAs, one per SM:
@@ -527,34 +563,28 @@ static int verify_kernels(mpvss_ctx* ctx) {
                     ctx->v_a2.as<uint32_t>(), s);
   };
   // Mode 3 only pays when the persistent CTAs finish inside the Horner launch: rounds of one
-  // exponentiation per SM (about 5 products per 4-bit window) against the t-1 Horner steps of about
-  // 3*digits+1 products; measured break-even near 0.6 (tools/overlap_sweep.sh).  Otherwise a2 goes first.
+  // exponentiation per SM (about 5 products per 4-bit window) against the t-1 Horner steps of
+  // nops products; measured break-even near 0.6 (tools/overlap_sweep.sh).  Otherwise a2 goes first.
   int overlap = ctx->modp_overlap;
   if (overlap == 3) {
     const size_t groups_per_warp = 32 / (size_t)ctx->modp_tpi;
     const size_t nwarps = (n + groups_per_warp - 1) / groups_per_warp;
     const size_t rounds = (nwarps + (size_t)ctx->sm_count - 1) / (size_t)ctx->sm_count;
     const double filler = (double)rounds * (5.0 * (ctx->v_rwin + ctx->v_cwin) + 30.0);
-    const double horner = (double)(t > 1 ? t - 1 : 0) * (3.0 * ctx->v_nd_max + 1.0);
+    const double horner = (double)(t > 1 ? t - 1 : 0) * (double)ctx->v_nops_max;
     if (filler > 0.6 * horner) overlap = 0;
   }
   const bool side = overlap == 2 || overlap == 3;
   if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
-  if (ctx->v_dual)
-    MPVSS_TRY(dev_horner2(ctx, ctx->v_tpi, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                          ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
-                          n, ctx->v_e.as<uint32_t>(), ctx->v_h, X));
-  else
-    MPVSS_TRY(dev_horner(ctx, ctx->v_tpi, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_pos.as<uint32_t>(),
-                         ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_skip.as<uint32_t>(), ctx->v_np,
-                         X));
+  MPVSS_TRY(dev_horner(ctx, ctx->v_tpi, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_ops.as<uint16_t>(),
+                       ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
   if (side) {
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
     // 3: persistent one-warp CTAs, one per SM, into the warp slot the Horner CTAs leave empty
-    if (overlap == 3) ctx->exp2_filler_smem = (size_t)ctx->sm_count;
+    if (overlap == 3) ctx->exp2_filler_ctas = (size_t)ctx->sm_count;
     int rc = launch_a2(ctx->aux[0]);
-    ctx->exp2_filler_smem = 0;
+    ctx->exp2_filler_ctas = 0;
     MPVSS_TRY(rc);
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
   }
@@ -563,6 +593,21 @@ static int verify_kernels(mpvss_ctx* ctx) {
   MPVSS_TRY(dev_exp2(ctx, K, ctx->gens.as<uint32_t>() + 64, 0, ctx->v_r.as<uint32_t>(), EW, ctx->v_rwin, X, EW,
                      ctx->v_c.as<uint32_t>(), 0, ctx->v_cwin, n, ctx->v_a1.as<uint32_t>(), nullptr, ctx->v_comb));
   if (side) MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+  // transcript rows F(X) F(Y) F(a1) F(a2) in local order (dleq.rs:87-99)
+  modp::FrameArgs FA{X, ctx->v_y.as<uint32_t>(), ctx->v_a1.as<uint32_t>(), ctx->v_a2.as<uint32_t>(),
+                     ctx->v_frames.as<uint8_t>(), (uint32_t)n};
+  MPVSS_CUDA(ctx, modp::launch_frames(FA, ctx->stream));
+  timing_launch(ctx);
+  if (ctx->validate) {
+    bool valid = true;
+    MPVSS_TRY(validate_elements(ctx, ctx->v_comm.as<uint32_t>(), t, &valid));
+    MPVSS_TRY(validate_elements(ctx, ctx->v_pk.as<uint32_t>(), n, &valid));
+    MPVSS_TRY(validate_elements(ctx, ctx->v_y.as<uint32_t>(), n, &valid));
+    if (!valid) {  // mark the rank's first row: 0xff is never part of a valid length (seen by all ranks)
+      const uint8_t mark = 0xff;
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->v_frames.p, &mark, 1, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
   MPVSS_TRY(timing_end(ctx));
   MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));  // X_i (with a2 underneath)
   MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));  // remaining DLEQ work
@@ -570,148 +615,173 @@ static int verify_kernels(mpvss_ctx* ctx) {
   return MPVSS_OK;
 }
 
-int transcript_check(mpvss_ctx* ctx, size_t n, const uint8_t* x, const uint8_t* y, const uint8_t* a1,
-                     const uint8_t* a2, const uint8_t* challenge, int* ok, uint8_t* digest_out) {
-  MPVSS_TRY(check_args(ctx, n > 0 && x && y && a1 && a2 && challenge && ok, "transcript_check: bad arguments"));
-  sha2::Sha256 h;
-  for (size_t i = 0; i < n; ++i) {  // participant.rs:438-447 -> dleq.rs:87-99, order (X, Y, a1, a2)
-    framed_update(h, x + i * EB);
-    framed_update(h, y + i * EB);
-    framed_update(h, a1 + i * EB);
-    framed_update(h, a2 + i * EB);
+int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
+  MPVSS_TRY(check_args(ctx, ok && ctx->v_n_total > 0, "verify_distribution_run: nothing staged"));
+  MPVSS_TRY(check_args(ctx, ctx->nranks <= 1 || (!x_out && !a1_out && !a2_out),
+                       "verify_distribution: x/a1/a2 outputs are not available with a communicator"));
+  const size_t n = ctx->v_n, n_total = ctx->v_n_total;
+  MPVSS_TRY(verify_kernels(ctx));
+  // one all-gather of the rows per phase, then one hash pass in participant order
+  const uint8_t* rows = ctx->v_frames.as<uint8_t>();
+  if (ctx->nranks > 1) {
+    MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p,
+                             transcript::rows_per_rank(n_total, ctx->nranks) * GEOM.row()));
+    rows = ctx->v_gather.as<uint8_t>();
   }
+  sha2::Sha256 h;
+  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h));
   uint8_t digest[32], c[EB];
   h.finalize(digest);
   challenge_from_digest(ctx, digest, c);
-  *ok = memcmp(c, challenge, EB) == 0;  // participant.rs:451-454
+  *ok = memcmp(c, ctx->v_challenge.data(), EB) == 0;  // participant.rs:451-454
+  for (int r = 0; r < ctx->nranks; ++r)  // a rank whose slice failed validation marked its first row
+    if (ctx->h_frames.as<uint8_t>()[(size_t)r * transcript::rows_per_rank(n_total, ctx->nranks) * GEOM.row()] == 0xff) *ok = 0;
   if (digest_out) memcpy(digest_out, digest, 32);
-  return MPVSS_OK;
-}
-
-int verify_compute(mpvss_ctx* ctx, void* x_dev, void* a1_dev, void* a2_dev) {
-  MPVSS_TRY(check_args(ctx, x_dev && a1_dev && a2_dev && ctx->v_n > 0, "verify_distribution_compute: nothing staged"));
-  MPVSS_TRY(verify_kernels(ctx));
-  const size_t bytes = ctx->v_n * EB;
-  MPVSS_CUDA(ctx, cudaMemcpyAsync(x_dev, ctx->v_x.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-  MPVSS_CUDA(ctx, cudaMemcpyAsync(a1_dev, ctx->v_a1.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-  MPVSS_CUDA(ctx, cudaMemcpyAsync(a2_dev, ctx->v_a2.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (x_out) MPVSS_TRY(d2h(ctx, x_out, ctx->v_x, n * EB));
+  if (a1_out) MPVSS_TRY(d2h(ctx, a1_out, ctx->v_a1, n * EB));
+  if (a2_out) MPVSS_TRY(d2h(ctx, a2_out, ctx->v_a2, n * EB));
   return sync(ctx);
 }
 
-int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t* a2_out, uint8_t* digest_out) {
-  MPVSS_TRY(check_args(ctx, ok && ctx->v_n > 0, "verify_distribution_run: nothing staged"));
-  const size_t n = ctx->v_n;
-  MPVSS_TRY(verify_kernels(ctx));
-  // results back in index order
-  PinBuf &hx = ctx->pin(0), &ha1 = ctx->pin(1), &ha2 = ctx->pin(2);
-  MPVSS_CUDA(ctx, hx.ensure(n * EB));
-  MPVSS_CUDA(ctx, ha1.ensure(n * EB));
-  MPVSS_CUDA(ctx, ha2.ensure(n * EB));
-  MPVSS_TRY(d2h(ctx, hx.p, ctx->v_x, n * EB));
-  MPVSS_TRY(d2h(ctx, ha1.p, ctx->v_a1, n * EB));
-  MPVSS_TRY(d2h(ctx, ha2.p, ctx->v_a2, n * EB));
+// --------------------------------------------------------------- distribute ----
+// Bring this rank's n local rows of `width` bytes (device) to the host in `publickeys` order for all
+// n_total participants: a plain copy without a communicator, else one all-gather of `kinds` row sets at once
+// ([rank][kind][rows_per_rank][width]) and a scatter on the host.
+static int gather_rows(mpvss_ctx* ctx, const void* const* dev_local, uint8_t* const* host_all, int kinds, size_t n,
+                       size_t n_total, size_t width) {
+  if (ctx->nranks <= 1) {
+    for (int k = 0; k < kinds; ++k)
+      if (host_all[k]) MPVSS_CUDA(ctx, cudaMemcpyAsync(host_all[k], dev_local[k], n * width, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync(ctx);
+  }
+  const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks), N = (size_t)ctx->nranks;
+  const size_t per_rank = (size_t)kinds * rpr * width;
+  DevBuf& loc = ctx->buf(22);
+  MPVSS_CUDA(ctx, loc.ensure(per_rank));
+  MPVSS_CUDA(ctx, ctx->v_gather.ensure(N * per_rank));
+  MPVSS_CUDA(ctx, cudaMemsetAsync(loc.p, 0, per_rank, ctx->stream));
+  for (int k = 0; k < kinds; ++k)
+    if (n) MPVSS_CUDA(ctx, cudaMemcpyAsync(loc.as<uint8_t>() + (size_t)k * rpr * width, dev_local[k], n * width,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+  MPVSS_TRY(comm_allgather(ctx, loc.p, ctx->v_gather.p, per_rank));
+  MPVSS_CUDA(ctx, ctx->h_frames.ensure(N * per_rank));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->h_frames.p, ctx->v_gather.p, N * per_rank, cudaMemcpyDeviceToHost, ctx->stream));
   MPVSS_TRY(sync(ctx));
-  MPVSS_TRY(transcript_check(ctx, n, hx.as<uint8_t>(), ctx->v_y_host.data(), ha1.as<uint8_t>(), ha2.as<uint8_t>(),
-                             ctx->v_challenge.data(), ok, digest_out));
-  if (x_out) memcpy(x_out, hx.p, n * EB);
-  if (a1_out) memcpy(a1_out, ha1.p, n * EB);
-  if (a2_out) memcpy(a2_out, ha2.p, n * EB);
+  const uint8_t* g = ctx->h_frames.as<uint8_t>();
+  for (int k = 0; k < kinds; ++k) {
+    if (!host_all[k]) continue;
+    for (size_t i = 0; i < n_total; ++i)
+      memcpy(host_all[k] + i * width, g + (i % N) * per_rank + ((size_t)k * rpr + i / N) * width, width);
+  }
   return MPVSS_OK;
 }
 
-// --------------------------------------------------------------- distribute ----
-int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t secret_len, const uint8_t* coeffs,
-               const uint8_t* witnesses, const uint8_t* publickeys, uint8_t* commitments_out, uint8_t* shares_out,
-               uint8_t* challenge_out, uint8_t* responses_out, uint8_t* u_out, uint8_t* x_out) {
-  MPVSS_TRY(check_args(ctx, n > 0 && t > 0 && t <= n && secret && coeffs && witnesses && publickeys &&
+int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, size_t secret_len,
+               const uint8_t* coeffs, const uint8_t* witnesses, const uint8_t* publickeys, uint8_t* commitments_out,
+               uint8_t* shares_out, uint8_t* challenge_out, uint8_t* responses_out, uint8_t* u_out, uint8_t* x_out) {
+  MPVSS_TRY(check_args(ctx, n_total > 0 && t > 0 && t <= n_total && secret && coeffs && witnesses && publickeys &&
                                 commitments_out && shares_out && challenge_out && responses_out && u_out &&
                                 secret_len <= EB,
-                       "distribute: bad arguments (threshold <= n, participant.rs:166)"));
-  std::vector<uint32_t> order(EW, 0), pos(n);
+                       "distribute: bad arguments (threshold <= n, participant.rs:166; secret at most 256 bytes)"));
+  std::vector<uint32_t> order(EW, 0);
   for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
-  if (order[EW - 1] != 0xffffffffu)
-    return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, "distribute: scalar kernel needs an order with an all-ones top limb");
-  for (size_t i = 0; i < n; ++i) pos[i] = (uint32_t)(i + 1);
-  std::vector<uint8_t> p(n * EB);
+  if (order[EW - 1] != 0xffffffffu || order[EW - 2] != 0xffffffffu)
+    return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, "distribute: scalar kernels need an order with all-ones top limbs");
+  // this rank's participants: rank, rank + N, ... (all of them without a communicator)
+  const size_t n = transcript::local_count(n_total, ctx->nranks, ctx->rank);
+  std::vector<uint32_t> pos(std::max<size_t>(n, 1));
+  for (size_t j = 0; j < n; ++j) pos[j] = (uint32_t)((size_t)ctx->rank + j * (size_t)ctx->nranks + 1);
+  std::vector<uint8_t> tw, tpk;
+  const uint8_t* w = slice_rows(ctx, witnesses, n_total, EB, tw);
+  const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
   const uint32_t* K = ctx->consts_q.as<uint32_t>();
   const uint32_t* G = ctx->gens.as<uint32_t>();
   DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dw = ctx->buf(2), &dpk = ctx->buf(3), &dC = ctx->buf(4),
-         &dX = ctx->buf(5), &dY = ctx->buf(6), &dA1 = ctx->buf(7), &dA2 = ctx->buf(8), &dGs = ctx->buf(9);
+         &dX = ctx->buf(5), &dY = ctx->buf(6), &dA1 = ctx->buf(7), &dA2 = ctx->buf(8), &dGs = ctx->buf(9),
+         &ds = ctx->buf(10), &dord = ctx->buf(11), &dpos = ctx->buf(12), &dR = ctx->buf(13), &dc = ctx->buf(14);
   // s = P(0) mod (q-1) = a_0 mod (q-1)  (participant.rs:267)
   uint8_t s_le[EB];
   big::to_le(big::mod(big::from_le(coeffs, EB), ctx->qm1), s_le, EB);
-  DevBuf& ds = ctx->buf(10);
   MPVSS_TRY(h2d(ctx, dco, coeffs, t * EB));
-  MPVSS_CUDA(ctx, dp.ensure(n * EB));
-  {
-    // p_i = P(i) mod (q-1) (participant.rs:202), one position per thread
-    DevBuf &dord = ctx->buf(11), &dpos = ctx->buf(12);
-    MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
-    MPVSS_TRY(h2d(ctx, dpos, pos.data(), n * 4));
-    modp::PolyArgs PA{dco.as<uint32_t>(), dord.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t,
-                      (uint32_t)n};
-    MPVSS_CUDA(ctx, modp::launch_poly(PA, ctx->stream));
-    MPVSS_TRY(d2h(ctx, p.data(), dp, n * EB));
-    MPVSS_TRY(sync(ctx));
-  }
-  MPVSS_TRY(h2d(ctx, dw, witnesses, n * EB));
-  MPVSS_TRY(h2d(ctx, dpk, publickeys, n * EB));
+  MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
+  MPVSS_TRY(h2d(ctx, dpos, pos.data(), pos.size() * 4));
   MPVSS_TRY(h2d(ctx, ds, s_le, EB));
-  for (DevBuf* b : {&dX, &dY, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
+  if (n) {
+    MPVSS_TRY(h2d(ctx, dw, w, n * EB));
+    MPVSS_TRY(h2d(ctx, dpk, pk, n * EB));
+  }
+  const size_t nn = std::max<size_t>(n, 1);
+  for (DevBuf* b : {&dp, &dX, &dY, &dA1, &dA2, &dR}) MPVSS_CUDA(ctx, b->ensure(nn * EB));
   MPVSS_CUDA(ctx, dC.ensure(t * EB));
   MPVSS_CUDA(ctx, dGs.ensure(EB));
-  uint32_t cw = windows_for(coeffs, EB, t), pw = windows_for(p.data(), EB, n), ww = windows_for(witnesses, EB, n);
+  MPVSS_CUDA(ctx, dc.ensure(EB));
+  // secret exponents (coefficients, P(i), witnesses) always run the full window count: the schedule must
+  // not depend on their size
+  const uint32_t FW = 512;
   const uint32_t *combG, *combg;
   MPVSS_TRY(comb_table(ctx, 0, &combG));
   MPVSS_TRY(comb_table(ctx, 1, &combg));
+  const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks);
+  MPVSS_CUDA(ctx, ctx->v_frames.ensure(rpr * GEOM.row()));
+  MPVSS_CUDA(ctx, cudaMemsetAsync(ctx->v_frames.p, 0, rpr * GEOM.row(), ctx->stream));
+  if (ctx->nranks > 1) MPVSS_CUDA(ctx, ctx->v_gather.ensure((size_t)ctx->nranks * rpr * GEOM.row()));
   timing_begin(ctx);
-  // C_j = g^a_j (participant.rs:189-193)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dco.as<uint32_t>(), EW, cw, nullptr, 0, nullptr, 0, 0, t, dC.as<uint32_t>(),
+  // C_j = g^a_j (participant.rs:189-193); every rank computes all t of them (replicated, fixed-base table)
+  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dco.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, t, dC.as<uint32_t>(),
                      nullptr, combg));
-  // X_i = prod_j C_j^(i^j) = g^P(i): the dealer knows P, one fixed-base exponentiation
-  // gives the same group element as the reference's t-term product (participant.rs:207-215)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n, dX.as<uint32_t>(),
-                     nullptr, combg));
-  // Y_i = y_i^P(i) (participant.rs:219)
-  MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dp.as<uint32_t>(), EW, pw, nullptr, 0, nullptr, 0, 0, n,
-                     dY.as<uint32_t>()));
-  // a1 = g^w, a2 = y^w (participant.rs:236-237)
-  MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>(),
-                     nullptr, combg));
-  MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, ww, nullptr, 0, nullptr, 0, 0, n,
-                     dA2.as<uint32_t>()));
   // G^s (participant.rs:268)
-  MPVSS_TRY(dev_exp2(ctx, K, G, 0, ds.as<uint32_t>(), EW, windows_for(s_le, EB, 1), nullptr, 0, nullptr, 0, 0, 1,
-                     dGs.as<uint32_t>(), nullptr, combG));
-  MPVSS_TRY(timing_end(ctx));
-  std::vector<uint8_t> X(n * EB), A1(n * EB), A2(n * EB);
-  uint8_t gs[EB];
-  MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
-  MPVSS_TRY(d2h(ctx, X.data(), dX, n * EB));
-  MPVSS_TRY(d2h(ctx, shares_out, dY, n * EB));
-  MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
-  MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
-  MPVSS_TRY(d2h(ctx, gs, dGs, EB));
-  MPVSS_TRY(sync(ctx));
-  sha2::Sha256 h;
-  for (size_t i = 0; i < n; ++i) {  // participant.rs:238-245
-    framed_update(h, X.data() + i * EB);
-    framed_update(h, shares_out + i * EB);
-    framed_update(h, A1.data() + i * EB);
-    framed_update(h, A2.data() + i * EB);
+  MPVSS_TRY(dev_exp2(ctx, K, G, 0, ds.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, 1, dGs.as<uint32_t>(), nullptr,
+                     combG));
+  if (n) {
+    // p_i = P(i) mod (q-1) (participant.rs:202), one position per thread
+    modp::PolyArgs PA{dco.as<uint32_t>(), dord.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t,
+                      (uint32_t)n};
+    MPVSS_CUDA(ctx, modp::launch_poly(PA, ctx->stream));
+    timing_launch(ctx);
+    // X_i = prod_j C_j^(i^j) = g^P(i): the dealer knows P, one fixed-base exponentiation
+    // gives the same group element as the reference's t-term product (participant.rs:207-215)
+    MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dp.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, n, dX.as<uint32_t>(),
+                       nullptr, combg));
+    // Y_i = y_i^P(i) (participant.rs:219)
+    MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dp.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, n,
+                       dY.as<uint32_t>()));
+    // a1 = g^w, a2 = y^w (participant.rs:236-237)
+    MPVSS_TRY(dev_exp2(ctx, K, G + 64, 0, dw.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, n, dA1.as<uint32_t>(),
+                       nullptr, combg));
+    MPVSS_TRY(dev_exp2(ctx, K, dpk.as<uint32_t>(), EW, dw.as<uint32_t>(), EW, FW, nullptr, 0, nullptr, 0, 0, n,
+                       dA2.as<uint32_t>()));
+    modp::FrameArgs FA{dX.as<uint32_t>(), dY.as<uint32_t>(), dA1.as<uint32_t>(), dA2.as<uint32_t>(),
+                       ctx->v_frames.as<uint8_t>(), (uint32_t)n};
+    MPVSS_CUDA(ctx, modp::launch_frames(FA, ctx->stream));
+    timing_launch(ctx);
   }
+  MPVSS_TRY(timing_end(ctx));
+  // transcript (participant.rs:238-252): one all-gather of the framed rows, one hash pass, on every rank
+  const uint8_t* rows = ctx->v_frames.as<uint8_t>();
+  if (ctx->nranks > 1) {
+    MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * GEOM.row()));
+    rows = ctx->v_gather.as<uint8_t>();
+  }
+  sha2::Sha256 h;
+  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h));
   uint8_t digest[32];
   h.finalize(digest);
-  challenge_from_digest(ctx, digest, challenge_out);  // participant.rs:251-252
-  big::Int c = big::from_le(challenge_out, EB);
-  for (size_t i = 0; i < n; ++i) {  // participant.rs:255-264: r = (w - (p*c mod ord)) mod ord
-    big::Int alpha_c = big::mulmod(big::from_le(p.data() + i * EB, EB), c, ctx->qm1);
-    big::Int w = big::from_le(witnesses + i * EB, EB);
-    // scalar_sub (modp.rs:184-192): negative -> add the order once, else reduce
-    big::Int r = big::cmp(w, alpha_c) >= 0 ? big::mod(big::sub(w, alpha_c), ctx->qm1)
-                                           : big::mod(big::sub(big::add(w, ctx->qm1), alpha_c), ctx->qm1);
-    big::to_le(r, responses_out + i * EB, EB);
+  challenge_from_digest(ctx, digest, challenge_out);
+  // responses r_i = (w_i - p_i * c) mod (q-1) on the device (participant.rs:255-264, modp.rs:180-192)
+  MPVSS_TRY(h2d(ctx, dc, challenge_out, EB));
+  if (n) {
+    modp::RespArgs RA{dord.as<uint32_t>(), dp.as<uint32_t>(), dw.as<uint32_t>(), dc.as<uint32_t>(), dR.as<uint32_t>(),
+                      (uint32_t)n, EW};
+    MPVSS_CUDA(ctx, modp::launch_resp(RA, ctx->stream));
+    ctx->last_launches += 1;
   }
+  const void* dev_rows[3] = {dY.p, dR.p, dX.p};
+  uint8_t* host_rows[3] = {shares_out, responses_out, x_out};
+  MPVSS_TRY(gather_rows(ctx, dev_rows, host_rows, x_out ? 3 : 2, n, n_total, EB));
+  uint8_t gs[EB];
+  MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
+  MPVSS_TRY(d2h(ctx, gs, dGs, EB));
+  MPVSS_TRY(sync(ctx));
   // U = secret XOR (int(SHA-256(bytes(G^s))) mod q)  (participant.rs:269-272)
   uint8_t tmp[EB], hs[32];
   size_t len = min_be(gs, tmp);
@@ -719,8 +789,9 @@ int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t
   big::Int mask = big::mod(big::from_be(hs, 32), ctx->q);
   big::Int u = big::bxor(big::from_be(secret, secret_len), mask);
   big::to_be(u, u_out, EB);
-  if (x_out) memcpy(x_out, X.data(), n * EB);
-  return MPVSS_OK;
+  // the scratch buffers held secrets (coefficients, P(i), witnesses)
+  for (DevBuf* b : {&dco, &dp, &dw, &ds}) MPVSS_CUDA(ctx, cudaMemsetAsync(b->p, 0, b->cap, ctx->stream));
+  return sync(ctx);
 }
 
 // ------------------------------------------------------------------ extract ----
@@ -765,7 +836,7 @@ int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const 
     big::to_le(x, inv.data() + i * EB, EB);
   }
   MPVSS_TRY(h2d(ctx, dinv, inv.data(), n * EB));
-  uint32_t skw = windows_for(private_keys, EB, n), ww = windows_for(witnesses, EB, n);
+  const uint32_t skw = 512, ww = 512;  // secret exponents: full window count, whatever their size
   const uint32_t* combG;
   MPVSS_TRY(comb_table(ctx, 0, &combG));
   float ms0 = ctx->last_ms;
@@ -797,15 +868,24 @@ int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const 
     framed_update(h, A2.data() + i * EB);
     uint8_t digest[32];
     h.finalize(digest);
-    uint8_t* c_le = challenges_out + i * EB;
-    challenge_from_digest(ctx, digest, c_le);
-    // r = w - sk*c (dleq.rs:42-50 with modp.rs:180-192)
-    big::Int c = big::from_le(c_le, EB);
-    big::Int alpha_c = big::mulmod(big::from_le(private_keys + i * EB, EB), c, ctx->qm1);
-    big::Int w = big::from_le(witnesses + i * EB, EB);
-    big::Int r = big::cmp(w, alpha_c) >= 0 ? big::mod(big::sub(w, alpha_c), ctx->qm1)
-                                           : big::sub(big::add(w, ctx->qm1), alpha_c);
-    big::to_le(r, responses_out + i * EB, EB);
+    challenge_from_digest(ctx, digest, challenges_out + i * EB);
+  }
+  {
+    // r = w - sk*c mod (q-1) on the device (dleq.rs:42-50 with modp.rs:180-192)
+    std::vector<uint32_t> order(EW, 0);
+    for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
+    DevBuf &dord = ctx->buf(11), &dch = ctx->buf(12), &dR = ctx->buf(13);
+    MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
+    MPVSS_TRY(h2d(ctx, dch, challenges_out, n * EB));
+    MPVSS_CUDA(ctx, dR.ensure(n * EB));
+    modp::RespArgs RA{dord.as<uint32_t>(), dsk.as<uint32_t>(), dw.as<uint32_t>(), dch.as<uint32_t>(), dR.as<uint32_t>(),
+                      (uint32_t)n, EW, EW};
+    MPVSS_CUDA(ctx, modp::launch_resp(RA, ctx->stream));
+    ctx->last_launches += 1;
+    MPVSS_TRY(d2h(ctx, responses_out, dR, n * EB));
+    // the scratch buffers held secrets (private keys, inverses, witnesses)
+    for (DevBuf* b : {&dsk, &dskg, &dinv, &dw}) MPVSS_CUDA(ctx, cudaMemsetAsync(b->p, 0, b->cap, ctx->stream));
+    MPVSS_TRY(sync(ctx));
   }
   if (status_out) memcpy(status_out, st.data(), n * sizeof(int));
   return MPVSS_OK;

@@ -18,6 +18,11 @@ namespace modp {
 // Layout of the constant block (device global memory, u32 limbs):
 //   [0,64) q   [64,128) 2^2048-q   [128,192) R mod q (Montgomery one)
 //   [192,256) R^2 mod q   [256] -q^-1 mod 2^32   [260,324) (q+1)/2
+// Per-group shared buffers are strided by their size plus GPAD words, so that the 32/TPI groups of a warp
+// start 8 banks apart: the LDS.64 that fetches the next two digits of b (every group reads the same word
+// index of its own buffer) then touches 2 x 4 distinct banks instead of one bank pair four times
+// (round-1 ncu: 4.2e9 shared-memory bank conflicts per Horner launch with a stride of 256 words).
+constexpr int GPAD = 8;
 enum { C_Q = 0, C_NQ = 64, C_ONE = 128, C_R2 = 192, C_NP = 256, C_QH = 260, C_WORDS = 324 };
 
 template <int TPI>
@@ -105,29 +110,37 @@ MP_DEV void finish_store(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, uint32_t* d
 }
 
 // ---------------------------------------------------------------- Horner ----
+// X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small integer i and
+// multiply by C_j".  acc^i follows a short addition chain per position (modp_chain.h: power tree, 13.4
+// products for a 12-bit i instead of the 16 of fixed 2-bit windows); the host lowers it to a list of ops
+//     if (save) slot[save-1] <- acc;  if (a) acc <- slot[a-1];  acc <- acc * B(b)
+// (bits 0-3 b, 4-7 a, 8-11 save; B(14) = Montgomery one = padding, B(15) = C_j closes the step).
+// Every lane group of a warp runs its own chain: the op fields only select shared-memory addresses, the
+// instruction stream is the same for all groups, so only the LENGTH of the op list has to agree inside
+// a warp (positions are sorted by it, shorter lists padded with products by one).
 struct HornerArgs {
   const uint32_t* consts;  // constant block
   const uint32_t* cm;      // t commitments, Montgomery form, 64 limbs each
-  const uint32_t* pos;     // n positions (1-based)
+  const uint16_t* ops;     // n x HC_OPS ops (one Horner step of each instance)
   const uint32_t* slot;    // n output slots (nullptr: instance i writes slot i; 0xffffffff: padding)
-  const uint32_t* nd;      // base-4 digit count per CTA (all instances of a CTA share it; the launcher
-                           // passes nd[blockIdx.x] so that the schedule is provably block-uniform and
-                           // ptxas needs no WARPSYNC around the shuffles); nullptr: `ndigits` everywhere
-  const uint32_t* skip;    // per CTA: bit s set = base-4 digit s is zero for every instance of the CTA, so
-                           // the window multiplication (by one) is skipped; nullptr: never skip
+  const uint32_t* nops;    // ops per step, per CTA (all instances of a CTA share it; the launcher passes
+                           // nops[blockIdx.x], which keeps the schedule provably block-uniform so that
+                           // ptxas needs no WARPSYNC around the shuffles); nullptr: `nops_all` everywhere
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
-  uint32_t t, n, ndigits;
+  uint32_t t, n, nops_all;
 };
 
-template <int TPI>
-constexpr int horner_smem_words = 128 + (32 / TPI) * (256 + sqr_scratch_words<TPI>);
+constexpr int HC_SLOTS = 6;   // == modp_chain::SLOTS
+constexpr int HC_OPS = 48;    // == modp_chain::OPS_MAX
+constexpr int HC_GSTRIDE = HC_SLOTS * 64 + GPAD;
 
-// X_i = (...((C_{t-1})^i * C_{t-2})^i ...)^i * C_0 : t-1 steps of "raise to the small
-// integer i (fixed 2-bit windows, same schedule for every group) and multiply by C_j".
+template <int TPI>
+constexpr int horner_smem_words = 128 + (32 / TPI) * (HC_GSTRIDE + HC_OPS / 2);
+
 // NP1: the modulus satisfies -q^-1 = 1 mod 2^32 (true for the RFC 3526 prime, whose low 64 bits are all
 // ones), so the Montgomery digit is the low limb itself and one multiply leaves the per-digit critical path.
 template <int TPI, bool NP1 = false>
-MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits, uint32_t skip) {
+MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t nops) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
   Lane ln = make_lane<TPI>();
@@ -138,136 +151,34 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   if (NP1) M.np = 1u;
-  uint32_t* cbuf = wsm;
-  uint32_t* one = wsm + 64;
-  uint32_t* tbl = wsm + 128 + gi * (256 + sqr_scratch_words<TPI>);  // tbl[0..2] = X, X^2, X^3 ; +192 squaring stage
-  uint32_t* sq = tbl + 192;
-  const SqrCtx sc = make_sqr_ctx<TPI>(tbl + 256, ln);
+  uint32_t* one = wsm;
+  uint32_t* cbuf = wsm + 64;
+  uint32_t* gbase = wsm + 128 + gi * HC_GSTRIDE;  // this group's chain slots
+  uint16_t* opsm = reinterpret_cast<uint16_t*>(wsm + 128 + GPW * HC_GSTRIDE) + gi * HC_OPS;
   warp_copy64(one, A.consts + C_ONE);
-  const uint32_t pos = A.pos[inst];
+  for (int k = ln.k; k < HC_OPS; k += TPI) opsm[k] = A.ops[(size_t)inst * HC_OPS + k];
   uint32_t acc[L];
   load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
   simt::syncwarp();
   for (int j = (int)A.t - 2; j >= 0; --j) {
     warp_copy64(cbuf, A.cm + (size_t)j * 64);
-    // window table X, X^2, X^3 (one code instance of the product: the loops below are not unrolled,
-    // a smaller kernel measured 4 % faster)
-    stage_shared<TPI>(tbl, acc, ln);
-    simt::syncwarp();
-    uint32_t x[L];
-#pragma unroll
-    for (int i = 0; i < L; ++i) x[i] = acc[i];
+    uint32_t op = opsm[0];
 #pragma unroll 1
-    for (int i = 1; i <= 2; ++i) {
-      mont_mul<TPI>(x, x, tbl, M, ln);
-      stage_shared<TPI>(tbl + i * 64, x, ln);
+    for (uint32_t k = 0; k < nops; ++k) {  // one code instance of the product for the whole step
+      const uint32_t nxt = opsm[k + 1 < (uint32_t)HC_OPS ? k + 1 : k];
+      const uint32_t sv = (op >> 8) & 15u, a = (op >> 4) & 15u, b = op & 15u;
+      simt::syncwarp();  // earlier readers of the slot are done
+      if (sv) stage<TPI>(gbase + (sv - 1) * 64, acc, ln);
       simt::syncwarp();
-    }
-    uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
-    load_slice<TPI>(acc, d ? tbl + (d - 1) * 64 : one, ln);
-    // windows ndigits-2 .. 0: two squarings and the table product; "window" -1: the product with C_j
-#pragma unroll 1
-    for (int s = (int)ndigits - 2; s >= -1; --s) {
-      const uint32_t* operand = cbuf;
-      bool mul = true;
-      if (s >= 0) {
-#pragma unroll 1
-        for (int rep = 0; rep < 2; ++rep) sqr_inplace<TPI>(acc, sq, sc, M, ln);  // one code instance
-        d = (pos >> (2 * s)) & 3u;
-        operand = d ? tbl + (d - 1) * 64 : one;
-        mul = !((skip >> s) & 1u);
-      }
-      if (mul) mont_mul<TPI>(acc, acc, operand, M, ln);
+      if (a) load_slice<TPI>(acc, gbase + (a - 1) * 64, ln);
+      const uint32_t* operand = b < 14u ? gbase + b * 64 : wsm + (b - 14u) * 64;
+      mont_mul<TPI>(acc, acc, operand, M, ln);
+      op = nxt;
     }
   }
   const uint32_t slot = A.slot ? A.slot[inst] : inst;
-  finish_store<TPI>(acc, sq, A.out + (size_t)(slot == 0xffffffffu ? 0 : slot) * 64, live && slot != 0xffffffffu, M,
+  finish_store<TPI>(acc, gbase, A.out + (size_t)(slot == 0xffffffffu ? 0 : slot) * 64, live && slot != 0xffffffffu, M,
                     ln);
-}
-
-// -------------------------------------------------------- Horner, two chunks ----
-// Same computation with the polynomial cut in two halves of B coefficients: every lane group
-// evaluates both halves of ONE position side by side (mont_mul2), which doubles the
-// independent work per lane without changing the schedule (both halves share the position's
-// digits).  Outputs H0 = prod_{j<B} C_j^(i^j) and H1 = prod_{j>=B} C_j^(i^(j-B)); the caller
-// finishes X_i = H0 * H1^(i^B mod (q-1)) with the exponentiation kernel.
-struct Horner2Args {
-  const uint32_t* consts;
-  const uint32_t* cm;      // t commitments, Montgomery form
-  const uint32_t* pos;
-  const uint32_t* slot;
-  const uint32_t* nd;      // per CTA, as in HornerArgs
-  const uint32_t* skip;    // per CTA, as in HornerArgs
-  uint32_t* out0;          // H0, canonical, indexed by slot
-  uint32_t* out1;          // H1
-  uint32_t t, n, B;        // B = ceil(t / 2) >= 2
-};
-
-template <int TPI>
-constexpr int horner2_smem_words = 192 + (32 / TPI) * 512;
-
-template <int TPI>
-MP_DEV void horner2_body(const Horner2Args& A, uint32_t wg, uint32_t* wsm, uint32_t ndigits, uint32_t skip) {
-  constexpr int L = Cfg<TPI>::L;
-  constexpr int GPW = 32 / TPI;
-  Lane ln = make_lane<TPI>();
-  const int gi = (int)simt::lane_id() / TPI;
-  uint32_t inst = wg * GPW + gi;
-  const bool live = inst < A.n;
-  if (!live) inst = A.n - 1;
-  Mod<L> M;
-  load_mod<TPI>(M, A.consts, ln);
-  uint32_t* cbuf0 = wsm;
-  uint32_t* cbuf1 = wsm + 64;
-  uint32_t* one = wsm + 128;
-  uint32_t* t0 = wsm + 192 + gi * 512;  // X, X^2, X^3, squaring stage of the low half
-  uint32_t* t1 = t0 + 256;              // same for the high half
-  uint32_t* sq0 = t0 + 192;
-  uint32_t* sq1 = t1 + 192;
-  warp_copy64(one, A.consts + C_ONE);
-  const uint32_t pos = A.pos[inst];
-  const uint32_t B = A.B, t = A.t;
-  uint32_t acc0[L], acc1[L];
-  load_slice<TPI>(acc0, A.cm + (size_t)(B - 1) * 64, ln);
-  load_slice<TPI>(acc1, (2 * B - 1 < t) ? A.cm + (size_t)(2 * B - 1) * 64 : A.consts + C_ONE, ln);
-  simt::syncwarp();
-  for (int j = (int)B - 2; j >= 0; --j) {
-    warp_copy64(cbuf0, A.cm + (size_t)j * 64);
-    warp_copy64(cbuf1, (B + j < t) ? A.cm + (size_t)(B + j) * 64 : A.consts + C_ONE);
-    stage_shared<TPI>(t0, acc0, ln);
-    stage_shared<TPI>(t1, acc1, ln);
-    simt::syncwarp();
-    uint32_t x0[L], x1[L];
-    mont_mul2<TPI>(x0, acc0, t0, x1, acc1, t1, M, ln);
-    stage_shared<TPI>(t0 + 64, x0, ln);
-    stage_shared<TPI>(t1 + 64, x1, ln);
-    simt::syncwarp();
-    mont_mul2<TPI>(x0, x0, t0, x1, x1, t1, M, ln);
-    stage_shared<TPI>(t0 + 128, x0, ln);
-    stage_shared<TPI>(t1 + 128, x1, ln);
-    simt::syncwarp();
-    uint32_t d = (pos >> (2 * (ndigits - 1))) & 3u;
-    load_slice<TPI>(acc0, d ? t0 + (d - 1) * 64 : one, ln);
-    load_slice<TPI>(acc1, d ? t1 + (d - 1) * 64 : one, ln);
-    for (int s = (int)ndigits - 2; s >= 0; --s) {
-#pragma unroll 1
-      for (int rep = 0; rep < 2; ++rep) {
-        stage_shared<TPI>(sq0, acc0, ln);
-        stage_shared<TPI>(sq1, acc1, ln);
-        simt::syncwarp();
-        mont_mul2<TPI>(acc0, acc0, sq0, acc1, acc1, sq1, M, ln);
-      }
-      d = (pos >> (2 * s)) & 3u;
-      if (!((skip >> s) & 1u))
-        mont_mul2<TPI>(acc0, acc0, d ? t0 + (d - 1) * 64 : one, acc1, acc1, d ? t1 + (d - 1) * 64 : one, M, ln);
-    }
-    mont_mul2<TPI>(acc0, acc0, cbuf0, acc1, acc1, cbuf1, M, ln);
-  }
-  const uint32_t slot = A.slot ? A.slot[inst] : inst;
-  const bool st = live && slot != 0xffffffffu;
-  const size_t off = (size_t)(slot == 0xffffffffu ? 0 : slot) * 64;
-  finish_store<TPI>(acc0, sq0, A.out0 + off, st, M, ln);
-  finish_store<TPI>(acc1, sq1, A.out1 + off, st, M, ln);
 }
 
 // ------------------------------------------------- (double) exponentiation ----
@@ -286,7 +197,7 @@ struct Exp2Args {
 };
 
 template <int TPI>
-constexpr int exp2_smem_words = 64 + (32 / TPI) * (16 * 64 + 64 + sqr_scratch_words<TPI>);
+constexpr int exp2_smem_words = 64 + (32 / TPI) * (16 * 64 + 64 + GPAD + sqr_scratch_words<TPI>);
 
 template <int TPI>
 MP_DEV void exp_window4(uint32_t (&acc)[Cfg<TPI>::L], const uint32_t* base64, const uint32_t* e, uint32_t windows,
@@ -344,7 +255,7 @@ struct CombArgs {
   uint32_t rows;         // byte positions covered (256 for full 2048-bit exponents)
 };
 template <int TPI>
-constexpr int comb_smem_words = 64 + (32 / TPI) * 128;
+constexpr int comb_smem_words = 64 + (32 / TPI) * (128 + GPAD);
 
 template <int TPI>
 MP_DEV void comb1_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
@@ -354,7 +265,7 @@ MP_DEV void comb1_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   uint32_t* r2 = wsm;
-  uint32_t* sq = wsm + 64 + gi * 128;
+  uint32_t* sq = wsm + 64 + gi * (128 + GPAD);
   warp_copy64(r2, A.consts + C_R2);
   simt::syncwarp();
   uint32_t b[L];
@@ -377,7 +288,7 @@ MP_DEV void comb2_body(const CombArgs& A, uint32_t wg, uint32_t* wsm) {
   if (!live) w = A.rows - 1;
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
-  uint32_t* b1 = wsm + 64 + gi * 128;
+  uint32_t* b1 = wsm + 64 + gi * (128 + GPAD);
   uint32_t* row = A.tbl + (size_t)w * 256 * 64;
   uint32_t x[L];
   load_slice<TPI>(x, A.consts + C_ONE, ln);
@@ -405,7 +316,7 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   uint32_t* r2 = wsm;
-  uint32_t* tbl = wsm + 64 + gi * (16 * 64 + 64 + sqr_scratch_words<TPI>);
+  uint32_t* tbl = wsm + 64 + gi * (16 * 64 + 64 + GPAD + sqr_scratch_words<TPI>);
   uint32_t* sq = tbl + 16 * 64;
   const SqrCtx sc = make_sqr_ctx<TPI>(sq + 64, ln);
   warp_copy64(r2, A.consts + C_R2);
@@ -425,6 +336,44 @@ MP_DEV void exp2_body(const Exp2Args& A, uint32_t wg, uint32_t* wsm) {
     mont_mul<TPI>(acc, acc, sq, M, ln);
   }
   finish_store<TPI>(acc, sq, A.out + (size_t)inst * 64, live, M, ln);
+}
+
+// ------------------------------------------------------- transcript frames ----
+// Row j of the Fiat-Shamir transcript (dleq.rs:58-61, 87-99; participant.rs:238-245, 438-447):
+//   F(X_j) F(Y_j) F(a1_j) F(a2_j),  F(e) = len_u64_be || minimal big-endian bytes (modp.rs:150-152),
+// each frame left-aligned in a slot of 8 + 256 bytes (zero padded), so that the host hashes the
+// device's bytes as they are.  One thread per frame; zero encodes as the single byte 00.
+struct FrameArgs {
+  const uint32_t *x, *y, *a1, *a2;  // n canonical values each, 64 little-endian limbs
+  uint8_t* out;                     // n rows of 4 * FRAME_BYTES
+  uint32_t n;
+};
+constexpr int FRAME_BYTES = 8 + 256;
+
+MP_DEV void frame_body(const FrameArgs& A, uint32_t tid) {
+  const uint32_t j = tid >> 2, e = tid & 3u;
+  if (j >= A.n) return;
+  const uint32_t* src = (e == 0 ? A.x : e == 1 ? A.y : e == 2 ? A.a1 : A.a2) + (size_t)j * 64;
+  uint8_t* dst = A.out + ((size_t)j * 4 + e) * FRAME_BYTES;
+  int top = 63;
+  while (top > 0 && src[top] == 0) --top;
+  const uint32_t w = src[top];
+  const uint32_t len = (uint32_t)top * 4 + ((w >> 24) ? 4u : (w >> 16) ? 3u : (w >> 8) ? 2u : 1u);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);  // frames are 8-byte aligned
+  d32[0] = 0;
+  d32[1] = ((len & 0xffu) << 24) | ((len >> 8) << 16);  // bytes 6, 7 = big-endian length
+  if (len == 256) {
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      const uint32_t v = src[63 - k];
+      d32[2 + k] = (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+    }
+  } else {
+    for (uint32_t k = 0; k < 256; ++k) {
+      const uint32_t b = len - 1 - k;  // little-endian byte index; wraps above len
+      dst[8 + k] = k < len ? (uint8_t)(src[b >> 2] >> ((b & 3u) * 8)) : (uint8_t)0;
+    }
+  }
 }
 
 // ------------------------------------------------- P(i) mod order (scalars) ----
@@ -493,6 +442,102 @@ MP_DEV void poly_body(const PolyArgs& A, uint32_t tid) {
   }
 #pragma unroll
   for (int i = 0; i < 64; ++i) A.out[(size_t)tid * 64 + i] = br ? acc[i] : r[i];
+}
+
+// ------------------------------------------------- DLEQ responses (scalars) ----
+// r_i = (w_i - (alpha_i * c mod order)) mod order  (dleq.rs:42-50 through modp.rs:180-192; call sites
+// participant.rs:255-264, 342-347): alpha_i < order, the challenge c < 2^256, w_i < 2^2048.  One instance
+// per thread on plain integers.  The order q-1 is even (no Montgomery form); its two top limbs are all
+// ones, so the limbs of alpha*c above 2^2048 are folded back with delta = 2^2048 - order < 2^1984, which
+// shortens the overflow by at least one limb per pass.
+struct RespArgs {
+  const uint32_t* order;  // 64 limbs
+  const uint32_t* alpha;  // n x 64 limbs (stride alpha_stride; 0 = shared)
+  const uint32_t* w;      // n x 64 limbs
+  const uint32_t* c;      // challenge(s), 64 limbs each, only the low 8 are read (stride c_stride; 0 = shared)
+  uint32_t* out;          // n x 64 limbs
+  uint32_t n, alpha_stride, c_stride;
+};
+MP_DEV void resp_body(const RespArgs& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  const uint32_t* al = A.alpha + (size_t)tid * A.alpha_stride;
+  const uint32_t* cc = A.c + (size_t)tid * A.c_stride;
+  uint32_t prod[72], delta[62];
+  {
+    uint64_t br = 0;
+    for (int i = 0; i < 62; ++i) {
+      uint64_t d = (uint64_t)0 - A.order[i] - br;
+      delta[i] = (uint32_t)d;
+      br = (d >> 32) & 1u;
+    }
+  }
+  for (int i = 0; i < 72; ++i) prod[i] = 0;
+  for (int j = 0; j < 8; ++j) {  // prod = alpha * c
+    const uint64_t cj = cc[j];
+    uint64_t carry = 0;
+    for (int i = 0; i < 64; ++i) {
+      carry += (uint64_t)al[i] * cj + prod[i + j];
+      prod[i + j] = (uint32_t)carry;
+      carry >>= 32;
+    }
+    prod[64 + j] = (uint32_t)carry;
+  }
+  for (int pass = 0; pass < 9; ++pass) {  // prod = lo + hi * delta until hi = 0
+    uint32_t hi[8], any = 0;
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = prod[64 + j];
+      any |= hi[j];
+      prod[64 + j] = 0;
+    }
+    if (!any) break;
+    for (int j = 0; j < 8; ++j) {
+      const uint64_t hj = hi[j];
+      uint64_t carry = 0;
+      for (int i = 0; i < 62; ++i) {
+        carry += (uint64_t)delta[i] * hj + prod[i + j];
+        prod[i + j] = (uint32_t)carry;
+        carry >>= 32;
+      }
+      for (int i = 62 + j; carry && i < 72; ++i) {
+        carry += prod[i];
+        prod[i] = (uint32_t)carry;
+        carry >>= 32;
+      }
+    }
+  }
+  // prod < 2^2048 now; bring it below the order, then r = w - prod (+ order if negative), reduced
+  uint32_t r[64];
+  auto sub_order = [&](uint32_t* v) {  // v -= order if v >= order
+    uint32_t t[64];
+    uint64_t br = 0;
+    for (int i = 0; i < 64; ++i) {
+      uint64_t d = (uint64_t)v[i] - A.order[i] - br;
+      t[i] = (uint32_t)d;
+      br = (d >> 32) & 1u;
+    }
+    if (!br)
+      for (int i = 0; i < 64; ++i) v[i] = t[i];
+  };
+  sub_order(prod);
+  const uint32_t* w = A.w + (size_t)tid * 64;
+  uint64_t br = 0;
+  for (int i = 0; i < 64; ++i) {
+    uint64_t d = (uint64_t)w[i] - prod[i] - br;
+    r[i] = (uint32_t)d;
+    br = (d >> 32) & 1u;
+  }
+  if (br) {  // negative: add the order once (modp.rs:186-188)
+    uint64_t c2 = 0;
+    for (int i = 0; i < 64; ++i) {
+      c2 += (uint64_t)r[i] + A.order[i];
+      r[i] = (uint32_t)c2;
+      c2 >>= 32;
+    }
+  } else {
+    sub_order(r);  // w may exceed the order: "% order"
+    sub_order(r);
+  }
+  for (int i = 0; i < 64; ++i) A.out[(size_t)tid * 64 + i] = r[i];
 }
 
 // ------------------------------------------------- Lagrange numerators / denominators ----
@@ -591,7 +636,7 @@ struct MulArgs {
 };
 
 template <int TPI>
-constexpr int mul_smem_words = 64 + (32 / TPI) * 64;
+constexpr int mul_smem_words = 64 + (32 / TPI) * (64 + GPAD);
 
 template <int TPI>
 MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
@@ -605,7 +650,7 @@ MP_DEV void mul_body(const MulArgs& A, uint32_t wg, uint32_t* wsm) {
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   uint32_t* r2 = wsm;
-  uint32_t* sq = wsm + 64 + gi * 64;
+  uint32_t* sq = wsm + 64 + gi * (64 + GPAD);
   warp_copy64(r2, A.consts + C_R2);
   simt::syncwarp();
   uint32_t acc[L];

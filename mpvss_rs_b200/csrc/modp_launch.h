@@ -8,9 +8,10 @@ constexpr int WARPS_PER_CTA = 4;     // exponentiation / multiplication kernels
 constexpr int HORNER_WARPS_PER_CTA = 1;  // Horner kernels: one warp per CTA keeps the per-CTA digit classes
                                          // fine-grained and lets the block scheduler spread warps evenly
 cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStream_t s);
-cudaError_t launch_horner2(int tpi, const Horner2Args& A, cudaStream_t s);
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s);
-cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t smem_bytes, cudaStream_t s);
+cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t ctas, cudaStream_t s);
+cudaError_t launch_frames(const FrameArgs& A, cudaStream_t s);
+cudaError_t launch_resp(const RespArgs& A, cudaStream_t s);
 cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s);
 cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s);
 cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s);

@@ -1,0 +1,94 @@
+// Host side of the Fiat-Shamir transcript (dleq.rs:58-61, 87-99; participant.rs:238-252, 438-454).
+//
+// The device writes every participant's four framed elements  F(X) F(Y) F(a1) F(a2),
+// F(e) = len_u64_be || bytes(e), into one fixed-size ROW per participant (frame kernels in modp.cu /
+// ec.cu): a frame occupies 8 + EB bytes, the bytes left-aligned (ModpGroup elements are minimal-length
+// big-endian, modp.rs:150-152, so a frame can be shorter than its slot; the curves' encodings have
+// fixed length).  The host therefore hashes device-produced bytes as they are: one SHA-256 pass over
+// the rows in `publickeys` order, no per-element byte reversal or length scan on the CPU.
+//
+// With N ranks (one GPU each) participant i lives on rank i % N at local row i / N; the rows of all ranks
+// arrive through one all-gather as [rank][local row], and the hash walks them in participant order.
+// The copy to the host is cut into chunks that are hashed while the next chunk is still in flight.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "ctx.h"
+#include "sha2.h"
+
+namespace transcript {
+
+struct Geom {
+  size_t eb;       // element bytes at the boundary
+  bool minimal;    // ModpGroup: frames carry minimal-length big-endian bytes
+  size_t frame() const { return 8 + eb; }
+  size_t row() const { return 4 * frame(); }
+};
+
+// rows per rank of a box of n_total participants dealt round robin to nranks
+inline size_t rows_per_rank(size_t n_total, int nranks) { return (n_total + (size_t)nranks - 1) / (size_t)nranks; }
+// participants owned by `rank`
+inline size_t local_count(size_t n_total, int nranks, int rank) {
+  return n_total > (size_t)rank ? (n_total - (size_t)rank + (size_t)nranks - 1) / (size_t)nranks : 0;
+}
+
+inline void hash_row(sha2::Sha256& h, const uint8_t* row, const Geom& g) {
+  if (!g.minimal) {
+    h.update(row, g.row());
+    return;
+  }
+  const size_t f = g.frame();
+  size_t len[4];
+  bool full = true;
+  for (int k = 0; k < 4; ++k) {
+    len[k] = ((size_t)row[k * f + 6] << 8) | row[k * f + 7];
+    full = full && len[k] == g.eb;
+  }
+  if (full) {
+    h.update(row, g.row());
+    return;
+  }
+  for (int k = 0; k < 4; ++k) h.update(row + k * f, 8 + len[k]);
+}
+
+// hash participants [i0, i1) of a gathered buffer laid out [rank][rows_per_rank][row]
+inline void hash_range(sha2::Sha256& h, const uint8_t* gathered, size_t i0, size_t i1, int nranks, size_t rpr,
+                       const Geom& g) {
+  const size_t row = g.row();
+  for (size_t i = i0; i < i1; ++i) hash_row(h, gathered + ((i % (size_t)nranks) * rpr + i / (size_t)nranks) * row, g);
+}
+
+// Copy the gathered rows from the device (ctx->stream, after everything queued there) in chunks of local
+// rows and hash them in participant order while later chunks are still copying.
+inline int fetch_and_hash(mpvss_ctx* ctx, const uint8_t* dev_rows, size_t n_total, int nranks, const Geom& g,
+                          sha2::Sha256& h) {
+  const size_t rpr = rows_per_rank(n_total, nranks), row = g.row();
+  MPVSS_CUDA(ctx, ctx->h_frames.ensure((size_t)nranks * rpr * row));
+  uint8_t* host = ctx->h_frames.as<uint8_t>();
+  constexpr size_t NCH = sizeof(ctx->ev_chunk) / sizeof(ctx->ev_chunk[0]);
+  // about 1 MiB per chunk and rank, at most NCH chunks
+  size_t rows_per_chunk = std::max<size_t>((1u << 20) / row, (rpr + NCH - 1) / NCH);
+  size_t nchunks = (rpr + rows_per_chunk - 1) / rows_per_chunk;
+  for (size_t c = 0; c < nchunks; ++c) {
+    const size_t j0 = c * rows_per_chunk, j1 = std::min(rpr, j0 + rows_per_chunk);
+    for (int r = 0; r < nranks; ++r) {
+      const size_t off = ((size_t)r * rpr + j0) * row;
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(host + off, dev_rows + off, (j1 - j0) * row, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+  }
+  for (size_t c = 0; c < nchunks; ++c) {
+    const size_t j0 = c * rows_per_chunk, j1 = std::min(rpr, j0 + rows_per_chunk);
+    MPVSS_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[c]));
+    hash_range(h, host, std::min(n_total, j0 * (size_t)nranks), std::min(n_total, j1 * (size_t)nranks), nranks, rpr, g);
+  }
+  return MPVSS_OK;
+}
+
+}  // namespace transcript
+
+// ---- communicator (comm.cu) -------------------------------------------------------------------
+// all-gather `bytes` per rank from src into dst ([rank][bytes]) on ctx->stream; a plain device copy
+// without a communicator
+int comm_allgather(mpvss_ctx* ctx, const void* src, void* dst, size_t bytes);
+void comm_release(mpvss_ctx* ctx);

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MPVSS_B200_LIB") or os.path.join(_HERE, "libmpvss_b20
 GROUP_MODP, GROUP_SECP256K1, GROUP_RISTRETTO255 = 0, 1, 2
 GROUP_IDS = {"modp": GROUP_MODP, "secp256k1": GROUP_SECP256K1, "ristretto255": GROUP_RISTRETTO255}
 GEN_MAIN, GEN_SUBGROUP = 0, 1
-OK, ERR_CUDA, ERR_ARG, ERR_ENCODING, ERR_UNSUPPORTED, ERR_NOT_INVERTIBLE = 0, -1, -2, -3, -4, -5
+OK, ERR_CUDA, ERR_ARG, ERR_ENCODING, ERR_UNSUPPORTED, ERR_NOT_INVERTIBLE, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _i64p = ctypes.POINTER(ctypes.c_int64)
@@ -33,11 +33,13 @@ SIGNATURES = {
     "mpvss_scalar_bytes": (_sz, [_ctxp]),
     "mpvss_last_kernel_ms": (ctypes.c_float, [_ctxp]),
     "mpvss_last_kernel_launches": (ctypes.c_int, [_ctxp]),
+    "mpvss_last_horner_products": (ctypes.c_uint64, [_ctxp, ctypes.c_int]),
     "mpvss_last_phase_ms": (ctypes.c_float, [_ctxp, ctypes.c_int]),
     "mpvss_batch_exp": (ctypes.c_int, [_ctxp, _u8p, _sz, _u8p, _sz, _u8p]),
     "mpvss_fixed_base_exp": (ctypes.c_int, [_ctxp, ctypes.c_int, _u8p, _sz, _u8p]),
     "mpvss_batch_mul": (ctypes.c_int, [_ctxp, _u8p, _u8p, _sz, _u8p]),
     "mpvss_poly_eval_exp": (ctypes.c_int, [_ctxp, _u8p, _sz, _i64p, _sz, _u8p]),
+    "mpvss_scalar_poly_eval": (ctypes.c_int, [_ctxp, _u8p, _sz, _i64p, _sz, _u8p]),
     "mpvss_dleq_verify_commit": (ctypes.c_int, [_ctxp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz, _sz, _u8p, _u8p]),
     "mpvss_dleq_prove_commit": (ctypes.c_int, [_ctxp, _u8p, _u8p, _u8p, _sz, _u8p, _u8p]),
     "mpvss_multi_exp": (ctypes.c_int, [_ctxp, _u8p, _u8p, _sz, _u8p]),
@@ -45,14 +47,19 @@ SIGNATURES = {
                                                  _u8p, _u8p, _u8p, _u8p]),
     "mpvss_verify_distribution_stage": (ctypes.c_int, [_ctxp, _sz, _sz, _u8p, _i64p, _u8p, _u8p, _u8p, _u8p]),
     "mpvss_verify_distribution_run": (ctypes.c_int, [_ctxp, _intp, _u8p, _u8p, _u8p, _u8p]),
-    "mpvss_verify_distribution_compute": (ctypes.c_int, [_ctxp, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "mpvss_transcript_check": (ctypes.c_int, [_ctxp, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _intp, _u8p]),
     "mpvss_distribute": (ctypes.c_int, [_ctxp, _sz, _sz, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p,
                                         _u8p, _u8p]),
     "mpvss_extract_shares": (ctypes.c_int, [_ctxp, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _intp]),
     "mpvss_verify_shares": (ctypes.c_int, [_ctxp, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _intp]),
     "mpvss_reconstruct": (ctypes.c_int, [_ctxp, _sz, _i64p, _u8p, _u8p, _u8p, _u8p]),
+    "mpvss_comm_unique_id": (ctypes.c_int, [_u8p, _sz]),
+    "mpvss_comm_init": (ctypes.c_int, [_ctxp, _u8p, _sz, ctypes.c_int, ctypes.c_int]),
+    "mpvss_comm_destroy": (ctypes.c_int, [_ctxp]),
+    "mpvss_comm_size": (ctypes.c_int, [_ctxp]),
+    "mpvss_comm_rank": (ctypes.c_int, [_ctxp]),
+    "mpvss_transcript_digest": (ctypes.c_int, [ctypes.c_int, _u8p, _sz, ctypes.c_int, _u8p]),
 }
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -88,6 +95,25 @@ def buf(data=None, size=None):
 
 def ptr(b):
     return ctypes.cast(b, _u8p) if b is not None else None
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the bytes to the other ranks)."""
+    b = buf(size=COMM_ID_BYTES)
+    st = load().mpvss_comm_unique_id(ptr(b), COMM_ID_BYTES)
+    if st != OK:
+        raise MpvssError(st, "mpvss_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(b)
+
+
+def transcript_digest(group: str, gathered_rows: bytes, n_total: int, nranks: int) -> bytes:
+    """SHA-256 of the framed transcript rows in participant order, from the all-gather layout
+    [rank][ceil(n_total / nranks)][4 x (8 + element bytes)] (host only: needs no device)."""
+    out = buf(size=32)
+    st = load().mpvss_transcript_digest(GROUP_IDS[group], ptr(buf(gathered_rows)), n_total, nranks, ptr(out))
+    if st != OK:
+        raise MpvssError(st, "mpvss_transcript_digest: bad arguments")
+    return bytes(out)
 
 
 class Context:
@@ -128,6 +154,25 @@ class Context:
 
     def last_phase_ms(self, phase):
         return float(self.lib.mpvss_last_phase_ms(self.h, phase))
+
+    def last_horner_products(self):
+        """(squarings, multiplications) executed by the last X_i launch on this context"""
+        return (int(self.lib.mpvss_last_horner_products(self.h, 0)), int(self.lib.mpvss_last_horner_products(self.h, 1)))
+
+    # ---- multi-GPU: one context per GPU, joined by an NCCL communicator inside the library ----
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        self.check(self.lib.mpvss_comm_init(self.h, ptr(buf(unique_id)), len(unique_id), nranks, rank))
+
+    def comm_destroy(self):
+        self.check(self.lib.mpvss_comm_destroy(self.h))
+
+    @property
+    def comm_size(self):
+        return int(self.lib.mpvss_comm_size(self.h))
+
+    @property
+    def comm_rank(self):
+        return int(self.lib.mpvss_comm_rank(self.h))
 
     @property
     def last_kernel_launches(self):

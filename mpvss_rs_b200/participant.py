@@ -150,6 +150,20 @@ class Group:
                                                         len(commitments), pos, n, ptr(out)))
         return c.dec_elems(out, n)
 
+    def scalar_poly_eval(self, coeffs, positions):
+        """Polynomial::get_value(i) % order for every position (polynomial.rs:50-58, participant.rs:202)."""
+        c, n = self.codec, len(positions)
+        out = buf(size=n * c.sb)
+        self.ctx.check(self.ctx.lib.mpvss_scalar_poly_eval(self.ctx.h, ptr(buf(c.enc_scalars(coeffs))), len(coeffs),
+                                                           (ctypes.c_int64 * n)(*positions), n, ptr(out)))
+        return c.dec_scalars(out, n)
+
+    def join(self, rank, world, dist=None):
+        """Make this group's context one rank of a multi-GPU communicator (sharding.join): afterwards
+        Participant.distribute_secret / verify_distribution_shares on it are collective calls."""
+        from .sharding import join
+        join(self.ctx, rank, world, dist)
+
     def dleq_verify_commit(self, g1, h1s, g2s, h2s, rs, cs):
         c, n = self.codec, len(rs)
         shared = not isinstance(cs, (list, tuple))
@@ -257,7 +271,7 @@ class Participant:
         pos, ys, rs = flat
         n, t = len(pos), len(box.commitments)
         ok = ctypes.c_int(0)
-        want = trace is not None
+        want = trace is not None and g.ctx.comm_size <= 1   # per-share values are not gathered across ranks
         x, a1, a2 = (buf(size=n * c.eb) if want else None for _ in range(3))
         dig = buf(size=32)
         g.ctx.check(g.ctx.lib.mpvss_verify_distribution(
@@ -265,7 +279,9 @@ class Participant:
             ptr(buf(c.enc_elems(box.publickeys))), ptr(buf(c.enc_elems(ys))), ptr(buf(c.enc_scalars(rs))),
             ptr(buf(c.enc_scalar(box.challenge))), ctypes.byref(ok), ptr(x), ptr(a1), ptr(a2), ptr(dig)))
         if want:
-            trace.update(X=c.dec_elems(x, n), a1=c.dec_elems(a1, n), a2=c.dec_elems(a2, n), digest=bytes(dig))
+            trace.update(X=c.dec_elems(x, n), a1=c.dec_elems(a1, n), a2=c.dec_elems(a2, n))
+        if trace is not None:
+            trace["digest"] = bytes(dig)
         return bool(ok.value)
 
     # -- extract_secret_share: participant.rs:294-353 / 1282-1338 / 1725-1781 --

@@ -32,6 +32,7 @@ typedef struct {
 } job_t;
 
 static void put(const BIGNUM* v, uint8_t* out) { BN_bn2binpad(v, out, EB); }
+static void put_pt(const EC_GROUP* g, const EC_POINT* p, uint8_t* out, BN_CTX* ctx);
 
 static void* worker(void* arg) {
   job_t* J = (job_t*)arg;
@@ -104,6 +105,70 @@ int cpu_modp_verify(const uint8_t* q, const uint8_t* commitments, size_t t, cons
   return 0;
 }
 
+
+/* out[i] = base[i]^exp[i] mod q (base_stride = 0: one shared base), i % nthreads per thread.  Used to
+ * synthesise a box for the CPU reference arm without touching the GPU library. */
+typedef struct {
+  const uint8_t *q, *base, *exp;
+  size_t base_stride, n, first, stride;
+  uint8_t* out;
+} ejob_t;
+static void* eworker(void* arg) {
+  ejob_t* J = (ejob_t*)arg;
+  BN_CTX* ctx = BN_CTX_new();
+  BIGNUM *q = BN_bin2bn(J->q, EB, NULL), *b = BN_new(), *e = BN_new(), *r = BN_new();
+  BN_MONT_CTX* mont = BN_MONT_CTX_new();
+  BN_MONT_CTX_set(mont, q, ctx);
+  for (size_t i = J->first; i < J->n; i += J->stride) {
+    BN_bin2bn(J->base + i * J->base_stride, EB, b);
+    BN_bin2bn(J->exp + i * EB, EB, e);
+    BN_mod_exp_mont(r, b, e, q, ctx, mont);
+    put(r, J->out + i * EB);
+  }
+  BN_free(q); BN_free(b); BN_free(e); BN_free(r);
+  BN_MONT_CTX_free(mont);
+  BN_CTX_free(ctx);
+  return NULL;
+}
+int cpu_modp_exp(const uint8_t* q, const uint8_t* base, size_t base_stride, const uint8_t* exp, size_t n, int nthreads,
+                 uint8_t* out) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = (int)n;
+  pthread_t* th = malloc(nthreads * sizeof(pthread_t));
+  ejob_t* jobs = malloc(nthreads * sizeof(ejob_t));
+  for (int k = 0; k < nthreads; ++k) {
+    ejob_t j = {q, base, exp, base_stride, n, (size_t)k, (size_t)nthreads, out};
+    jobs[k] = j;
+    pthread_create(&th[k], NULL, eworker, &jobs[k]);
+  }
+  for (int k = 0; k < nthreads; ++k) pthread_join(th[k], NULL);
+  free(th);
+  free(jobs);
+  return 0;
+}
+
+/* out[i] = scalar[i] * P[i] on secp256k1 (points == NULL: the generator), single thread: box synthesis */
+int cpu_secp_mul(const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out) {
+  BN_CTX* ctx = BN_CTX_new();
+  EC_GROUP* g = EC_GROUP_new_by_curve_name(NID_secp256k1);
+  EC_POINT *p = EC_POINT_new(g), *r = EC_POINT_new(g);
+  BIGNUM* k = BN_new();
+  for (size_t i = 0; i < n; ++i) {
+    BN_bin2bn(scalars + i * 32, 32, k);
+    if (points) {
+      EC_POINT_oct2point(g, p, points + i * 33, 33, ctx);
+      EC_POINT_mul(g, r, NULL, p, k, ctx);
+    } else {
+      EC_POINT_mul(g, r, k, NULL, NULL, ctx);
+    }
+    put_pt(g, r, out + i * 33, ctx);
+  }
+  BN_free(k);
+  EC_POINT_free(p); EC_POINT_free(r);
+  EC_GROUP_free(g);
+  BN_CTX_free(ctx);
+  return 0;
+}
 
 /* ---- secp256k1 (OpenSSL proxy for k256 0.13, Cargo.toml:24) -------------------------------
  * schedule 0 (reference): X_i = sum_j (i^j mod n) * C_j, t variable-base scalar multiplications

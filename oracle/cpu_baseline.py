@@ -25,6 +25,10 @@ def load():
     lib.cpu_secp_verify.argtypes = [p, sz, ctypes.POINTER(ctypes.c_int64), p, p, p, p, sz, ctypes.c_int, ctypes.c_int,
                                     p, p, p]
     lib.cpu_secp_verify.restype = ctypes.c_int
+    lib.cpu_modp_exp.argtypes = [p, p, sz, p, sz, ctypes.c_int, p]
+    lib.cpu_modp_exp.restype = ctypes.c_int
+    lib.cpu_secp_mul.argtypes = [p, p, sz, p]
+    lib.cpu_secp_mul.restype = ctypes.c_int
     return lib
 
 
@@ -54,3 +58,24 @@ def secp_verify(commitments, positions, pks, ys, rs, c, nthreads=1, schedule=0):
                         s, nthreads, schedule, xo, a1o, a2o)
     dec = lambda b: [b.raw[i * 33:(i + 1) * 33] for i in range(s)]
     return dec(xo), dec(a1o), dec(a2o)
+
+
+def modp_exp(q, bases, exps, nthreads=1):
+    """[b^e mod q]; `bases` may be one int (shared base)."""
+    lib = load()
+    n = len(exps)
+    shared = isinstance(bases, int)
+    out = ctypes.create_string_buffer(256 * n)
+    lib.cpu_modp_exp(be(q), be(bases) if shared else b"".join(be(v) for v in bases), 0 if shared else 256,
+                     b"".join(be(v) for v in exps), n, nthreads, out)
+    return [int.from_bytes(out.raw[i * 256:(i + 1) * 256], "big") for i in range(n)]
+
+
+def secp_mul(points, scalars):
+    """[k * P]; points None = the generator.  33-byte encodings."""
+    lib = load()
+    n = len(scalars)
+    out = ctypes.create_string_buffer(33 * n)
+    lib.cpu_secp_mul(None if points is None else b"".join(points), b"".join(int(k).to_bytes(32, "big") for k in scalars),
+                     n, out)
+    return [out.raw[i * 33:(i + 1) * 33] for i in range(n)]

@@ -36,21 +36,27 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
     default: return -1;            \
   }
 
-extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
-                               uint32_t n, uint32_t ndigits, uint32_t* out, const uint32_t* skip) {
+extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint16_t* ops,
+                               uint32_t n, uint32_t nops, uint32_t* out) {
   const bool np1 = consts[modp::C_NP] == 1u;
-  modp::HornerArgs A{consts, cm, pos, nullptr, nullptr, nullptr, out, t, n, ndigits};
+  modp::HornerArgs A{consts, cm, ops, nullptr, nullptr, out, t, n, nops};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, ndigits, skip ? skip[w] : 0u);
-                            else modp::horner_body<T, false>(A, w, s, ndigits, skip ? skip[w] : 0u); }));
+                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, nops);
+                            else modp::horner_body<T, false>(A, w, s, nops); }));
   return 0;
 }
 
-extern "C" int emu_modp_horner2(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint32_t* pos,
-                                uint32_t n, const uint32_t* nd, uint32_t* out0, uint32_t* out1) {
-  modp::Horner2Args A{consts, cm, pos, nullptr, nullptr, nullptr, out0, out1, t, n, (t + 1) / 2};
-  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner2_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { modp::horner2_body<T>(A, w, s, nd[0], 0u); }));
+extern "C" int emu_modp_frames(const uint32_t* x, const uint32_t* y, const uint32_t* a1, const uint32_t* a2, uint32_t n,
+                               uint8_t* out) {
+  modp::FrameArgs A{x, y, a1, a2, out, n};
+  for (uint32_t i = 0; i < 4 * n; ++i) modp::frame_body(A, i);
+  return 0;
+}
+
+extern "C" int emu_modp_resp(const uint32_t* order, const uint32_t* alpha, uint32_t alpha_stride, const uint32_t* w,
+                             const uint32_t* c, uint32_t c_stride, uint32_t n, uint32_t* out) {
+  modp::RespArgs A{order, alpha, w, c, out, n, alpha_stride, c_stride};
+  for (uint32_t i = 0; i < n; ++i) modp::resp_body(A, i);
   return 0;
 }
 

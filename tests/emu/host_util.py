@@ -10,7 +10,7 @@ _p, _s = ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t
 
 def build():
     ni = os.path.join(CSRC, "sha256_ni.cpp")
-    deps = [SRC, ni, os.path.join(CSRC, "bigint.h"), os.path.join(CSRC, "sha2.h")]
+    deps = [SRC, ni, os.path.join(CSRC, "bigint.h"), os.path.join(CSRC, "sha2.h"), os.path.join(CSRC, "modp_chain.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         obj = os.path.join(HERE, "sha256_ni.o")
         subprocess.check_call(["g++", "-O2", "-fPIC", "-msha", "-msse4.1", "-mssse3", "-c", ni, "-o", obj])
@@ -21,6 +21,8 @@ def build():
     L.hc_modinv.argtypes = [_p, _s, _p, _s, _p, _s]
     L.hc_sha256.argtypes = [_p, _s, _s, _p]
     L.hc_sha512.argtypes = [_p, _s, _s, _p]
+    L.hc_chain_ops.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint16),
+                               ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
     return L
 
 

@@ -104,31 +104,129 @@ def test_split_sqr_edge_patterns(lib, modulus):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == x, i
 
 
+def _chain_ops(hl, p, limit=1 << 12):
+    """ops of one Horner step for position p from the product's host code (modp_chain.h)"""
+    import ctypes
+    ops = (ctypes.c_uint16 * 64)()
+    sq, ml = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    n = hl.hc_chain_ops(p, limit, ops, ctypes.byref(sq), ctypes.byref(ml))
+    assert n > 0, p
+    return list(ops[:n]), sq.value, ml.value
+
+
+def _run_ops(ops, x, cj, mul=lambda a, b: a * b % Q):
+    """execute an op list the way modp::horner_body does, on Python integers"""
+    slot, acc = [None] * 6, x
+    for op in ops:
+        sv, a, b = (op >> 8) & 15, (op >> 4) & 15, op & 15
+        if sv:
+            slot[sv - 1] = acc
+        if a:
+            acc = slot[a - 1]
+        acc = mul(acc, 1 if b == 14 else cj if b == 15 else slot[b])
+    return acc
+
+
+def test_addition_chain_ops_compute_x_to_the_p_times_c():
+    """Host-side chain builder (power tree below the limit, sliding windows above it): every op list
+    evaluates acc^p * C_j within the kernel's 6 slots and 48 ops; products are counted."""
+    import host_util
+    hl = host_util.build()
+    rng = random.Random(5)
+    x, cj = rng.randrange(2, Q), rng.randrange(2, Q)
+    ps = list(range(1, 300)) + [4095, 4096, 4097, 65535, 65536, 131071, 131072, 131073, (1 << 31) - 1, 0x6DB6DB6D,
+                                0x55555555, 0x7FFFFFFE] + [rng.randrange(1, 1 << 17) for _ in range(300)]
+    total_len = 0
+    for p in ps:
+        for limit in (1 << 12, 1 << 17):
+            ops, sq, ml = _chain_ops(hl, p, limit)
+            assert len(ops) <= 48 and sq + ml == len(ops) and ops[-1] == 15
+            assert _run_ops(ops, x, cj) == pow(x, p, Q) * cj % Q, (p, limit)
+            if limit == 1 << 17 and p <= 4096:
+                total_len += len(ops) - 1
+    # the power tree is at least as short as the fixed 2-bit windows it replaces (2 + 3 (d - 1) products)
+    for p in (1, 2, 3, 4, 15, 255, 1000, 4095):
+        d = 1
+        while p >> (2 * d):
+            d += 1
+        assert len(_chain_ops(hl, p, 1 << 17)[0]) - 1 <= 2 + 3 * (d - 1)
+
+
 @pytest.mark.parametrize("tpi", [4, 8, 16])
 def test_horner_kernel_equals_reference_schedule(lib, tpi):
+    """X_i = prod_j C_j^(i^j) by the chain kernel == the reference's t full exponentiations
+    (participant.rs:423-434), every lane group of a warp running a different chain of equal length."""
+    import host_util
+    hl = host_util.build()
     C = eu.consts_block(Q)
     rng = random.Random(tpi)
-    t = 5
+    t = 4
     comm = [pow(4, rng.randrange(Q - 1), Q) for _ in range(t)]
     cm = np.concatenate([eu.to_limbs(c * R % Q) for c in comm])
-    positions = [1, 2, 3, 5, 11, 14, 15, 64, 255][: 9 if tpi != 4 else 9]
-    nd = 4
-    pos = np.array(positions, dtype=np.uint32)
-    n = len(positions)
-    out = np.zeros(64 * n, dtype=np.uint32)
-    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, nd, eu.P(out), None) == 0
-    for i in range(n):
-        assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
-    # block-uniform skipping of window multiplications whose digit is zero for the whole warp
     gpw = 32 // tpi
-    positions = [64 + k for k in range(gpw)] + [80 + 16 * 0 + k for k in range(gpw)]   # digits (1,0,0,x), (1,1,0,x)
-    pos = np.array(positions, dtype=np.uint32)
+    positions = [1, 2, 3, 5, 11, 14, 15, 64, 255, 4096, 70000, 200001][:max(gpw, 4) + 2]
+    lists = [_chain_ops(hl, p)[0] for p in positions]
+    nops = max(len(l) for l in lists)
+    ops = np.full(48 * len(positions), 14, dtype=np.uint16)          # padding: products by one
+    for i, l in enumerate(lists):
+        ops[48 * i:48 * i + len(l) - 1] = l[:-1]
+        ops[48 * i + nops - 1] = 15                                  # the C_j product closes the step
     n = len(positions)
-    skip = np.array([0b0110 if gpw <= 4 else 0b0100, 0b0010 if gpw <= 4 else 0b0000], dtype=np.uint32)
     out = np.zeros(64 * n, dtype=np.uint32)
-    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, eu.P(pos), n, 4, eu.P(out), eu.P(skip)) == 0
+    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, ops.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint16)),
+                               n, nops, eu.P(out)) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
+
+
+def test_frame_kernel_minimal_big_endian():
+    """Transcript rows from the device: len_u64_be || minimal big-endian bytes (dleq.rs:58-61,
+    modp.rs:150-152), including short values and zero."""
+    lib = eu.build()
+    rng = random.Random(9)
+    vals = [[rng.randrange(Q) for _ in range(4)] for _ in range(5)]
+    vals[1] = [0, 1, 255, 256]
+    vals[2] = [(1 << 2040) - 1, 1 << 2040, (1 << 2047), Q - 1]
+    vals[3] = [rng.getrandbits(b) for b in (2039, 1000, 33, 8)]
+    n = len(vals)
+    cols = [np.concatenate([eu.to_limbs(v[k]) for v in vals]) for k in range(4)]
+    out = np.zeros(n * 4 * 264, dtype=np.uint8)
+    import ctypes
+    assert lib.emu_modp_frames(eu.P(cols[0]), eu.P(cols[1]), eu.P(cols[2]), eu.P(cols[3]), n,
+                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))) == 0
+    raw = out.tobytes()
+    for j in range(n):
+        for k in range(4):
+            fr = raw[(4 * j + k) * 264:(4 * j + k + 1) * 264]
+            body = G.element_to_bytes(vals[j][k])
+            assert fr[:8] == len(body).to_bytes(8, "big") and fr[8:8 + len(body)] == body
+            assert not any(fr[8 + len(body):])
+
+
+def test_response_kernel(lib):
+    """r = (w - (alpha * c mod (q-1))) mod (q-1) with the reference's scalar_sub (modp.rs:180-192)."""
+    rng = random.Random(17)
+    order = Q - 1
+    n = 12
+    alpha = [rng.randrange(order) for _ in range(n)]
+    w = [rng.randrange(Q) for _ in range(n)]
+    c = [rng.getrandbits(256) for _ in range(n)]
+    alpha[0], w[0], c[0] = order - 1, 0, (1 << 256) - 1
+    alpha[1], w[1] = (1 << 2048) - 1, (1 << 2048) - 1          # unreduced inputs
+    alpha[2], c[2] = 0, 5
+    w[3] = order
+    c[4] = 0
+    A = np.concatenate([eu.to_limbs(x) for x in alpha])
+    W = np.concatenate([eu.to_limbs(x) for x in w])
+    Cc = np.concatenate([eu.to_limbs(x) for x in c])
+    out = np.zeros(64 * n, dtype=np.uint32)
+    assert lib.emu_modp_resp(eu.P(eu.to_limbs(order)), eu.P(A), 64, eu.P(W), eu.P(Cc), 64, n, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == G.scalar_sub(w[i], G.scalar_mul(alpha[i], c[i])) % order, i
+    # one shared challenge (distribute_secret)
+    assert lib.emu_modp_resp(eu.P(eu.to_limbs(order)), eu.P(A), 64, eu.P(W), eu.P(Cc), 0, n, eu.P(out)) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == (w[i] - alpha[i] * c[0]) % order, i
 
 
 @pytest.mark.parametrize("tpi", [8, 16])

@@ -235,9 +235,9 @@ def test_dleq_and_pvss_wrappers(modp_group):
     assert m.PVSS(modp_group).verify_distribution_shares(box) is True
 
 
-def test_overlap_and_dual_modes_agree(modp_group):
+def test_overlap_modes_and_lane_counts_agree(modp_group):
     """Every placement of the X-independent a2 launch (before the Horner launch, beside it, as persistent
-    one-warp CTAs in the idle warp slots) and every chunking mode yields the same X, a1, a2 and verdict."""
+    one-warp CTAs in the idle warp slots) and every lane count per value yields the same X, a1, a2."""
     import mpvss_rs_b200 as m
     n, t = 1024, 683
     sks, co, ws = _setup(n, t, 5)
@@ -246,14 +246,14 @@ def test_overlap_and_dual_modes_agree(modp_group):
     box = dealer.distribute_secret(SECRET, pks, t, coeffs=co, witnesses=ws)
     ref = None
     try:
-        for key, values in (("modp_overlap", (0, 2, 3)), ("modp_dual", (1, 2, 0))):
+        for key, values in (("modp_overlap", (0, 2, 3)), ("modp_tpi", (4, 16, 8))):
             for v in values:
                 modp_group.ctx.set_int(key, v)
                 tr = {}
                 assert dealer.verify_distribution_shares(box, trace=tr) is True, (key, v)
-                cur = (tr["X"], tr["a1"], tr["a2"])
+                cur = (tr["X"], tr["a1"], tr["a2"], tr["digest"])
                 ref = ref or cur
                 assert cur == ref, (key, v)
     finally:
         modp_group.ctx.set_int("modp_overlap", 3)
-        modp_group.ctx.set_int("modp_dual", 0)
+        modp_group.ctx.set_int("modp_tpi", 8)

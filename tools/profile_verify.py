@@ -10,13 +10,10 @@ ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--t", type=int, default=128)
 ap.add_argument("--tpi", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--dual", type=int, default=-1)
 a = ap.parse_args()
 g = m.Group("modp")
 if a.tpi:
     g.ctx.set_int("modp_tpi", a.tpi)
-if a.dual >= 0:
-    g.ctx.set_int("modp_dual", a.dual)
 box = bench.build_box(g, a.n, a.t, 7)
 ok = ctypes.c_int(0)
 for _ in range(a.reps):

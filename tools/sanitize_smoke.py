@@ -18,7 +18,7 @@ for name in ("modp", "secp256k1", "ristretto255"):
     assert all(d.verify_shares(sbs, box, pks))
     assert d.reconstruct(sbs[:t], box) == 424242
     if name == "modp":
-        for mode in (1, 2):
-            g.ctx.set_int("modp_dual", mode)
+        for tpi in (4, 16, 8):
+            g.ctx.set_int("modp_tpi", tpi)
             assert d.verify_distribution_shares(box)
     print(name, "ok")
