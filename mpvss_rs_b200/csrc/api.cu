@@ -111,6 +111,7 @@ void mpvss_ctx_destroy(mpvss_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_chunk)
     if (e) cudaEventDestroy(e);
   ctx->ec_consts.release();
+  ctx->ec_comb.release();
   for (auto& b : ctx->scratch) b.release();
   for (auto& b : ctx->pinned) b.release();
   for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_mid, ctx->ev_h0, ctx->ev_h1, ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1]})
@@ -133,7 +134,7 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     return MPVSS_OK;
   }
   if (std::string(key) == "ec_threads") {
-    if (value < 32) return mpvss_fail(ctx, MPVSS_ERR_ARG, "ec_threads must be >= 32");
+    if (value != 0 && value < 32) return mpvss_fail(ctx, MPVSS_ERR_ARG, "ec_threads must be 0 (auto) or >= 32");
     ctx->ec_threads = (size_t)value;
     return MPVSS_OK;
   }

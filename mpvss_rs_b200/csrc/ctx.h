@@ -81,7 +81,8 @@ struct mpvss_ctx {
   bool validate = false;     // range / subgroup check of ModpGroup elements entering the verify calls
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----
-  size_t ec_threads = 131072;   // target thread count of the chunked Horner launch ("ec_threads")
+  size_t ec_threads = 0;        // target thread count of the chunked Horner launch ("ec_threads"); 0 = one full wave
+  DevBuf ec_comb;               // fixed-base table of the generator (ec::COMB_WORDS words)
   DevBuf ec_consts;             // secp::Consts / rist::Consts
   big::Int ec_order;            // group order (scalar field modulus)
   std::vector<uint8_t> ec_gen;  // encoded generator (both generators of the trait are this point)
@@ -92,7 +93,9 @@ struct mpvss_ctx {
   uint32_t v_rwin = 0, v_cwin = 0;
   size_t v_np = 0;  // padded instance count of the Horner launch
   uint32_t v_nops_max = 1;  // products per Horner step of the longest staged addition chain
-  std::vector<uint8_t> v_challenge, v_y_host;
+  std::vector<uint8_t> v_challenge;
+  std::vector<uint32_t> v_hpos;  // staged positions (elliptic-curve groups: roofline accounting)
+  size_t ec_chunks = 1;          // chunks per position of the last elliptic-curve Horner launch
   const uint32_t* v_comb = nullptr;  // fixed-base table of g for a1 = g^r * X^c
   DevBuf v_slot, v_nd, v_ops, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2, v_st;
   // framed transcript rows (dleq.rs:58-61, 87-99): per participant 4 x (u64 BE length || bytes), written by the

@@ -48,8 +48,17 @@ void put_mont(uint32_t* dst, const big::Int& v, const big::Int& m) {
   put8(dst, big::mulmod(big::mod(v, m), big::mod(R, m), m));
 }
 
+// Field multiplications / squarings of the point operations as the kernels execute them (secp.cuh /
+// rist.cuh); used only to count the algorithmic work of a Horner launch for the roofline figure.
+struct OpCost {
+  uint32_t m, s;
+};
 struct SecpTraits {
   using Cv = secp::SecpCurve;
+  // dbl-2009-l 2M+5S; add-2007-bl 11M+5S; madd-2007-bl 7M+4S; small_mul_iso set-up (2P, 3P, two rescalings,
+  // scale, final Z product) 16M+9S; the first window addition lands on the identity and is free
+  static constexpr OpCost DBL{2, 5}, DBL_NOT{2, 5}, ADD{11, 5}, MADD{7, 4}, WIN_ADD{7, 4}, SMALL_FIXED{16, 9};
+  static constexpr bool TOP_ADD_FREE = true;
   static constexpr size_t EB = 33;
   static constexpr bool SCALAR_BE = true;
   static big::Int order() { return hex_int("fffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141"); }
@@ -86,6 +95,10 @@ struct SecpTraits {
 
 struct RistTraits {
   using Cv = rist::RistCurve;
+  // dbl-2008-hwcd 4M+4S (3M+4S without T); add-2008-hwcd-3 9M; adding an affine commitment 10M;
+  // small_mul_ext set-up (2P, 3P) 13M+4S
+  static constexpr OpCost DBL{4, 4}, DBL_NOT{3, 4}, ADD{9, 0}, MADD{10, 0}, WIN_ADD{9, 0}, SMALL_FIXED{13, 4};
+  static constexpr bool TOP_ADD_FREE = false;
   static constexpr size_t EB = 32;
   static constexpr bool SCALAR_BE = false;
   static big::Int order() { return hex_int("1000000000000000000000000000000014def9dea2f79cd65812631a5cf5d3ed"); }
@@ -188,15 +201,27 @@ struct Ec {
     T::generator(ctx->ec_gen.data());
     MPVSS_TRY(h2d(ctx, ctx->ec_consts, &C, sizeof C));
     MPVSS_TRY(h2d(ctx, ctx->gens, ctx->ec_gen.data(), EB));
+    // fixed-base table of the generator (both generators of the trait are this point): 960 affine multiples
+    MPVSS_CUDA(ctx, ctx->ec_comb.ensure(ec::COMB_WORDS * 4));
+    ec::CombArgs<Cv> CA{K(ctx), ctx->gens.as<uint8_t>(), ctx->ec_comb.as<uint32_t>()};
+    MPVSS_CUDA(ctx, ec::launch_comb_build<Cv>(CA, ctx->stream));
     return sync(ctx);
   }
 
   // device-pointer launch helpers -----------------------------------------------------------
   static int dev_exp2(mpvss_ctx* ctx, const uint8_t* b1, uint32_t b1s, const uint32_t* e1, const uint8_t* b2,
                       uint32_t b2s, const uint32_t* e2, uint32_t e2s, size_t n, uint8_t* out, Point* out_jac,
-                      uint32_t* status, cudaStream_t stream = nullptr) {
-    ec::Exp2Args<Cv> A{K(ctx), b1, e1, b2, e2, out, out_jac, status, (uint32_t)n, b1s, 8, b2s, e2s, 0};
+                      uint32_t* status, cudaStream_t stream = nullptr, bool b1_is_generator = false) {
+    ec::Exp2Args<Cv> A{K(ctx), b1, e1, b2, e2, out, out_jac, status, (uint32_t)n, b1s, 8, b2s, e2s,
+                       b1_is_generator ? ctx->ec_comb.as<uint32_t>() : nullptr};
     MPVSS_CUDA(ctx, ec::launch_exp2<Cv>(A, stream ? stream : ctx->stream));
+    timing_launch(ctx);
+    return MPVSS_OK;
+  }
+  // out[i] = e[i] * G from the fixed-base table (staged through shared memory by the kernel)
+  static int dev_fixed(mpvss_ctx* ctx, const uint32_t* e, size_t n, uint8_t* out) {
+    ec::FixedArgs<Cv> A{K(ctx), ctx->ec_comb.as<uint32_t>(), e, out, (uint32_t)n};
+    MPVSS_CUDA(ctx, ec::launch_fixed<Cv>(A, ctx->stream));
     timing_launch(ctx);
     return MPVSS_OK;
   }
@@ -229,8 +254,12 @@ struct Ec {
     ec::DecodeArgs<Cv> D{K(ctx), comm, cxy.as<uint32_t>(), cst.as<uint32_t>(), (uint32_t)t};
     MPVSS_CUDA(ctx, ec::launch_decode<Cv>(D, ctx->stream));
     timing_launch(ctx);
-    // enough chunks to fill the chip (ctx->ec_threads threads), at least 16 coefficients per chunk
-    size_t Kc = std::max<size_t>(1, std::min<size_t>(ctx->ec_threads / std::max<size_t>(n, 1), std::max<size_t>(1, t / 16)));
+    // Enough chunks to fill the chip ONCE: the Horner kernel keeps 4 CTAs of 128 threads resident per SM, and
+    // every extra chunk costs a full scalar multiplication, so the thread count is the largest multiple of
+    // n that still fits one wave (148 x 4 x 128 = 75776 threads; 131072 threads, round 1, ran 1.73 waves and
+    // twice the chunk scalings).  "ec_threads" overrides the target; at least 16 coefficients per chunk.
+    const size_t target = ctx->ec_threads ? ctx->ec_threads : (size_t)ctx->sm_count * ec::HORNER_CTAS_PER_SM * 128;
+    size_t Kc = std::max<size_t>(1, std::min<size_t>(target / std::max<size_t>(n, 1), std::max<size_t>(1, t / 16)));
     size_t B = (t + Kc - 1) / Kc;
     Kc = (t + B - 1) / B;
     MPVSS_CUDA(ctx, part.ensure(Kc * n * sizeof(Point)));
@@ -242,7 +271,34 @@ struct Ec {
                       (uint32_t)(Kc * n)};
     MPVSS_CUDA(ctx, ec::launch_sum<Cv>(S, ctx->stream));
     timing_launch(ctx);
+    ctx->ec_chunks = Kc;
     return MPVSS_OK;
+  }
+  // field products of the Horner + chunk-scaling + chunk-sum launches for these positions (roofline accounting)
+  static void count_horner(mpvss_ctx* ctx, const std::vector<uint32_t>& pos, size_t t) {
+    const uint64_t Kc = ctx->ec_chunks ? ctx->ec_chunks : 1;
+    uint64_t M = 0, S = 0;
+    auto add = [&](OpCost c, uint64_t times) {
+      M += c.m * times;
+      S += c.s * times;
+    };
+    for (uint32_t p : pos) {
+      uint32_t nd = 1, nz = 0;
+      while (nd < 16 && (p >> (2 * nd))) ++nd;
+      for (uint32_t d = 0; d + 1 < nd; ++d) nz += ((p >> (2 * d)) & 3u) != 0;
+      const uint64_t steps = t - Kc;                       // Horner steps of all chunks of this position
+      add(T::SMALL_FIXED, steps);
+      add(T::DBL_NOT, steps * (nd - 1));
+      add(T::DBL, steps * (nd - 1));
+      add(T::WIN_ADD, steps * (nz + (T::TOP_ADD_FREE ? 0 : 1)));
+      add(T::MADD, steps);
+      // chunks 1..K-1: acc <- pos^(kB) * acc, fixed 4-bit windows (7 dbl + 7 add table, 63 x 4 dbl, ~60 adds)
+      add(T::DBL, (Kc - 1) * (7 + 252));
+      add(T::ADD, (Kc - 1) * (7 + 60));
+      add(T::ADD, Kc - 1);                                  // chunk sum
+    }
+    ctx->horner_sqr = S;
+    ctx->horner_mul = M;
   }
 
   static int positions_u32(mpvss_ctx* ctx, const int64_t* positions, size_t n, std::vector<uint32_t>& pos) {
@@ -276,8 +332,19 @@ struct Ec {
     return sync(ctx);
   }
   static int fixed_base_exp(mpvss_ctx* ctx, int generator, const uint8_t* scalars, size_t n, uint8_t* out) {
-    MPVSS_TRY(bad(ctx, generator == MPVSS_GEN_MAIN || generator == MPVSS_GEN_SUBGROUP, "fixed_base_exp: generator"));
-    return batch_exp(ctx, ctx->ec_gen.data(), 0, scalars, n, out);
+    MPVSS_TRY(bad(ctx, (generator == MPVSS_GEN_MAIN || generator == MPVSS_GEN_SUBGROUP) && scalars && out && n > 0,
+                  "fixed_base_exp: bad arguments"));
+    std::vector<uint32_t> e;
+    MPVSS_TRY(scalars_in(ctx, scalars, n, e));
+    DevBuf &de = ctx->buf(1), &dout = ctx->buf(2);
+    MPVSS_TRY(h2d(ctx, de, e.data(), n * 32));
+    MPVSS_CUDA(ctx, dout.ensure(n * EB));
+    timing_begin(ctx);
+    MPVSS_TRY(dev_fixed(ctx, de.as<uint32_t>(), n, dout.as<uint8_t>()));
+    MPVSS_TRY(timing_end(ctx));
+    MPVSS_TRY(d2h(ctx, out, dout, n * EB));
+    MPVSS_CUDA(ctx, cudaMemsetAsync(de.p, 0, de.cap, ctx->stream));  // private keys / witnesses pass through here
+    return sync(ctx);
   }
   static int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     MPVSS_TRY(bad(ctx, a && b && out && n > 0, "batch_mul: bad arguments"));
@@ -307,6 +374,7 @@ struct Ec {
     timing_begin(ctx);
     MPVSS_TRY(dev_horner(ctx, dc.as<uint8_t>(), t, dp.as<uint32_t>(), n, ctx->buf(3), ctx->buf(4), ctx->buf(5),
                          dout.as<uint8_t>()));
+    count_horner(ctx, pos, t);
     MPVSS_TRY(timing_end(ctx));
     MPVSS_TRY(check_status(ctx, ctx->buf(4), t, "poly_eval_exp (commitments)"));
     MPVSS_TRY(d2h(ctx, out, dout, n * EB));
@@ -332,8 +400,9 @@ struct Ec {
     for (DevBuf* b : {&ds1, &ds2}) MPVSS_CUDA(ctx, b->ensure(n * 4));
     uint32_t cs = c_stride ? 8 : 0;
     timing_begin(ctx);
+    const bool gen = memcmp(g1, ctx->ec_gen.data(), EB) == 0;  // the usual case: fixed-base table
     MPVSS_TRY(dev_exp2(ctx, dg1.as<uint8_t>(), 0, dr.as<uint32_t>(), dh1.as<uint8_t>(), EB, dc.as<uint32_t>(), cs, n,
-                       da1.as<uint8_t>(), nullptr, ds1.as<uint32_t>()));
+                       da1.as<uint8_t>(), nullptr, ds1.as<uint32_t>(), nullptr, gen));
     MPVSS_TRY(dev_exp2(ctx, dg2.as<uint8_t>(), EB, dr.as<uint32_t>(), dh2.as<uint8_t>(), EB, dc.as<uint32_t>(), cs, n,
                        da2.as<uint8_t>(), nullptr, ds2.as<uint32_t>()));
     MPVSS_TRY(timing_end(ctx));
@@ -428,6 +497,7 @@ struct Ec {
     ctx->v_challenge.assign(challenge, challenge + SB);
     ctx->v_n = n;
     ctx->v_t = t;
+    ctx->v_hpos = pos;
     MPVSS_TRY(sync(ctx));
     ctx->v_n_total = n_total;
     return MPVSS_OK;
@@ -448,6 +518,7 @@ struct Ec {
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint8_t>(), t, ctx->v_pos.as<uint32_t>(), n, ctx->v_cm, ctx->v_nd,
                          ctx->buf(12), X));
+    count_horner(ctx, ctx->v_hpos, t);
     // a2 = r*y + c*Y does not depend on X: a small grid (one thread per share) on a side stream, issued
     // after the Horner launches so that it only takes CTA slots they leave free
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
@@ -457,7 +528,7 @@ struct Ec {
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_mid, ctx->stream));
     // a1 = r*g + c*X  (dleq.rs:66-84)
     MPVSS_TRY(dev_exp2(ctx, ctx->gens.as<uint8_t>(), 0, ctx->v_r.as<uint32_t>(), X, EB, ctx->v_c.as<uint32_t>(), 0, n,
-                       ctx->v_a1.as<uint8_t>(), nullptr, st));
+                       ctx->v_a1.as<uint8_t>(), nullptr, st, nullptr, true));
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
     ec::FrameArgs FA{X, ctx->v_y.as<uint8_t>(), ctx->v_a1.as<uint8_t>(), ctx->v_a2.as<uint8_t>(),
                      ctx->v_frames.as<uint8_t>(), (uint32_t)n, (uint32_t)EB};
@@ -573,11 +644,11 @@ struct Ec {
     timing_launch(ctx);
     // C_j = a_j * g ; X_i = p_i * g (dealer shortcut: same element as sum_j i^j C_j) ; Y_i = p_i * y_i ;
     // a1 = w * g ; a2 = w * y_i
-    MPVSS_TRY(dev_exp2(ctx, G, 0, dco.as<uint32_t>(), nullptr, 0, nullptr, 0, t, dC.as<uint8_t>(), nullptr, nullptr));
-    MPVSS_TRY(dev_exp2(ctx, G, 0, dp.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dX.as<uint8_t>(), nullptr, nullptr));
+    MPVSS_TRY(dev_fixed(ctx, dco.as<uint32_t>(), t, dC.as<uint8_t>()));
+    MPVSS_TRY(dev_fixed(ctx, dp.as<uint32_t>(), n, dX.as<uint8_t>()));
     MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dp.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dY.as<uint8_t>(),
                        nullptr, dst.as<uint32_t>()));
-    MPVSS_TRY(dev_exp2(ctx, G, 0, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA1.as<uint8_t>(), nullptr, nullptr));
+    MPVSS_TRY(dev_fixed(ctx, dw.as<uint32_t>(), n, dA1.as<uint8_t>()));
     MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA2.as<uint8_t>(),
                        nullptr, dst.as<uint32_t>() + n));
     MPVSS_TRY(timing_end(ctx));
@@ -640,10 +711,10 @@ struct Ec {
     ec::InvArgs IA{KN(ctx), dsk.as<uint32_t>(), dinv.as<uint32_t>(), dis.as<uint32_t>(), (uint32_t)n};
     MPVSS_CUDA(ctx, ec::launch_inv(IA, ctx->stream));  // 1/sk (participant.rs:1299 / 1742)
     timing_launch(ctx);
-    MPVSS_TRY(dev_exp2(ctx, G, 0, dsk.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dpk.as<uint8_t>(), nullptr, nullptr));
+    MPVSS_TRY(dev_fixed(ctx, dsk.as<uint32_t>(), n, dpk.as<uint8_t>()));
     MPVSS_TRY(dev_exp2(ctx, dY.as<uint8_t>(), EB, dinv.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dS.as<uint8_t>(),
                        nullptr, dst.as<uint32_t>()));
-    MPVSS_TRY(dev_exp2(ctx, G, 0, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA1.as<uint8_t>(), nullptr, nullptr));
+    MPVSS_TRY(dev_fixed(ctx, dw.as<uint32_t>(), n, dA1.as<uint8_t>()));
     MPVSS_TRY(dev_exp2(ctx, dS.as<uint8_t>(), EB, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA2.as<uint8_t>(),
                        nullptr, dst.as<uint32_t>() + n));
     MPVSS_TRY(timing_end(ctx));

@@ -75,27 +75,105 @@ struct Exp2Args {
   typename Cv::Point* out_jac;  // projective results, or nullptr
   uint32_t* status;    // per instance: 0 ok, 1 invalid encoding
   uint32_t n, b1_stride, e1_stride, b2_stride, e2_stride;
-  uint32_t negate_mask_stride;  // unused (reserved)
+  const uint32_t* comb1;  // optional fixed-base table of b1 (COMB_WORDS words, CombArgs layout): e1 * b1 becomes 64
+                          // mixed additions of table entries, no doublings (b1 is then not decoded)
 };
 
+// ---- fixed-base table of the generator ("comb"): T[w][d-1] = (d * 16^w) G, affine, w < 64, d = 1..15 ----
+// 960 entries x 64 bytes = 60 KB: the kernels that use it stage it through shared memory once per CTA
+// (north_star: "fixed-base precomputed tables staged through shared memory"), then every scalar
+// multiplication by G is 64 table lookups and at most 64 mixed additions.
+constexpr int COMB_ENTRIES = 64 * 15;
+constexpr int COMB_WORDS = COMB_ENTRIES * 16;
+
 template <class Cv>
-MP_DEV void exp2_body(const Exp2Args<Cv>& A, uint32_t tid) {
+MP_DEV typename Cv::Point comb_mul(const uint32_t* tbl, const uint32_t* e, const typename Cv::Consts& C) {
+  typename Cv::Point acc = Cv::infinity(C);
+#pragma unroll 1
+  for (int w = 0; w < 64; ++w) {
+    const uint32_t d = nibble(e, w);
+    if (d) {
+      const uint32_t* q = tbl + (size_t)(w * 15 + (d - 1)) * 16;
+      typename Cv::Affine a;
+      a.x = fp256::load(q);
+      a.y = fp256::load(q + 8);
+      a.inf = 0;
+      acc = Cv::madd(acc, a, C);
+    }
+  }
+  return acc;
+}
+
+template <class Cv>
+struct CombArgs {
+  const typename Cv::Consts* C;
+  const uint8_t* gen;  // encoded generator
+  uint32_t* tbl;       // COMB_WORDS words
+};
+// entry (w, d): one thread each, (d << 4w) * G by the generic ladder, then to affine
+template <class Cv>
+MP_DEV void comb_build_body(const CombArgs<Cv>& A, uint32_t tid) {
+  if (tid >= (uint32_t)COMB_ENTRIES) return;
+  using Point = typename Cv::Point;
+  const typename Cv::Consts& C = *A.C;
+  const uint32_t w = tid / 15, d = tid % 15 + 1;
+  typename Cv::Affine g;
+  Cv::decode(g, A.gen, C);
+  uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  e[w >> 3] = d << ((w & 7) * 4);
+  Point tbl[16];
+  Point r = scalar_mul2<Cv>(Cv::from_aff(g, C), e, nullptr, e, tbl, tbl, C);
+  typename Cv::Affine a = Cv::to_affine(r, C);
+  fp256::store(A.tbl + (size_t)tid * 16, a.x);
+  fp256::store(A.tbl + (size_t)tid * 16 + 8, a.y);
+}
+
+// out[i] = e[i] * G from the table (Group::exp with a generator: commitments, public keys, a1 = w * G)
+template <class Cv>
+struct FixedArgs {
+  const typename Cv::Consts* C;
+  const uint32_t* tbl;   // global copy of the table
+  const uint32_t* e;     // n scalars, 8 little-endian limbs each
+  uint8_t* out;          // n encodings
+  uint32_t n;
+};
+template <class Cv>
+MP_DEV void fixed_body(const FixedArgs<Cv>& A, uint32_t tid, const uint32_t* tbl) {
+  if (tid >= A.n) return;
+  uint32_t e[8];
+  for (int i = 0; i < 8; ++i) e[i] = A.e[(size_t)tid * 8 + i];
+  Cv::encode(A.out + (size_t)tid * Cv::EB, comb_mul<Cv>(tbl, e, *A.C), *A.C);
+}
+
+// `comb` = the staged table of b1 (shared memory) when A.comb1 is set, else unused
+template <class Cv>
+MP_DEV void exp2_body(const Exp2Args<Cv>& A, uint32_t tid, const uint32_t* comb = nullptr) {
   if (tid >= A.n) return;
   using Point = typename Cv::Point;
   const typename Cv::Consts& C = *A.C;
   typename Cv::Affine a1, a2;
-  bool ok = Cv::decode(a1, A.b1 + (size_t)tid * A.b1_stride, C);
+  bool ok = true;
+  if (!A.comb1) ok = Cv::decode(a1, A.b1 + (size_t)tid * A.b1_stride, C);
   if (A.b2) ok = Cv::decode(a2, A.b2 + (size_t)tid * A.b2_stride, C) && ok;
   if (A.status) A.status[tid] = ok ? 0u : 1u;
   Point tbl1[16], tbl2[16];
-  Point p1 = Cv::from_aff(a1, C), p2;
+  Point p1, p2;
+  if (!A.comb1) p1 = Cv::from_aff(a1, C);
   if (A.b2) p2 = Cv::from_aff(a2, C);
   uint32_t e1[8], e2[8];
   for (int i = 0; i < 8; ++i) {
     e1[i] = A.e1[(size_t)tid * A.e1_stride + i];
     e2[i] = A.b2 ? A.e2[(size_t)tid * A.e2_stride + i] : 0u;
   }
-  Point r = ok ? scalar_mul2<Cv>(p1, e1, A.b2 ? &p2 : nullptr, e2, tbl1, tbl2, C) : Cv::infinity(C);
+  Point r = Cv::infinity(C);
+  if (ok) {
+    if (A.comb1) {
+      r = comb_mul<Cv>(comb, e1, C);
+      if (A.b2) r = Cv::add(r, scalar_mul2<Cv>(p2, e2, nullptr, e2, tbl2, tbl2, C), C);
+    } else {
+      r = scalar_mul2<Cv>(p1, e1, A.b2 ? &p2 : nullptr, e2, tbl1, tbl2, C);
+    }
+  }
   if (A.out_jac) A.out_jac[tid] = r;
   if (A.out) Cv::encode(A.out + (size_t)tid * Cv::EB, r, C);
 }
@@ -180,8 +258,7 @@ MP_DEV void horner_body(const HornerArgs<Cv>& A, uint32_t tid) {
       }
     }
     e = from_mont(e, C.N);
-    Point tbl[16];
-    acc = scalar_mul2<Cv>(acc, e.v, nullptr, e.v, tbl, tbl, C);
+    acc = Cv::scalar_mul_wide(acc, e.v, C);
   }
   A.out[tid] = acc;
 }

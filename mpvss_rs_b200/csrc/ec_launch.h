@@ -5,8 +5,16 @@
 #include "rist.cuh"
 #include "ec_kernels.cuh"
 
+// resident 128-thread CTAs per SM of the Horner kernel (its register budget is 65536 / (128 x this))
+#ifndef EC_HORNER_MIN_BLOCKS
+#define EC_HORNER_MIN_BLOCKS 4
+#endif
+
 namespace ec {
+constexpr int HORNER_CTAS_PER_SM = EC_HORNER_MIN_BLOCKS;
 template <class Cv> cudaError_t launch_exp2(const Exp2Args<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_fixed(const FixedArgs<Cv>& A, cudaStream_t s);
+template <class Cv> cudaError_t launch_comb_build(const CombArgs<Cv>& A, cudaStream_t s);
 template <class Cv> cudaError_t launch_decode(const DecodeArgs<Cv>& A, cudaStream_t s);
 template <class Cv> cudaError_t launch_horner(const HornerArgs<Cv>& A, cudaStream_t s);
 template <class Cv> cudaError_t launch_sum(const SumArgs<Cv>& A, cudaStream_t s);

@@ -12,8 +12,8 @@
 // registers; chain elements that are needed again live in SLOTS shared-memory slots per lane group,
 // assigned here by a linear scan over the elements' last uses.  One op:
 //     if (save) slot[save-1] <- acc;  if (a) acc <- slot[a-1];  acc <- acc * B(b)
-// with B(b) = slot[b] for b < 14, the Montgomery one for b = 14 (padding) and C_j for b = 15 (the
-// last op of every Horner step).  Encoding: bits 0-3 b, 4-7 a, 8-11 save.
+// with B(b) = slot[b] for b < SLOTS, the Montgomery one for b = SLOTS (padding) and C_j for b = SLOTS + 1
+// (the last op of every Horner step).  Encoding: bits 0-3 b, 4-7 a, 8-11 save.
 #pragma once
 #include <stdint.h>
 #include <algorithm>
@@ -23,7 +23,7 @@ namespace modp_chain {
 
 constexpr int SLOTS = 6;          // chain slots per lane group (the allocator needs at most 5 up to 2^31)
 constexpr int OPS_MAX = 48;       // ops per Horner step, the product with C_j included
-constexpr uint32_t B_ONE = 14, B_CJ = 15;
+constexpr uint32_t B_ONE = SLOTS, B_CJ = SLOTS + 1;  // operand codes behind the chain slots
 constexpr uint32_t TREE_LIMIT = 1u << 17;
 
 struct Step {

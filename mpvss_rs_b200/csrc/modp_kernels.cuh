@@ -114,7 +114,9 @@ MP_DEV void finish_store(uint32_t (&acc)[Cfg<TPI>::L], uint32_t* sq, uint32_t* d
 // multiply by C_j".  acc^i follows a short addition chain per position (modp_chain.h: power tree, 13.4
 // products for a 12-bit i instead of the 16 of fixed 2-bit windows); the host lowers it to a list of ops
 //     if (save) slot[save-1] <- acc;  if (a) acc <- slot[a-1];  acc <- acc * B(b)
-// (bits 0-3 b, 4-7 a, 8-11 save; B(14) = Montgomery one = padding, B(15) = C_j closes the step).
+// (bits 0-3 b, 4-7 a, 8-11 save; B(6) = Montgomery one = padding, B(7) = C_j closes the step: both are
+// kept as per-group copies behind the chain slots, so that the operand address is ONE expression of the
+// op field -- a select between two buffers cost 18 register moves per 10 digits in the product loop).
 // Every lane group of a warp runs its own chain: the op fields only select shared-memory addresses, the
 // instruction stream is the same for all groups, so only the LENGTH of the op list has to agree inside
 // a warp (positions are sorted by it, shorter lists padded with products by one).
@@ -130,12 +132,12 @@ struct HornerArgs {
   uint32_t t, n, nops_all;
 };
 
-constexpr int HC_SLOTS = 6;   // == modp_chain::SLOTS
+constexpr int HC_SLOTS = 6;   // == modp_chain::SLOTS; slot 6 = Montgomery one, slot 7 = C_j
 constexpr int HC_OPS = 48;    // == modp_chain::OPS_MAX
-constexpr int HC_GSTRIDE = HC_SLOTS * 64 + GPAD;
+constexpr int HC_GSTRIDE = (HC_SLOTS + 2) * 64 + GPAD;
 
 template <int TPI>
-constexpr int horner_smem_words = 128 + (32 / TPI) * (HC_GSTRIDE + HC_OPS / 2);
+constexpr int horner_smem_words = (32 / TPI) * (HC_GSTRIDE + HC_OPS / 2);
 
 // NP1: the modulus satisfies -q^-1 = 1 mod 2^32 (true for the RFC 3526 prime, whose low 64 bits are all
 // ones), so the Montgomery digit is the low limb itself and one multiply leaves the per-digit critical path.
@@ -151,17 +153,20 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   Mod<L> M;
   load_mod<TPI>(M, A.consts, ln);
   if (NP1) M.np = 1u;
-  uint32_t* one = wsm;
-  uint32_t* cbuf = wsm + 64;
-  uint32_t* gbase = wsm + 128 + gi * HC_GSTRIDE;  // this group's chain slots
-  uint16_t* opsm = reinterpret_cast<uint16_t*>(wsm + 128 + GPW * HC_GSTRIDE) + gi * HC_OPS;
-  warp_copy64(one, A.consts + C_ONE);
+  uint32_t* gbase = wsm + gi * HC_GSTRIDE;  // this group's chain slots, then one and C_j
+  uint16_t* opsm = reinterpret_cast<uint16_t*>(wsm + GPW * HC_GSTRIDE) + gi * HC_OPS;
   for (int k = ln.k; k < HC_OPS; k += TPI) opsm[k] = A.ops[(size_t)inst * HC_OPS + k];
   uint32_t acc[L];
+  load_slice<TPI>(acc, A.consts + C_ONE, ln);
+  stage<TPI>(gbase + HC_SLOTS * 64, acc, ln);
   load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
   simt::syncwarp();
   for (int j = (int)A.t - 2; j >= 0; --j) {
-    warp_copy64(cbuf, A.cm + (size_t)j * 64);
+    {
+      uint32_t cj[L];
+      load_slice<TPI>(cj, A.cm + (size_t)j * 64, ln);
+      stage_shared<TPI>(gbase + (HC_SLOTS + 1) * 64, cj, ln);  // visible after the first op's barrier
+    }
     uint32_t op = opsm[0];
 #pragma unroll 1
     for (uint32_t k = 0; k < nops; ++k) {  // one code instance of the product for the whole step
@@ -171,8 +176,7 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
       if (sv) stage<TPI>(gbase + (sv - 1) * 64, acc, ln);
       simt::syncwarp();
       if (a) load_slice<TPI>(acc, gbase + (a - 1) * 64, ln);
-      const uint32_t* operand = b < 14u ? gbase + b * 64 : wsm + (b - 14u) * 64;
-      mont_mul<TPI>(acc, acc, operand, M, ln);
+      mont_mul<TPI>(acc, acc, gbase + b * 64, M, ln);
       op = nxt;
     }
   }

@@ -46,19 +46,29 @@ MP_DEV Fe mont_one(const Modulus&) {
   r.v[0] = 1;
   return r;
 }
-MP_NOINLINE Fe pow(const Fe& a, const uint32_t (&e)[8], const Modulus& P) {
-  Fe r = F::mont_one(P);
-  bool started = false;
+MP_NOINLINE Fe sqn(Fe a, int n) {
 #pragma unroll 1
-  for (int i = 255; i >= 0; --i) {
-    if (started) r = F::sqr(r, P);
-    if ((e[i >> 5] >> (i & 31)) & 1u) {
-      r = started ? F::mul(r, a, P) : a;
-      started = true;
-    }
-  }
-  return r;
+  for (int i = 0; i < n; ++i) a = F::sqr(a);
+  return a;
 }
+// a^((p-5)/8) = a^(2^252 - 3): the classic curve25519 chain, 251 squarings + 11 multiplications instead
+// of the 252 + ~250 of bit-by-bit square-and-multiply
+MP_NOINLINE Fe pow_p58(const Fe& a) {
+  Fe t0 = F::sqr(a);                      // 2
+  Fe t1 = F::mul(sqn(t0, 2), a);          // 9
+  t0 = F::mul(t0, t1);                    // 11
+  t0 = F::mul(F::sqr(t0), t1);            // 31 = 2^5 - 1
+  t1 = F::mul(sqn(t0, 5), t0);            // 2^10 - 1
+  Fe t2 = F::mul(sqn(t1, 10), t1);        // 2^20 - 1
+  t2 = F::mul(sqn(t2, 20), t2);           // 2^40 - 1
+  t1 = F::mul(sqn(t2, 10), t1);           // 2^50 - 1
+  t2 = F::mul(sqn(t1, 50), t1);           // 2^100 - 1
+  Fe t3 = F::mul(sqn(t2, 100), t2);       // 2^200 - 1
+  t1 = F::mul(sqn(t3, 50), t1);           // 2^250 - 1
+  return F::mul(sqn(t1, 2), a);           // 2^252 - 3
+}
+// a^(p-2) = (a^((p-5)/8))^8 * a^3
+MP_NOINLINE Fe inv(const Fe& a) { return F::mul(sqn(pow_p58(a), 3), F::mul(F::sqr(a), a)); }
 }  // namespace F
 
 struct Consts {
@@ -131,7 +141,8 @@ MP_NOINLINE Ext ext_dbl(Ext p, const Consts& C, bool need_t = true) {
 
 // [k]p for a small scalar k < 4^nd, fixed 2-bit windows (the generic ladder of ec_kernels.cuh with
 // the T coordinate skipped in the first doubling of every window)
-MP_DEV Ext small_mul_ext(const Ext& p, uint32_t k, uint32_t nd, const Consts& C) {
+template <class DigitFn>
+MP_DEV Ext small_mul_ext(const Ext& p, DigitFn digit, uint32_t nd, const Consts& C) {
   Ext t2 = ext_dbl(p, C), t3 = ext_add(t2, p, C);
   Ext acc = ext_identity(C.P);
 #pragma unroll 1
@@ -140,7 +151,7 @@ MP_DEV Ext small_mul_ext(const Ext& p, uint32_t k, uint32_t nd, const Consts& C)
       acc = ext_dbl(acc, C, false);
       acc = ext_dbl(acc, C);
     }
-    uint32_t d = (k >> (2 * s)) & 3u;
+    uint32_t d = digit(s);
     Ext q = (d == 3) ? t3 : ((d == 2) ? t2 : p);
     if (d) acc = ext_add(acc, q, C);
   }
@@ -157,7 +168,7 @@ MP_NOINLINE bool sqrt_ratio_m1(Fe* out, const Fe& u, const Fe& v, const Consts& 
   const Modulus& P = C.P;
   Fe v3 = F::mul(F::sqr(v, P), v, P);
   Fe v7 = F::mul(F::sqr(v3, P), v, P);
-  Fe r = F::mul(F::mul(u, v3, P), F::pow(F::mul(u, v7, P), C.pm5d8, P), P);
+  Fe r = F::mul(F::mul(u, v3, P), F::pow_p58(F::mul(u, v7, P)), P);
   Fe check = F::mul(v, F::sqr(r, P), P);
   Fe sm1 = load(C.sqrt_m1);
   Fe nu = F::neg(u, P);
@@ -239,7 +250,11 @@ struct RistCurve {
   using Affine = Aff;
   static constexpr int EB = 32;
   MP_DEV static Point small_mul(const Point& p, uint32_t k, uint32_t nd, const Consts& C) {
-    return small_mul_ext(p, k, nd, C);
+    return small_mul_ext(p, [k](int s) { return (k >> (2 * s)) & 3u; }, nd, C);
+  }
+  // [e]p for a full-width scalar (8 little-endian limbs): the same 2-bit windows, table in registers
+  MP_DEV static Point scalar_mul_wide(const Point& p, const uint32_t* e, const Consts& C) {
+    return small_mul_ext(p, [e](int s) { return (e[s >> 4] >> ((s & 15) * 2)) & 3u; }, 128, C);
   }
   MP_DEV static Point infinity(const Consts& C) { return ext_identity(C.P); }
   MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return ext_from_aff(a, C.P); }
@@ -247,6 +262,14 @@ struct RistCurve {
   MP_DEV static Point add(const Point& p, const Point& q, const Consts& C) { return ext_add(p, q, C); }
   MP_DEV static Point madd(const Point& p, const Affine& q, const Consts& C) {
     return ext_add(p, ext_from_aff(q, C.P), C);
+  }
+  MP_DEV static Affine to_affine(const Point& p, const Consts&) {
+    Affine a;
+    const Fe zi = F::inv(p.Z);
+    a.x = F::mul(p.X, zi);
+    a.y = F::mul(p.Y, zi);
+    a.inf = 0;
+    return a;
   }
   MP_DEV static bool decode(Affine& a, const uint8_t* in, const Consts& C) { return rist::decode(a, in, C); }
   MP_DEV static void encode(uint8_t* out, const Point& p, const Consts& C) { rist::encode(out, p, C); }

@@ -60,12 +60,49 @@ MP_NOINLINE Fe pow(const Fe& a, const uint32_t (&e)[8], const Modulus& P) {
   }
   return r;
 }
-MP_NOINLINE Fe inv(const Fe& a, const Modulus& P) {
-  uint32_t e[8];
-  e[0] = simt::sub_cc(P.m[0], 2);
-#pragma unroll
-  for (int i = 1; i < 8; ++i) e[i] = simt::subc_cc(P.m[i], 0);
-  return F::pow(a, e, P);
+// a^(2^n) by n squarings
+MP_NOINLINE Fe sqn(Fe a, int n) {
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) a = F::sqr(a);
+  return a;
+}
+// Shared prefix of the inversion and square-root chains: x2 = a^(2^2 - 1), x22 = a^(2^22 - 1),
+// x223 = a^(2^223 - 1) (the exponents p - 2 and (p + 1) / 4 are runs of ones around the 2^32 + 977 gap;
+// 238 squarings + 10 multiplications).
+struct Runs {
+  Fe x2, x22, x223;
+};
+MP_NOINLINE Runs runs_of_ones(const Fe& a) {
+  Runs r;
+  r.x2 = F::mul(sqn(a, 1), a);
+  Fe x3 = F::mul(sqn(r.x2, 1), a);
+  Fe x6 = F::mul(sqn(x3, 3), x3);
+  Fe x9 = F::mul(sqn(x6, 3), x3);
+  Fe x11 = F::mul(sqn(x9, 2), r.x2);
+  r.x22 = F::mul(sqn(x11, 11), x11);
+  Fe x44 = F::mul(sqn(r.x22, 22), r.x22);
+  Fe x88 = F::mul(sqn(x44, 44), x44);
+  Fe x176 = F::mul(sqn(x88, 88), x88);
+  Fe x220 = F::mul(sqn(x176, 44), x44);
+  r.x223 = F::mul(sqn(x220, 3), x3);
+  return r;
+}
+// a^(p-2): 255 squarings + 15 multiplications instead of the 256 + ~250 of bit-by-bit square-and-multiply
+// (p - 2 = 2^256 - 2^32 - 979 = [223 ones] 0 [22 ones] 0000 1 0 11 01 in binary)
+MP_NOINLINE Fe inv(const Fe& a, const Modulus&) {
+  Runs r = runs_of_ones(a);
+  Fe t = F::mul(sqn(r.x223, 23), r.x22);
+  t = F::mul(sqn(t, 5), a);
+  t = F::mul(sqn(t, 3), r.x2);
+  return F::mul(sqn(t, 2), a);
+}
+// a^((p+1)/4), a square root of a when a is a square (p = 3 mod 4): 253 squarings + 13 multiplications
+// ((p + 1) / 4 = 2^254 - 2^30 - 244 = [223 ones] 0 [22 ones] 0000 11 00)
+MP_NOINLINE Fe sqrt_candidate(const Fe& a, const Modulus&) {
+  Runs r = runs_of_ones(a);
+  Fe t = F::mul(sqn(r.x223, 23), r.x22);
+  t = F::mul(sqn(t, 6), r.x2);
+  return sqn(t, 2);
 }
 }  // namespace F
 
@@ -174,7 +211,9 @@ MP_NOINLINE Jac jac_madd(Jac p, Aff q, const Modulus& P) {
 // their Z by the scale.  Rescaling twice (by the Z of 2P, then by the Z of 3P) leaves P, 2P, 3P all
 // affine on one curve, so the window additions are mixed additions (7M + 4S instead of 11M + 5S).
 // The group element is the same as with the generic ladder: only the representative changes.
-MP_DEV Jac small_mul_iso(const Jac& p, uint32_t k, uint32_t nd, const Modulus& P) {
+// `digit(s)` returns base-4 digit s of the scalar (s = 0 least significant), nd digits in all.
+template <class DigitFn>
+MP_DEV Jac small_mul_iso(const Jac& p, DigitFn digit, uint32_t nd, const Modulus& P) {
   if (jac_is_inf(p)) return p;
   Fe x1 = p.X, y1 = p.Y;
   // 2P on the first curve: mdbl-2007-bl (Z1 = 1, a = 0), 1M + 5S
@@ -212,7 +251,7 @@ MP_DEV Jac small_mul_iso(const Jac& p, uint32_t k, uint32_t nd, const Modulus& P
       acc = jac_dbl(acc, P);
       acc = jac_dbl(acc, P);
     }
-    uint32_t d = (k >> (2 * s)) & 3u;
+    uint32_t d = digit(s);
     Aff q = (d == 3) ? t3 : ((d == 2) ? t2 : t1);
     if (d) acc = jac_madd(acc, q, P);
   }
@@ -279,7 +318,7 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
   if (simt::subc(0, 0) == 0) return false;
   Fe xm = F::to_mont(x, P);
   Fe y2 = F::add(F::mul(F::sqr(xm, P), xm, P), load(C.b7), P);
-  Fe y = F::pow(y2, C.sqrt_e, P);
+  Fe y = F::sqrt_candidate(y2, P);
   if (!eq(F::sqr(y, P), y2)) return false;
   Fe yn = F::from_mont(y, P);
   if ((yn.v[0] & 1u) != (uint32_t)(in[0] & 1)) y = F::neg(y, P);
@@ -295,13 +334,20 @@ struct SecpCurve {
   using Affine = Aff;
   static constexpr int EB = 33;
   MP_DEV static Point small_mul(const Point& p, uint32_t k, uint32_t nd, const Consts& C) {
-    return small_mul_iso(p, k, nd, C.P);
+    return small_mul_iso(p, [k](int s) { return (k >> (2 * s)) & 3u; }, nd, C.P);
+  }
+  // [e]p for a full-width scalar (8 little-endian limbs) through the same 2-bit windows with the affine
+  // table P, 2P, 3P: 256 doublings + ~96 mixed additions, the table in registers (no per-thread point
+  // array in local memory as a 4-bit window table would need)
+  MP_DEV static Point scalar_mul_wide(const Point& p, const uint32_t* e, const Consts& C) {
+    return small_mul_iso(p, [e](int s) { return (e[s >> 4] >> ((s & 15) * 2)) & 3u; }, 128, C.P);
   }
   MP_DEV static Point infinity(const Consts& C) { return jac_infinity(C.P); }
   MP_DEV static Point from_aff(const Affine& a, const Consts& C) { return jac_from_aff(a, C.P); }
   MP_DEV static Point dbl(const Point& p, const Consts& C) { return jac_dbl(p, C.P); }
   MP_DEV static Point add(const Point& p, const Point& q, const Consts& C) { return jac_add(p, q, C.P); }
   MP_DEV static Point madd(const Point& p, const Affine& q, const Consts& C) { return jac_madd(p, q, C.P); }
+  MP_DEV static Affine to_affine(const Point& p, const Consts& C) { return jac_to_aff(p, C.P); }
   MP_DEV static bool decode(Affine& a, const uint8_t* in, const Consts& C) { return secp::decode(a, in, C); }
   MP_DEV static void encode(uint8_t* out, const Point& p, const Consts& C) {
     secp::encode(out, jac_to_aff(p, C.P), C.P);

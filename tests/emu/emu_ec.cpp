@@ -9,8 +9,21 @@ namespace {
 template <class Cv>
 int t_exp2(const void* consts, const uint8_t* b1, uint32_t b1s, const uint32_t* e1, uint32_t e1s, const uint8_t* b2,
            uint32_t b2s, const uint32_t* e2, uint32_t e2s, uint32_t n, uint8_t* out, uint32_t* status) {
-  ec::Exp2Args<Cv> A{(const typename Cv::Consts*)consts, b1, e1, b2, e2, out, nullptr, status, n, b1s, e1s, b2s, e2s, 0};
+  ec::Exp2Args<Cv> A{(const typename Cv::Consts*)consts, b1, e1, b2, e2, out, nullptr, status, n, b1s, e1s, b2s, e2s, nullptr};
   for (uint32_t t = 0; t < n; ++t) ec::exp2_body<Cv>(A, t);
+  return 0;
+}
+// fixed-base table of the generator, then e1 * G [+ e2 * B2] through it and e * G alone
+template <class Cv>
+int t_comb(const void* consts, const uint8_t* gen, uint32_t* tbl, const uint32_t* e1, const uint8_t* b2,
+           const uint32_t* e2, uint32_t n, uint8_t* out_fixed, uint8_t* out_exp2, uint32_t* status) {
+  const typename Cv::Consts* C = (const typename Cv::Consts*)consts;
+  ec::CombArgs<Cv> B{C, gen, tbl};
+  for (uint32_t t = 0; t < (uint32_t)ec::COMB_ENTRIES; ++t) ec::comb_build_body<Cv>(B, t);
+  ec::FixedArgs<Cv> F{C, tbl, e1, out_fixed, n};
+  for (uint32_t t = 0; t < n; ++t) ec::fixed_body<Cv>(F, t, tbl);
+  ec::Exp2Args<Cv> A{C, gen, e1, b2, e2, out_exp2, nullptr, status, n, 0, 8, (uint32_t)Cv::EB, 8, tbl};
+  for (uint32_t t = 0; t < n; ++t) ec::exp2_body<Cv>(A, t, tbl);
   return 0;
 }
 template <class Cv>
@@ -45,6 +58,11 @@ int t_poly_eval_exp(const void* consts, const uint8_t* commitments, uint32_t t, 
                                      const uint8_t* b2, uint32_t b2s, const uint32_t* e2, uint32_t e2s, uint32_t n,   \
                                      uint8_t* out, uint32_t* st) {                                                    \
     return t_exp2<Cv>(c, b1, b1s, e1, e1s, b2, b2s, e2, e2s, n, out, st);                                             \
+  }                                                                                                                   \
+  extern "C" int emu_##prefix##_comb(const void* c, const uint8_t* gen, uint32_t* tbl, const uint32_t* e1,             \
+                                     const uint8_t* b2, const uint32_t* e2, uint32_t n, uint8_t* of, uint8_t* oe,     \
+                                     uint32_t* st) {                                                                  \
+    return t_comb<Cv>(c, gen, tbl, e1, b2, e2, n, of, oe, st);                                                        \
   }                                                                                                                   \
   extern "C" int emu_##prefix##_add(const void* c, const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* out,      \
                                     uint32_t* st) {                                                                   \

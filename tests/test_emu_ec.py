@@ -120,6 +120,38 @@ def test_point_kernels(L, cv):
 
 
 @pytest.mark.parametrize("cv", ["secp", "rist"])
+def test_fixed_base_table(L, cv):
+    """Generator table T[w][d-1] = (d * 16^w) G (affine), e * G from 64 lookups, and the DLEQ form
+    e1 * G + e2 * B through it (Group::exp with a generator: secp256k1.rs:91-100 / ristretto255.rs:161-170)."""
+    Gc, consts, order, EB = CURVES[cv]
+    G = Gc()
+    C = consts()
+    rng = random.Random(23)
+    n = 8
+    e1 = [rng.randrange(order) for _ in range(n)]
+    e2 = [rng.randrange(order) for _ in range(n)]
+    e1[0], e1[1], e1[2], e1[3] = 0, 1, order - 1, 0xF << 252 if cv == "secp" else (1 << 252)
+    e2[4] = 0
+    pts2 = [G.exp(G.generator(), rng.randrange(1, order)) for _ in range(n)]
+    pts2[5], e2[5] = G.generator(), order - e1[5]                  # e1 G + e2 G = identity
+    pts2[6], e2[6] = G.generator(), e1[6]                          # equal addends
+    gen = U8(G.element_to_bytes(G.generator()))
+    b2 = U8(b"".join(G.element_to_bytes(p) for p in pts2))
+    tbl = np.zeros(64 * 15 * 16, dtype=np.uint32)
+    E1 = np.concatenate([eu.to_limbs(x % order, 8) for x in e1])
+    E2 = np.concatenate([eu.to_limbs(x, 8) for x in e2])
+    of, oe = (ctypes.c_uint8 * (EB * n))(), (ctypes.c_uint8 * (EB * n))()
+    st = np.zeros(n, dtype=np.uint32)
+    getattr(L, f"emu_{cv}_comb")(eu.P(C), gen, eu.P(tbl), eu.P(E1), b2, eu.P(E2), n, of, oe, eu.P(st))
+    for i in range(n):
+        k = e1[i] % order
+        assert bytes(of)[EB * i:EB * i + EB] == G.element_to_bytes(G.exp(G.generator(), k)), i
+        want = G.mul(G.exp(G.generator(), k), G.exp(pts2[i], e2[i]))
+        assert bytes(oe)[EB * i:EB * i + EB] == G.element_to_bytes(want), i
+    assert not st.any()
+
+
+@pytest.mark.parametrize("cv", ["secp", "rist"])
 @pytest.mark.parametrize("K", [1, 2, 7])
 def test_chunked_horner_equals_reference_schedule(L, cv, K):
     Gc, consts, order, EB = CURVES[cv]

@@ -123,7 +123,7 @@ def _run_ops(ops, x, cj, mul=lambda a, b: a * b % Q):
             slot[sv - 1] = acc
         if a:
             acc = slot[a - 1]
-        acc = mul(acc, 1 if b == 14 else cj if b == 15 else slot[b])
+        acc = mul(acc, 1 if b == 6 else cj if b == 7 else slot[b])
     return acc
 
 
@@ -140,7 +140,7 @@ def test_addition_chain_ops_compute_x_to_the_p_times_c():
     for p in ps:
         for limit in (1 << 12, 1 << 17):
             ops, sq, ml = _chain_ops(hl, p, limit)
-            assert len(ops) <= 48 and sq + ml == len(ops) and ops[-1] == 15
+            assert len(ops) <= 48 and sq + ml == len(ops) and ops[-1] == 7
             assert _run_ops(ops, x, cj) == pow(x, p, Q) * cj % Q, (p, limit)
             if limit == 1 << 17 and p <= 4096:
                 total_len += len(ops) - 1
@@ -167,10 +167,10 @@ def test_horner_kernel_equals_reference_schedule(lib, tpi):
     positions = [1, 2, 3, 5, 11, 14, 15, 64, 255, 4096, 70000, 200001][:max(gpw, 4) + 2]
     lists = [_chain_ops(hl, p)[0] for p in positions]
     nops = max(len(l) for l in lists)
-    ops = np.full(48 * len(positions), 14, dtype=np.uint16)          # padding: products by one
+    ops = np.full(48 * len(positions), 6, dtype=np.uint16)          # padding: products by one
     for i, l in enumerate(lists):
         ops[48 * i:48 * i + len(l) - 1] = l[:-1]
-        ops[48 * i + nops - 1] = 15                                  # the C_j product closes the step
+        ops[48 * i + nops - 1] = 7                                  # the C_j product closes the step
     n = len(positions)
     out = np.zeros(64 * n, dtype=np.uint32)
     assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, ops.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint16)),
