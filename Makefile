@@ -28,3 +28,14 @@ clean:
 	rm -f $(OBJ) $(LIB) tests/emu/*.so
 
 .PHONY: all emu clean
+
+# The reference itself (Rust) as the oracle's anchor: builds oracle/ref_harness against /root/reference and
+# regenerates tests/golden/ref_vectors.json.  Needs cargo + the crates of /root/reference/Cargo.toml;
+# neither exists in the graft image, so this target only reports that there.
+oracle_ref:
+	@if command -v cargo >/dev/null 2>&1; then \
+	  cd oracle/ref_harness && cargo build --release --target-dir ../_ref && \
+	  ../_ref/release/mpvss_ref_harness > ../../tests/golden/ref_vectors.json && \
+	  echo "wrote tests/golden/ref_vectors.json"; \
+	else echo "oracle_ref: no cargo in this image -- parity stays pinned by KATs + independent implementations"; fi
+.PHONY: oracle_ref

@@ -146,6 +146,15 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->modp_overlap = value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "modp_msm") {
+    if (value < 0 || value > 2) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_msm must be 0, 1 or 2");
+    ctx->modp_msm = value;
+    return MPVSS_OK;
+  }
+  if (std::string(key) == "msm_threshold") {
+    ctx->msm_threshold = value;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "validate") {
     ctx->validate = value != 0;
     return MPVSS_OK;

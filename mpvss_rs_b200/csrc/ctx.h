@@ -78,6 +78,8 @@ struct mpvss_ctx {
   DevBuf gens;               // [0,64) main generator G = 2, [64,128) subgroup generator g = 4, [128,192) one
   DevBuf comb[2];            // fixed-base tables of the two generators (built on first use, 16.8 MB each)
   int modp_comb = 1;         // use them ("modp_comb")
+  int modp_msm = 2;          // multi_exp / reconstruct by buckets: 0 never, 1 always, 2 from msm_threshold bases on
+  int msm_threshold = 8192;
   bool validate = false;     // range / subgroup check of ModpGroup elements entering the verify calls
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----

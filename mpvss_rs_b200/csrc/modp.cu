@@ -57,6 +57,23 @@ __global__ void __launch_bounds__(64) poly_kernel(PolyArgs A) { poly_body(A, blo
 __global__ void __launch_bounds__(64) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, blockIdx.x * 64 + threadIdx.x); }
 
 template <int TPI>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) msm_bucket_kernel(MsmBucketArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t w = threadIdx.x >> 5;
+  msm_bucket_body<TPI>(A, blockIdx.x * WARPS_PER_CTA + w, smem + w * msm_smem_words<TPI>);
+}
+template <int TPI>
+__global__ void __launch_bounds__(32) msm_window_kernel(MsmWindowArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  msm_window_body<TPI>(A, blockIdx.x, smem);
+}
+template <int TPI>
+__global__ void __launch_bounds__(32) msm_fold_kernel(MsmFoldArgs A) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  msm_fold_body<TPI>(A, smem);
+}
+
+template <int TPI>
 static uint32_t ctas_for(uint32_t n) {
   uint32_t per_cta = WARPS_PER_CTA * (32 / TPI);
   return (n + per_cta - 1) / per_cta;
@@ -154,6 +171,20 @@ cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s) {
     comb1_kernel<T><<<1, 32, sm, s>>>(A);
     comb2_kernel<T><<<(A.rows + 32 / T - 1) / (32 / T), 32, sm, s>>>(A);
   });
+  return cudaGetLastError();
+}
+
+// bucket multi-exponentiation: buckets, per-window products, final fold (8 lanes per value)
+cudaError_t launch_msm(const MsmBucketArgs& B, uint32_t* wprod, uint32_t* out, cudaStream_t s) {
+  if (B.windows == 0 || B.k == 0) return cudaErrorInvalidValue;
+  constexpr int T = 8;
+  const uint32_t groups = B.windows * 255u, per_cta = WARPS_PER_CTA * (32 / T);
+  size_t sm = WARPS_PER_CTA * msm_smem_words<T> * 4;
+  msm_bucket_kernel<T><<<(groups + per_cta - 1) / per_cta, WARPS_PER_CTA * 32, sm, s>>>(B);
+  MsmWindowArgs W{B.consts, B.buckets, wprod, B.windows};
+  msm_window_kernel<T><<<B.windows, 32, msm_window_smem_words<T> * 4, s>>>(W);
+  MsmFoldArgs F{B.consts, wprod, out, B.windows};
+  msm_fold_kernel<T><<<1, 32, msm_smem_words<T> * 4, s>>>(F);
   return cudaGetLastError();
 }
 

@@ -238,7 +238,12 @@ int batch_mul(mpvss_ctx* ctx, const uint8_t* a, const uint8_t* b, size_t n, uint
 // value (16 limbs per lane) spend the fewest instructions per MAC: measured 6.4 vs 5.7 TMAC/s at
 // per launch of 32768 positions (Horner 2104 vs 2149 ms); at 16384 and below 8 lanes per value win.
 static int horner_tpi(const mpvss_ctx* ctx, size_t n) {
-  return (ctx->modp_tpi_auto && n >= 32768) ? 4 : ctx->modp_tpi;
+  if (!ctx->modp_tpi_auto) return ctx->modp_tpi;
+  if (n >= 32768) return 4;
+  // few positions (a small box, or one box split over many GPUs): 16 lanes per value double the warps;
+  // below 4 warps per SM at 8 lanes the launch is latency-bound and the extra warps pay
+  if (n * 8 / 32 < (size_t)4 * (size_t)ctx->sm_count) return 16;
+  return ctx->modp_tpi;
 }
 
 struct PosPlan {
@@ -406,16 +411,55 @@ static int dev_product_tree(mpvss_ctx* ctx, uint32_t* v, DevBuf& tmp, size_t n) 
   return MPVSS_OK;
 }
 
+// Bucket method (Pippenger, 8-bit windows) for prod_i bases[i]^scalars[i]: the host sorts the indices of every
+// window by digit (counting sort over the exponent bytes it already holds), the device does the rest
+// (modp::launch_msm).  `db` holds the bases in normal form; the result lands in dout[0].
+static int multi_exp_buckets(mpvss_ctx* ctx, DevBuf& db, const uint8_t* scalars, size_t n, DevBuf& dout) {
+  const uint32_t windows = (windows_for(scalars, EB, n) + 1) / 2;  // exponent bytes in use
+  std::vector<uint32_t> idx((size_t)windows * n), start((size_t)windows * 257);
+  for (uint32_t w = 0; w < windows; ++w) {
+    uint32_t cnt[257] = {0};
+    for (size_t i = 0; i < n; ++i) ++cnt[scalars[i * EB + w] + 1];
+    for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+    memcpy(&start[(size_t)w * 257], cnt, sizeof cnt);
+    uint32_t cur[256];
+    memcpy(cur, cnt, sizeof cur);
+    for (size_t i = 0; i < n; ++i) idx[(size_t)w * n + cur[scalars[i * EB + w]]++] = (uint32_t)i;
+  }
+  DevBuf &dm = ctx->buf(15), &didx = ctx->buf(16), &dst = ctx->buf(17), &dbk = ctx->buf(18), &dwp = ctx->buf(19);
+  MPVSS_TRY(h2d(ctx, didx, idx.data(), idx.size() * 4));
+  MPVSS_TRY(h2d(ctx, dst, start.data(), start.size() * 4));
+  MPVSS_CUDA(ctx, dm.ensure(n * EB));
+  MPVSS_CUDA(ctx, dbk.ensure((size_t)windows * 256 * EB));
+  MPVSS_CUDA(ctx, dwp.ensure((size_t)windows * EB));
+  const uint32_t* K = ctx->consts_q.as<uint32_t>();
+  MPVSS_TRY(dev_mul(ctx, K, db.as<uint32_t>(), EW, nullptr, 0, 1, n, dm.as<uint32_t>()));  // to Montgomery form
+  modp::MsmBucketArgs B{K, dm.as<uint32_t>(), didx.as<uint32_t>(), dst.as<uint32_t>(), dbk.as<uint32_t>(), windows,
+                        (uint32_t)n};
+  MPVSS_CUDA(ctx, modp::launch_msm(B, dwp.as<uint32_t>(), dout.as<uint32_t>(), ctx->stream));
+  timing_launch(ctx, 3);
+  return MPVSS_OK;
+}
+
 int multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* out) {
   MPVSS_TRY(check_args(ctx, bases && scalars && out && n > 0, "multi_exp: bad arguments"));
   DevBuf &db = ctx->buf(0), &de = ctx->buf(1), &dout = ctx->buf(2), &tmp = ctx->buf(3);
   MPVSS_TRY(h2d(ctx, db, bases, n * EB));
-  MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  // One exponentiation per base + product tree has a depth of ~2560 products whatever n is, as long as all
+  // n / 4 warps are resident at once; the bucket method does 8x less work but is just as deep (2040 sequential
+  // squarings in its final fold), so it takes over once the direct form needs several waves ("modp_msm":
+  // 0 never, 1 always, 2 = automatic).
+  const bool buckets = ctx->modp_msm == 1 || (ctx->modp_msm == 2 && n >= (size_t)ctx->msm_threshold);
   timing_begin(ctx);
-  MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), db.as<uint32_t>(), EW, de.as<uint32_t>(), EW,
-                     windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n, dout.as<uint32_t>()));
-  MPVSS_TRY(dev_product_tree(ctx, dout.as<uint32_t>(), tmp, n));
+  if (buckets) {
+    MPVSS_TRY(multi_exp_buckets(ctx, db, scalars, n, dout));
+  } else {
+    MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
+    MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), db.as<uint32_t>(), EW, de.as<uint32_t>(), EW,
+                       windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n, dout.as<uint32_t>()));
+    MPVSS_TRY(dev_product_tree(ctx, dout.as<uint32_t>(), tmp, n));
+  }
   MPVSS_TRY(timing_end(ctx));
   MPVSS_TRY(d2h(ctx, out, dout, EB));
   return sync(ctx);

@@ -626,6 +626,146 @@ MP_DEV void lagrange_body(const LagrangeArgs& A, uint32_t tid) {
   lagrange_product(A.den + (size_t)tid * 64, A, tid, true, A.negative + tid);
 }
 
+// --------------------------------------------- bucket multi-exponentiation ----
+// prod_i S_i^(e_i) for k distinct bases and unstructured full-width exponents (the reconstruct fold,
+// participant.rs:490-509, and Group-level multi_exp): Pippenger's bucket method with 8-bit windows.
+//   1. the host sorts, per window w, the indices i by the byte e_i[w] (counting sort);
+//   2. msm_bucket_body: one lane group per (w, d), d = 1..255: B[w][d] = prod of the bases in that bucket;
+//   3. msm_window_body: one warp per window: W_w = prod_d B[w][d]^d by running products, the 255 buckets
+//      cut into one segment per lane group (depth 2 * 256 / groups + ~12 instead of 510 products);
+//   4. msm_fold_body: result = prod_w W_w^(2^(8w)), Horner from the top window (8 squarings + 1 product
+//      per window: the 2040 sequential squarings no method can avoid for a fresh base).
+// Work: windows * (k + ~600) products instead of k * (4 * windows + ...) for one exponentiation per base.
+struct MsmBucketArgs {
+  const uint32_t* consts;
+  const uint32_t* bases;   // k values, Montgomery form
+  const uint32_t* idx;     // windows * k indices, window-major, sorted by digit
+  const uint32_t* start;   // windows * 257 bucket boundaries inside each window's index list
+  uint32_t* buckets;       // windows * 256 values (entry d = 0 unused), Montgomery form
+  uint32_t windows, k;
+};
+template <int TPI>
+constexpr int msm_smem_words = (32 / TPI) * (2 * 64 + GPAD);
+
+template <int TPI>
+MP_DEV void msm_bucket_body(const MsmBucketArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  Lane ln = make_lane<TPI>();
+  const int gi = (int)simt::lane_id() / TPI;
+  const uint32_t total = A.windows * 255u;
+  uint32_t id = wg * GPW + gi;
+  const bool live = id < total;
+  if (!live) id = total - 1;
+  const uint32_t w = id / 255u, d = id % 255u + 1u;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* stage_buf = wsm + gi * (2 * 64 + GPAD);
+  uint32_t* one = stage_buf + 64;
+  uint32_t acc[L], x[L];
+  load_slice<TPI>(acc, A.consts + C_ONE, ln);
+  stage_shared<TPI>(one, acc, ln);
+  const uint32_t lo = A.start[w * 257u + d], hi = A.start[w * 257u + d + 1];
+  uint32_t cnt = live ? hi - lo : 0u, mx = cnt;
+  for (int off = 16; off >= 1; off >>= 1) {  // longest bucket of the warp: every group runs that many products
+    uint32_t o = simt::shfl(mx, (int)simt::lane_id() ^ off);
+    mx = o > mx ? o : mx;
+  }
+  simt::syncwarp();
+  for (uint32_t j = 0; j < mx; ++j) {
+    const bool have = j < cnt;
+    if (have) load_slice<TPI>(x, A.bases + (size_t)A.idx[(size_t)w * A.k + lo + j] * 64, ln);
+    simt::syncwarp();
+    if (have) stage<TPI>(stage_buf, x, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, have ? stage_buf : one, M, ln);
+  }
+  if (live) stage<TPI>(A.buckets + ((size_t)w * 256 + d) * 64, acc, ln);
+}
+
+struct MsmWindowArgs {
+  const uint32_t* consts;
+  const uint32_t* buckets;  // windows * 256 values (Montgomery)
+  uint32_t* wprod;          // windows values (Montgomery): W_w
+  uint32_t windows;
+};
+template <int TPI>
+constexpr int msm_window_smem_words = (32 / TPI) * (4 * 64 + GPAD);
+
+// one warp per window; lane group s owns the buckets d = s*SEG+1 .. s*SEG+SEG (SEG = 256 / groups; d = 256 does
+// not exist and counts as one):  W = prod_s A_s * (R_s^SEG)^s,  A_s = prod_d B_d^(d - s*SEG),  R_s = prod_d B_d
+template <int TPI>
+MP_DEV void msm_window_body(const MsmWindowArgs& A, uint32_t wg, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  constexpr int GPW = 32 / TPI;
+  constexpr uint32_t SEG = 256 / GPW;
+  Lane ln = make_lane<TPI>();
+  const uint32_t gi = simt::lane_id() / TPI;
+  const uint32_t w = wg < A.windows ? wg : A.windows - 1;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* buf = wsm + gi * (4 * 64 + GPAD);  // [0] operand stage, [1] run, [2] scratch, [3] result exchange
+  uint32_t run[L], acc[L], x[L];
+  load_slice<TPI>(run, A.consts + C_ONE, ln);
+  load_slice<TPI>(acc, A.consts + C_ONE, ln);
+  simt::syncwarp();
+  for (uint32_t d = SEG; d >= 1; --d) {  // running products from the top of the segment
+    const uint32_t b = gi * SEG + d;
+    load_slice<TPI>(x, b < 256u ? A.buckets + ((size_t)w * 256 + b) * 64 : A.consts + C_ONE, ln);
+    stage_shared<TPI>(buf, x, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(run, run, buf, M, ln);
+    stage_shared<TPI>(buf + 64, run, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, buf + 64, M, ln);
+  }
+  // run = R_s, acc = A_s.  y = R_s^SEG (log2 SEG squarings), then y^s by s - 1 products (s < groups <= 8)
+  uint32_t y[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) y[i] = run[i];
+  for (uint32_t q = SEG; q > 1; q >>= 1) sqr_plain<TPI>(y, buf, M, ln);
+  stage_shared<TPI>(buf + 128, y, ln);  // y
+  load_slice<TPI>(x, A.consts + C_ONE, ln);
+  stage_shared<TPI>(buf + 64, x, ln);   // one
+  simt::syncwarp();
+  for (uint32_t e = 0; e < (uint32_t)GPW - 1; ++e)  // acc *= y while e < s, else * one (same schedule for all groups)
+    mont_mul<TPI>(acc, acc, e < gi ? buf + 128 : buf + 64, M, ln);
+  // product over the groups of the warp through shared memory
+  stage_shared<TPI>(buf + 192, acc, ln);
+  simt::syncwarp();
+  load_slice<TPI>(acc, wsm + 192, ln);  // group 0's value
+  for (uint32_t s = 1; s < (uint32_t)GPW; ++s) mont_mul<TPI>(acc, acc, wsm + s * (4 * 64 + GPAD) + 192, M, ln);
+  if (wg < A.windows && gi == 0) stage<TPI>(A.wprod + (size_t)w * 64, acc, ln);
+}
+
+struct MsmFoldArgs {
+  const uint32_t* consts;
+  const uint32_t* wprod;  // windows values (Montgomery)
+  uint32_t* out;          // 1 value, canonical
+  uint32_t windows;
+};
+template <int TPI>
+MP_DEV void msm_fold_body(const MsmFoldArgs& A, uint32_t* wsm) {
+  constexpr int L = Cfg<TPI>::L;
+  Lane ln = make_lane<TPI>();
+  const uint32_t gi = simt::lane_id() / TPI;
+  Mod<L> M;
+  load_mod<TPI>(M, A.consts, ln);
+  uint32_t* buf = wsm + gi * (2 * 64 + GPAD);  // every group computes the same value (one warp in all)
+  uint32_t acc[L], x[L];
+  load_slice<TPI>(acc, A.wprod + (size_t)(A.windows - 1) * 64, ln);
+  simt::syncwarp();
+  for (int w = (int)A.windows - 2; w >= 0; --w) {
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) sqr_plain<TPI>(acc, buf, M, ln);
+    load_slice<TPI>(x, A.wprod + (size_t)w * 64, ln);
+    stage_shared<TPI>(buf, x, ln);
+    simt::syncwarp();
+    mont_mul<TPI>(acc, acc, buf, M, ln);
+  }
+  finish_store<TPI>(acc, buf, A.out, gi == 0, M, ln);
+}
+
 // ------------------------------------------------------- element-wise mul ----
 struct MulArgs {
   const uint32_t* consts;

@@ -16,4 +16,5 @@ cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s);
 cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s);
 cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s);
 cudaError_t launch_mul(int tpi, const MulArgs& A, cudaStream_t s);
+cudaError_t launch_msm(const MsmBucketArgs& B, uint32_t* wprod, uint32_t* out, cudaStream_t s);
 }  // namespace modp

@@ -60,6 +60,21 @@ extern "C" int emu_modp_resp(const uint32_t* order, const uint32_t* alpha, uint3
   return 0;
 }
 
+// bucket multi-exponentiation end to end (8 lanes per value): buckets, window products, fold
+extern "C" int emu_modp_msm(const uint32_t* consts, const uint32_t* bases_mont, const uint32_t* idx,
+                            const uint32_t* start, uint32_t windows, uint32_t k, uint32_t* buckets, uint32_t* wprod,
+                            uint32_t* out) {
+  constexpr int T = 8;
+  modp::MsmBucketArgs B{consts, bases_mont, idx, start, buckets, windows, k};
+  run_warps(warps_for<T>(windows * 255), modp::msm_smem_words<T>,
+            [&](uint32_t w, uint32_t* s) { modp::msm_bucket_body<T>(B, w, s); });
+  modp::MsmWindowArgs W{consts, buckets, wprod, windows};
+  run_warps(windows, modp::msm_window_smem_words<T>, [&](uint32_t w, uint32_t* s) { modp::msm_window_body<T>(W, w, s); });
+  modp::MsmFoldArgs F{consts, wprod, out, windows};
+  run_warps(1, modp::msm_smem_words<T>, [&](uint32_t, uint32_t* s) { modp::msm_fold_body<T>(F, s); });
+  return 0;
+}
+
 extern "C" int emu_modp_exp2(int tpi, const uint32_t* consts, const uint32_t* b1, uint32_t b1s, const uint32_t* e1,
                              uint32_t e1s, uint32_t e1w, const uint32_t* b2, uint32_t b2s, const uint32_t* e2,
                              uint32_t e2s, uint32_t e2w, uint32_t n, uint32_t* out, const uint32_t* comb) {

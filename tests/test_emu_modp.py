@@ -311,3 +311,34 @@ def test_lagrange_kernel(lib):
         assert eu.from_limbs(num[64 * i:64 * i + 64]) == abs(n_) % order
         assert eu.from_limbs(den[64 * i:64 * i + 64]) == abs(d_) % order
         assert bool(neg[i]) == (n_ * d_ < 0)
+
+
+def test_bucket_multi_exponentiation(lib):
+    """Pippenger buckets (8-bit windows): prod_i S_i^(e_i) for 3-byte exponents, empty and crowded buckets,
+    zero digits and a zero exponent (the reconstruct fold, participant.rs:490-509)."""
+    C = eu.consts_block(Q)
+    rng = random.Random(31)
+    k, windows = 21, 3
+    bases = [rng.randrange(2, Q) for _ in range(k)]
+    exps = [rng.getrandbits(24) for _ in range(k)]
+    exps[0], exps[1], exps[2], exps[3] = 0, 0xFF00FF, 0x000001, 0xFFFFFF
+    for i in range(4, 10):
+        exps[i] = (exps[i] & 0xFFFF00) | 0x2A                    # a crowded bucket in window 0
+    idx = np.zeros(windows * k, dtype=np.uint32)
+    start = np.zeros(windows * 257, dtype=np.uint32)
+    for w in range(windows):
+        order = sorted(range(k), key=lambda i: ((exps[i] >> (8 * w)) & 0xFF, i))
+        idx[w * k:(w + 1) * k] = order
+        digs = [(exps[i] >> (8 * w)) & 0xFF for i in order]
+        for d in range(257):
+            start[w * 257 + d] = sum(1 for x in digs if x < d)
+    bm = np.concatenate([eu.to_limbs(b * R % Q) for b in bases])
+    buckets = np.zeros(windows * 256 * 64, dtype=np.uint32)
+    wprod = np.zeros(windows * 64, dtype=np.uint32)
+    out = np.zeros(64, dtype=np.uint32)
+    assert lib.emu_modp_msm(eu.P(C), eu.P(bm), eu.P(idx), eu.P(start), windows, k, eu.P(buckets), eu.P(wprod),
+                            eu.P(out)) == 0
+    want = 1
+    for b, e in zip(bases, exps):
+        want = want * pow(b, e, Q) % Q
+    assert eu.from_limbs(out) == want

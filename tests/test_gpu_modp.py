@@ -257,3 +257,39 @@ def test_overlap_modes_and_lane_counts_agree(modp_group):
     finally:
         modp_group.ctx.set_int("modp_overlap", 3)
         modp_group.ctx.set_int("modp_tpi", 8)
+
+
+def test_bucket_multi_exp_equals_direct(modp_group):
+    """multi_exp / reconstruct through the bucket method (Pippenger, 8-bit windows) give the same element as
+    one exponentiation per base + product tree, and both equal the integer result."""
+    import mpvss_rs_b200 as m
+    rng = random.Random(77)
+    k = 300
+    bases = [pow(2, rng.randrange(Q - 1), Q) for _ in range(k)]
+    exps = [rng.randrange(Q - 1) for _ in range(k)]
+    exps[0], exps[1] = 0, 1
+    want = 1
+    for b, e in zip(bases, exps):
+        want = want * pow(b, e, Q) % Q
+    try:
+        modp_group.ctx.set_int("modp_msm", 0)
+        assert modp_group.multi_exp(bases, exps) == want
+        modp_group.ctx.set_int("modp_msm", 1)
+        assert modp_group.multi_exp(bases, exps) == want
+        # short exponents (fewer windows) and a single base
+        assert modp_group.multi_exp(bases[:5], [3, 0, 255, 256, 65535]) == \
+            pow(bases[0], 3, Q) * pow(bases[2], 255, Q) * pow(bases[3], 256, Q) * pow(bases[4], 65535, Q) % Q
+        assert modp_group.multi_exp(bases[:1], exps[5:6]) == pow(bases[0], exps[5], Q)
+        # reconstruct from a scattered subset, G^s against the oracle
+        n, t = 40, 27
+        sks, co, ws = _setup(n, t, 15)
+        dealer = m.Participant(modp_group)
+        pks = modp_group.fixed_base_exp(sks)
+        box = dealer.distribute_secret(SECRET, pks, t, coeffs=co, witnesses=ws)
+        sel = sorted(rng.sample(range(n), t))
+        sbs = dealer.extract_secret_shares(box, [sks[i] for i in sel], [ws[i] for i in sel])
+        tr = {}
+        assert dealer.reconstruct(sbs, box, trace=tr) == SECRET
+        assert tr["G_s"] == pow(2, co[0] % (Q - 1), Q)
+    finally:
+        modp_group.ctx.set_int("modp_msm", 2)

@@ -21,16 +21,53 @@ def test_polynomial_kats():
     assert pvss.poly_eval_mod(co, 278, 15486967) == 4115179
 
 
-def test_util_kats():
-    assert ext_gcd(26, 3)[0] == 1                             # util.rs:84-91 family
+def test_util_kats_verbatim():
+    """The reference's own vectors, value for value (src/util.rs:84-138, 164-190)."""
+    assert ext_gcd(26, 3) == (1, -1, 9)                       # util.rs:84-91: (g, x, y)
+    assert 26 * -1 + 3 * 9 == 1
+    assert mod_inverse(3, 26) == 9                            # util.rs:93-113
+    assert mod_inverse(4, 32) is None
+    values = [0, 1, 2, 3, 4, 5, 6]                            # util.rs:115-138
+    assert lagrange_coefficient(9, values) == (0, 1)
+    assert lagrange_coefficient(1, values) == (720, 120)
+    assert lagrange_coefficient(2, values) == (360, -24)
+    assert lagrange_coefficient(3, values) == (240, 12)
+    assert lagrange_coefficient(3, [1, 3, 4]) == (4, -2)
+    assert 1337 ^ 42 == 1299                                  # util.rs:155-161 (the U mask is this XOR)
+    h = hashlib.sha256()                                      # util.rs:164-190: SHA-256 over decimal strings
+    h.update(b"43589072349864890574839")
+    h.update(b"14735247304952934566")
+    assert h.hexdigest() == "e25e5b7edf4ea66e5238393fb4f183e0fc1593c69a522f9255a51bd0bc2b7ba7"
+    assert int(h.hexdigest(), 16) == 102389418883295205726805934198606438410316463205994911160958467170744727731111
+
+
+def test_util_kats_family():
     g, x, y = ext_gcd(240, 46)
     assert g == 2 and 240 * x + 46 * y == 2
-    assert mod_inverse(3, 26) == 9                            # util.rs:93-100
     assert mod_inverse(4, 26) is None
-    assert lagrange_coefficient(1, [1, 2, 3]) == (6, 2)       # util.rs:102-138 family: prod j / prod (j-i)
+    assert lagrange_coefficient(1, [1, 2, 3]) == (6, 2)       # prod j / prod (j - i)
     assert lagrange_coefficient(2, [1, 2, 3]) == (3, -1)
     assert lagrange_coefficient(3, [1, 2, 3]) == (2, 2)
     assert lagrange_coefficient(4, [1, 2, 3]) == (0, 1)
+
+
+def test_dleq_init_kat_verbatim():
+    """dleq.rs:356-377: a1 = g1^w, a2 = g2^w mod q for the reference's fixed small values."""
+    g = ModpGroup()
+    g1, g2, w = 8443, 1299721, 81647
+    a1, a2 = pvss.prover_commitments(g, g1, g2, w) if hasattr(pvss, "prover_commitments") else (g.exp(g1, w), g.exp(g2, w))
+    assert (a1, a2) == (pow(g1, w, g.q), pow(g2, w, g.q))
+
+
+def test_ristretto_scalar_conversion_kats_verbatim():
+    """ristretto255.rs:260-275, 697-717: BigInt -> Scalar -> BigInt round trips (big-endian in, LE inside)."""
+    g = Ristretto255Group()
+    for v in (0x0102030405060708, 123456789, 1 << 200):
+        assert g.scalar_from_int(v) == v
+        assert int.from_bytes(g.scalar_to_bytes(g.scalar_from_int(v)), "little") == v
+    assert len(g.scalar_to_bytes(g.scalar_from_int(42))) == 32          # ristretto255.rs:690-696
+    a, b, c = ED_L - 3, ED_L // 2 + 7, 11                                 # ristretto255.rs:340-376: sums agree
+    assert (g.scalar_from_int(a) + g.scalar_from_int(b) + g.scalar_from_int(c)) % ED_L == g.scalar_from_int((a + b + c) % ED_L)
 
 
 def test_dleq_response_kat():
@@ -118,6 +155,80 @@ def test_ristretto255_vectors():
     cs = [g.exp(g.generator(), x) for x in a]
     assert ristretto_eq(g.mul(g.mul(cs[0], cs[1]), cs[2]), g.exp(g.generator(), sum(a)))
     assert g.scalar_from_int(ED_L + 5) == 5                   # ristretto255.rs:78-105
+
+
+def _ed_compress(P):
+    """standard Ed25519 encoding of an extended point: y with the sign of x in bit 255"""
+    from oracle.groups import ED_P
+    X, Y, Z, _ = P
+    zi = pow(Z, -1, ED_P)
+    x, y = X * zi % ED_P, Y * zi % ED_P
+    return (y | ((x & 1) << 255)).to_bytes(32, "little")
+
+
+def test_ristretto_edwards_arithmetic_against_libsodium():
+    """The oracle's Edwards arithmetic under ristretto255 at FULL-WIDTH scalars against an independent
+    implementation: libsodium's crypto_scalarmult_ed25519_noclamp / crypto_core_ed25519_add through PyNaCl
+    (the bundled libsodium exports no ristretto255 API; the encodings are pinned by RFC 9496 above)."""
+    nb = pytest.importorskip("nacl.bindings")
+    g = Ristretto255Group()
+    rng = random.Random(2024)
+    B = g.generator()
+    Benc = _ed_compress(B)
+    assert Benc.hex() == "5866666666666666666666666666666666666666666666666666666666666666"  # Ed25519 basepoint
+    pts = []
+    for _ in range(12):
+        k = rng.randrange(1, ED_L)
+        P = g.exp(B, k)
+        want = nb.crypto_scalarmult_ed25519_noclamp(k.to_bytes(32, "little"), Benc)
+        assert _ed_compress(P) == want
+        pts.append((k, P, want))
+    for (k1, P1, e1), (k2, P2, e2) in zip(pts, pts[1:]):
+        assert _ed_compress(g.mul(P1, P2)) == nb.crypto_core_ed25519_add(e1, e2)
+        # variable-base: k2 * (k1 * B)
+        assert _ed_compress(g.exp(P1, k2)) == nb.crypto_scalarmult_ed25519_noclamp(k2.to_bytes(32, "little"), e1)
+    # the ristretto encoding of a point and of its libsodium twin decode to the same ristretto element
+    k, P, e = pts[0]
+    assert ristretto_eq(ristretto_decode(g.element_to_bytes(P)), P)
+
+
+def test_secp256k1_dleq_commitments_against_openssl():
+    """a1 = r*G + c*X, a2 = r*y + c*Y and the Horner X_i of the oracle against OpenSSL EC_POINT arithmetic
+    (oracle/cpu_baseline.c), both schedules, at full-width scalars."""
+    from oracle import cpu_baseline as cb
+    g = Secp256k1Group()
+    n, t = 5, 4
+    sks = synth.private_keys(8, n, "secp256k1", g.order())
+    pks = [g.generate_public_key(s) for s in sks]
+    box = pvss.distribute_secret(g, 99, pks, t, synth.coefficients(8, t, g.order()), synth.witnesses(8, n, g.order()))
+    tr = {}
+    assert pvss.verify_distribution_shares(g, box, trace=tr)
+    enc = g.element_to_bytes
+    keys = [enc(pk) for pk in pks]
+    for schedule in (0, 1):
+        xs, a1, a2 = cb.secp_verify([enc(c) for c in box.commitments], list(range(1, n + 1)), keys,
+                                    [enc(box.shares[k]) for k in keys], [box.responses[k] for k in keys],
+                                    box.challenge, nthreads=2, schedule=schedule)
+        assert xs == [enc(x) for x in tr["X"]] and a1 == [enc(x) for x in tr["a1"]] and a2 == [enc(x) for x in tr["a2"]]
+    # the k256 identity encoding question (33 zero bytes) never arises inside a valid transcript
+    assert all(e != bytes(33) for e in xs + a1 + a2)
+
+
+def test_modp_transcript_against_openssl():
+    """X_i, a1, a2 of the ModpGroup oracle against OpenSSL BN_mod_exp (both schedules)."""
+    from oracle import cpu_baseline as cb
+    g = ModpGroup()
+    n, t = 4, 3
+    sks = synth.private_keys(6, n, "modp", g.order(), g.q)
+    pks = [g.generate_public_key(s) for s in sks]
+    box = pvss.distribute_secret(g, 99, pks, t, synth.coefficients(6, t, g.order()), synth.witnesses(6, n, g.q))
+    tr = {}
+    assert pvss.verify_distribution_shares(g, box, trace=tr)
+    keys = [g.element_to_bytes(pk) for pk in pks]
+    for schedule in (0, 1):
+        xs, a1, a2 = cb.modp_verify(g.q, box.commitments, list(range(1, n + 1)), pks, [box.shares[k] for k in keys],
+                                    [box.responses[k] for k in keys], box.challenge, nthreads=2, schedule=schedule)
+        assert (xs, a1, a2) == (tr["X"], tr["a1"], tr["a2"])
 
 
 # ---- protocol round trips (reference tests restated with injected randomness) -------------
