@@ -614,77 +614,112 @@ struct Ec {
   }
 
   // ---- distribute_secret -------------------------------------------------------------------------
-  static int distribute(mpvss_ctx* ctx, size_t n, size_t t, const uint8_t* secret, size_t secret_len,
+  // With a communicator the call is collective: rank r deals participants r, r + N, ... (commitments are
+  // computed by every rank), one all-gather carries the framed transcript rows, a second one the shares,
+  // responses and X of all ranks.
+  static int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, size_t secret_len,
                         const uint8_t* coeffs, const uint8_t* witnesses, const uint8_t* publickeys,
                         uint8_t* commitments_out, uint8_t* shares_out, uint8_t* challenge_out, uint8_t* responses_out,
                         uint8_t* u_out, uint8_t* x_out) {
-    MPVSS_TRY(bad(ctx, n > 0 && t > 0 && t <= n && secret && coeffs && witnesses && publickeys && commitments_out &&
-                           shares_out && challenge_out && responses_out && u_out && secret_len <= EB,
-                  "distribute: bad arguments (threshold <= n, participant.rs:1100)"));
-    std::vector<uint32_t> co, wl, pos;
+    MPVSS_TRY(bad(ctx, n_total > 0 && t > 0 && t <= n_total && secret && coeffs && witnesses && publickeys &&
+                           commitments_out && shares_out && challenge_out && responses_out && u_out && secret_len <= EB,
+                  "distribute: bad arguments (threshold <= n, participant.rs:1100; secret at most one element long)"));
+    std::vector<uint32_t> co, wl_all;
     MPVSS_TRY(scalars_in(ctx, coeffs, t, co));
-    MPVSS_TRY(scalars_in(ctx, witnesses, n, wl));
-    MPVSS_TRY(positions_u32(ctx, nullptr, n, pos));
+    MPVSS_TRY(scalars_in(ctx, witnesses, n_total, wl_all));   // every rank checks all of them alike
+    const size_t n = transcript::local_count(n_total, ctx->nranks, ctx->rank), N = (size_t)ctx->nranks;
+    const size_t nn = std::max<size_t>(n, 1);
+    std::vector<uint32_t> pos(nn), wl(nn * 8);
+    for (size_t j = 0; j < n; ++j) {
+      const size_t i = (size_t)ctx->rank + j * N;
+      pos[j] = (uint32_t)(i + 1);
+      memcpy(&wl[j * 8], &wl_all[i * 8], 32);
+    }
+    std::vector<uint8_t> tpk;
+    const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
     DevBuf &dco = ctx->buf(0), &dp = ctx->buf(1), &dw = ctx->buf(2), &dpk = ctx->buf(3), &dC = ctx->buf(4),
            &dX = ctx->buf(5), &dY = ctx->buf(6), &dA1 = ctx->buf(7), &dA2 = ctx->buf(8), &dpos = ctx->buf(9),
-           &dst = ctx->buf(10);
+           &dst = ctx->buf(10), &dR = ctx->buf(13);
     MPVSS_TRY(h2d(ctx, dco, co.data(), t * 32));
-    MPVSS_TRY(h2d(ctx, dw, wl.data(), n * 32));
-    MPVSS_TRY(h2d(ctx, dpk, publickeys, n * EB));
-    MPVSS_TRY(h2d(ctx, dpos, pos.data(), n * 4));
-    MPVSS_CUDA(ctx, dp.ensure(n * 32));
+    MPVSS_TRY(h2d(ctx, dw, wl.data(), nn * 32));
+    if (n) MPVSS_TRY(h2d(ctx, dpk, pk, n * EB));
+    MPVSS_TRY(h2d(ctx, dpos, pos.data(), nn * 4));
+    MPVSS_CUDA(ctx, dp.ensure(nn * 32));
+    MPVSS_CUDA(ctx, dR.ensure(nn * 32));
     MPVSS_CUDA(ctx, dC.ensure(t * EB));
-    for (DevBuf* b : {&dX, &dY, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
-    MPVSS_CUDA(ctx, dst.ensure(2 * n * 4));
-    const uint8_t* G = ctx->gens.as<uint8_t>();
+    for (DevBuf* b : {&dX, &dY, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(nn * EB));
+    MPVSS_CUDA(ctx, dst.ensure(2 * nn * 4));
+    const transcript::Geom g = geom();
+    const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks);
+    MPVSS_CUDA(ctx, ctx->v_frames.ensure(rpr * g.row()));
+    MPVSS_CUDA(ctx, cudaMemsetAsync(ctx->v_frames.p, 0, rpr * g.row(), ctx->stream));
+    if (ctx->nranks > 1) MPVSS_CUDA(ctx, ctx->v_gather.ensure(N * rpr * g.row()));
     timing_begin(ctx);
-    // p_i = P(i) mod order (participant.rs:1155-1157 / 1619-1621)
-    ec::PolyArgs PA{KN(ctx), dco.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t, (uint32_t)n};
-    MPVSS_CUDA(ctx, ec::launch_poly(PA, ctx->stream));
-    timing_launch(ctx);
-    // C_j = a_j * g ; X_i = p_i * g (dealer shortcut: same element as sum_j i^j C_j) ; Y_i = p_i * y_i ;
-    // a1 = w * g ; a2 = w * y_i
+    // C_j = a_j * g (participant.rs:1130-1146 / 1603-1610), fixed-base table; every rank computes all of them
     MPVSS_TRY(dev_fixed(ctx, dco.as<uint32_t>(), t, dC.as<uint8_t>()));
-    MPVSS_TRY(dev_fixed(ctx, dp.as<uint32_t>(), n, dX.as<uint8_t>()));
-    MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dp.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dY.as<uint8_t>(),
-                       nullptr, dst.as<uint32_t>()));
-    MPVSS_TRY(dev_fixed(ctx, dw.as<uint32_t>(), n, dA1.as<uint8_t>()));
-    MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA2.as<uint8_t>(),
-                       nullptr, dst.as<uint32_t>() + n));
-    MPVSS_TRY(timing_end(ctx));
-    MPVSS_TRY(check_status(ctx, dst, 2 * n, "distribute (public keys)"));
-    std::vector<uint8_t> X(n * EB), A1(n * EB), A2(n * EB);
-    std::vector<uint32_t> p(n * 8);
-    MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
-    MPVSS_TRY(d2h(ctx, X.data(), dX, n * EB));
-    MPVSS_TRY(d2h(ctx, shares_out, dY, n * EB));
-    MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
-    MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
-    MPVSS_TRY(d2h(ctx, p.data(), dp, n * 32));
-    MPVSS_TRY(sync(ctx));
-    sha2::Sha256 h;
-    for (size_t i = 0; i < n; ++i) {  // participant.rs:1205-1212: (X, Y, a1, a2)
-      framed(h, X.data() + i * EB);
-      framed(h, shares_out + i * EB);
-      framed(h, A1.data() + i * EB);
-      framed(h, A2.data() + i * EB);
+    if (n) {
+      // p_i = P(i) mod order (participant.rs:1155-1157 / 1619-1621)
+      ec::PolyArgs PA{KN(ctx), dco.as<uint32_t>(), dpos.as<uint32_t>(), dp.as<uint32_t>(), (uint32_t)t, (uint32_t)n};
+      MPVSS_CUDA(ctx, ec::launch_poly(PA, ctx->stream));
+      timing_launch(ctx);
+      // X_i = p_i * g (dealer shortcut: same element as sum_j i^j C_j) ; Y_i = p_i * y_i ; a1 = w * g ; a2 = w * y_i
+      MPVSS_TRY(dev_fixed(ctx, dp.as<uint32_t>(), n, dX.as<uint8_t>()));
+      MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dp.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dY.as<uint8_t>(),
+                         nullptr, dst.as<uint32_t>()));
+      MPVSS_TRY(dev_fixed(ctx, dw.as<uint32_t>(), n, dA1.as<uint8_t>()));
+      MPVSS_TRY(dev_exp2(ctx, dpk.as<uint8_t>(), EB, dw.as<uint32_t>(), nullptr, 0, nullptr, 0, n, dA2.as<uint8_t>(),
+                         nullptr, dst.as<uint32_t>() + n));
+      ec::FrameArgs FA{dX.as<uint8_t>(), dY.as<uint8_t>(), dA1.as<uint8_t>(), dA2.as<uint8_t>(),
+                       ctx->v_frames.as<uint8_t>(), (uint32_t)n, (uint32_t)EB};
+      MPVSS_CUDA(ctx, ec::launch_frames(FA, ctx->stream));
+      timing_launch(ctx);
     }
+    MPVSS_TRY(timing_end(ctx));
+    // an undecodable public key: mark the rows (the collectives below must still run on every rank)
+    int bad_pk = n ? check_status(ctx, dst, 2 * n, "distribute (public keys)") : MPVSS_OK;
+    if (bad_pk != MPVSS_OK && bad_pk != MPVSS_ERR_ENCODING) return bad_pk;
+    if (bad_pk == MPVSS_ERR_ENCODING) {
+      const uint8_t mark = 0xff;
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->v_frames.p, &mark, 1, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const uint8_t* rows = ctx->v_frames.as<uint8_t>();
+    if (ctx->nranks > 1) {
+      MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * g.row()));
+      rows = ctx->v_gather.as<uint8_t>();
+    }
+    sha2::Sha256 h;  // participant.rs:1205-1212: (X, Y, a1, a2) in publickeys order
+    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h));
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (ctx->h_frames.as<uint8_t>()[(size_t)r * rpr * g.row()] == 0xff)
+        return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "distribute: invalid public key encoding");
     big::Int c = challenge_of(ctx, h, nullptr);
     scalar_out(c, challenge_out);
     const big::Int& ord = ctx->ec_order;
-    for (size_t i = 0; i < n; ++i) {  // r = w - p*c
-      big::Int pi(p.begin() + i * 8, p.begin() + i * 8 + 8), wi(wl.begin() + i * 8, wl.begin() + i * 8 + 8);
+    std::vector<uint32_t> p(nn * 8);
+    std::vector<uint8_t> resp(nn * SB);
+    MPVSS_TRY(d2h(ctx, p.data(), dp, nn * 32));
+    MPVSS_TRY(sync(ctx));
+    for (size_t j = 0; j < n; ++j) {  // r = w - p*c (participant.rs:1221-1231 / 1679-1688)
+      big::Int pi(p.begin() + j * 8, p.begin() + j * 8 + 8), wi(wl.begin() + j * 8, wl.begin() + j * 8 + 8);
       big::trim(pi);
       big::trim(wi);
-      scalar_out(big::submod(wi, big::mulmod(pi, c, ord), ord), responses_out + i * SB);
+      scalar_out(big::submod(wi, big::mulmod(pi, c, ord), ord), resp.data() + j * SB);
     }
+    MPVSS_TRY(h2d(ctx, dR, resp.data(), nn * SB));
+    const void* dev_rows[3] = {dY.p, dR.p, dX.p};
+    uint8_t* host_rows[3] = {shares_out, responses_out, x_out};
+    const size_t widths[3] = {EB, SB, EB};
+    MPVSS_TRY(transcript::gather_rows(ctx, dev_rows, host_rows, widths, x_out ? 3 : 2, n, n_total));
+    MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
+    MPVSS_TRY(sync(ctx));
     // U = secret XOR mask(a_0 * G)  (participant.rs:1234-1260 / 1691-1703); C_0 is that point
     big::Int mask;
     if (!T::mask_of(commitments_out, ord, &mask))
       return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "distribute: SHA-256(G^s) is not a canonical scalar");
     big::to_be(big::bxor(big::from_be(secret, secret_len), mask), u_out, EB);
-    if (x_out) memcpy(x_out, X.data(), n * EB);
-    return MPVSS_OK;
+    // the scratch buffers held secrets (coefficients, P(i), witnesses)
+    for (DevBuf* b : {&dco, &dp, &dw}) MPVSS_CUDA(ctx, cudaMemsetAsync(b->p, 0, b->cap, ctx->stream));
+    return sync(ctx);
   }
 
   // ---- extract_secret_share (batch) ----------------------------------------------------------------

@@ -56,6 +56,28 @@ __global__ void __launch_bounds__(64) resp_kernel(RespArgs A) { resp_body(A, blo
 __global__ void __launch_bounds__(64) poly_kernel(PolyArgs A) { poly_body(A, blockIdx.x * 64 + threadIdx.x); }
 __global__ void __launch_bounds__(64) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, blockIdx.x * 64 + threadIdx.x); }
 
+// Counting sort of the exponent bytes for the bucket method: CTA w orders the indices 0..k-1 by byte w of
+// their exponent (idx, window-major) and writes the 257 bucket boundaries (start).  The order inside a
+// bucket depends on the atomics and does not matter: a bucket is a product.
+__global__ void __launch_bounds__(256) msm_sort_kernel(const uint8_t* scalars, uint32_t k, uint32_t* idx, uint32_t* start) {
+  __shared__ uint32_t cnt[257], cur[256];
+  const uint32_t w = blockIdx.x;
+  for (uint32_t d = threadIdx.x; d < 257; d += blockDim.x) cnt[d] = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) atomicAdd(&cnt[scalars[(size_t)i * 256 + w] + 1u], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
+  __syncthreads();
+  for (uint32_t d = threadIdx.x; d < 257; d += blockDim.x) {
+    start[w * 257u + d] = cnt[d];
+    if (d < 256) cur[d] = cnt[d];
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x)
+    idx[(size_t)w * k + atomicAdd(&cur[scalars[(size_t)i * 256 + w]], 1u)] = i;
+}
+
 template <int TPI>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) msm_bucket_kernel(MsmBucketArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -175,9 +197,11 @@ cudaError_t launch_comb_build(int tpi, const CombArgs& A, cudaStream_t s) {
 }
 
 // bucket multi-exponentiation: buckets, per-window products, final fold (8 lanes per value)
-cudaError_t launch_msm(const MsmBucketArgs& B, uint32_t* wprod, uint32_t* out, cudaStream_t s) {
-  if (B.windows == 0 || B.k == 0) return cudaErrorInvalidValue;
+cudaError_t launch_msm(const MsmBucketArgs& B, const uint32_t* scalars, uint32_t* idx, uint32_t* start,
+                       uint32_t* wprod, uint32_t* out, cudaStream_t s) {
+  if (B.windows == 0 || B.windows > 256 || B.k == 0) return cudaErrorInvalidValue;
   constexpr int T = 8;
+  msm_sort_kernel<<<B.windows, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(scalars), B.k, idx, start);
   const uint32_t groups = B.windows * 255u, per_cta = WARPS_PER_CTA * (32 / T);
   size_t sm = WARPS_PER_CTA * msm_smem_words<T> * 4;
   msm_bucket_kernel<T><<<(groups + per_cta - 1) / per_cta, WARPS_PER_CTA * 32, sm, s>>>(B);

@@ -411,24 +411,13 @@ static int dev_product_tree(mpvss_ctx* ctx, uint32_t* v, DevBuf& tmp, size_t n) 
   return MPVSS_OK;
 }
 
-// Bucket method (Pippenger, 8-bit windows) for prod_i bases[i]^scalars[i]: the host sorts the indices of every
-// window by digit (counting sort over the exponent bytes it already holds), the device does the rest
-// (modp::launch_msm).  `db` holds the bases in normal form; the result lands in dout[0].
-static int multi_exp_buckets(mpvss_ctx* ctx, DevBuf& db, const uint8_t* scalars, size_t n, DevBuf& dout) {
-  const uint32_t windows = (windows_for(scalars, EB, n) + 1) / 2;  // exponent bytes in use
-  std::vector<uint32_t> idx((size_t)windows * n), start((size_t)windows * 257);
-  for (uint32_t w = 0; w < windows; ++w) {
-    uint32_t cnt[257] = {0};
-    for (size_t i = 0; i < n; ++i) ++cnt[scalars[i * EB + w] + 1];
-    for (int d = 0; d < 256; ++d) cnt[d + 1] += cnt[d];
-    memcpy(&start[(size_t)w * 257], cnt, sizeof cnt);
-    uint32_t cur[256];
-    memcpy(cur, cnt, sizeof cur);
-    for (size_t i = 0; i < n; ++i) idx[(size_t)w * n + cur[scalars[i * EB + w]]++] = (uint32_t)i;
-  }
+// Bucket method (Pippenger, 8-bit windows) for prod_i bases[i]^scalars[i], all on the device: counting sort of
+// every window's exponent bytes, bucket products, per-window products, final fold (modp::launch_msm).
+// `db` holds the bases in normal form, `de` the exponents; the result lands in dout[0].
+static int multi_exp_buckets(mpvss_ctx* ctx, DevBuf& db, DevBuf& de, uint32_t windows, size_t n, DevBuf& dout) {
   DevBuf &dm = ctx->buf(15), &didx = ctx->buf(16), &dst = ctx->buf(17), &dbk = ctx->buf(18), &dwp = ctx->buf(19);
-  MPVSS_TRY(h2d(ctx, didx, idx.data(), idx.size() * 4));
-  MPVSS_TRY(h2d(ctx, dst, start.data(), start.size() * 4));
+  MPVSS_CUDA(ctx, didx.ensure((size_t)windows * n * 4));
+  MPVSS_CUDA(ctx, dst.ensure((size_t)windows * 257 * 4));
   MPVSS_CUDA(ctx, dm.ensure(n * EB));
   MPVSS_CUDA(ctx, dbk.ensure((size_t)windows * 256 * EB));
   MPVSS_CUDA(ctx, dwp.ensure((size_t)windows * EB));
@@ -436,8 +425,9 @@ static int multi_exp_buckets(mpvss_ctx* ctx, DevBuf& db, const uint8_t* scalars,
   MPVSS_TRY(dev_mul(ctx, K, db.as<uint32_t>(), EW, nullptr, 0, 1, n, dm.as<uint32_t>()));  // to Montgomery form
   modp::MsmBucketArgs B{K, dm.as<uint32_t>(), didx.as<uint32_t>(), dst.as<uint32_t>(), dbk.as<uint32_t>(), windows,
                         (uint32_t)n};
-  MPVSS_CUDA(ctx, modp::launch_msm(B, dwp.as<uint32_t>(), dout.as<uint32_t>(), ctx->stream));
-  timing_launch(ctx, 3);
+  MPVSS_CUDA(ctx, modp::launch_msm(B, de.as<uint32_t>(), didx.as<uint32_t>(), dst.as<uint32_t>(), dwp.as<uint32_t>(),
+                                   dout.as<uint32_t>(), ctx->stream));
+  timing_launch(ctx, 4);
   return MPVSS_OK;
 }
 
@@ -451,11 +441,11 @@ int multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size
   // squarings in its final fold), so it takes over once the direct form needs several waves ("modp_msm":
   // 0 never, 1 always, 2 = automatic).
   const bool buckets = ctx->modp_msm == 1 || (ctx->modp_msm == 2 && n >= (size_t)ctx->msm_threshold);
+  MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
   timing_begin(ctx);
   if (buckets) {
-    MPVSS_TRY(multi_exp_buckets(ctx, db, scalars, n, dout));
+    MPVSS_TRY(multi_exp_buckets(ctx, db, de, (windows_for(scalars, EB, n) + 1) / 2, n, dout));
   } else {
-    MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
     MPVSS_TRY(dev_exp2(ctx, ctx->consts_q.as<uint32_t>(), db.as<uint32_t>(), EW, de.as<uint32_t>(), EW,
                        windows_for(scalars, EB, n), nullptr, 0, nullptr, 0, 0, n, dout.as<uint32_t>()));
     MPVSS_TRY(dev_product_tree(ctx, dout.as<uint32_t>(), tmp, n));
@@ -688,38 +678,6 @@ int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t
 }
 
 // --------------------------------------------------------------- distribute ----
-// Bring this rank's n local rows of `width` bytes (device) to the host in `publickeys` order for all
-// n_total participants: a plain copy without a communicator, else one all-gather of `kinds` row sets at once
-// ([rank][kind][rows_per_rank][width]) and a scatter on the host.
-static int gather_rows(mpvss_ctx* ctx, const void* const* dev_local, uint8_t* const* host_all, int kinds, size_t n,
-                       size_t n_total, size_t width) {
-  if (ctx->nranks <= 1) {
-    for (int k = 0; k < kinds; ++k)
-      if (host_all[k]) MPVSS_CUDA(ctx, cudaMemcpyAsync(host_all[k], dev_local[k], n * width, cudaMemcpyDeviceToHost, ctx->stream));
-    return sync(ctx);
-  }
-  const size_t rpr = transcript::rows_per_rank(n_total, ctx->nranks), N = (size_t)ctx->nranks;
-  const size_t per_rank = (size_t)kinds * rpr * width;
-  DevBuf& loc = ctx->buf(22);
-  MPVSS_CUDA(ctx, loc.ensure(per_rank));
-  MPVSS_CUDA(ctx, ctx->v_gather.ensure(N * per_rank));
-  MPVSS_CUDA(ctx, cudaMemsetAsync(loc.p, 0, per_rank, ctx->stream));
-  for (int k = 0; k < kinds; ++k)
-    if (n) MPVSS_CUDA(ctx, cudaMemcpyAsync(loc.as<uint8_t>() + (size_t)k * rpr * width, dev_local[k], n * width,
-                                           cudaMemcpyDeviceToDevice, ctx->stream));
-  MPVSS_TRY(comm_allgather(ctx, loc.p, ctx->v_gather.p, per_rank));
-  MPVSS_CUDA(ctx, ctx->h_frames.ensure(N * per_rank));
-  MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->h_frames.p, ctx->v_gather.p, N * per_rank, cudaMemcpyDeviceToHost, ctx->stream));
-  MPVSS_TRY(sync(ctx));
-  const uint8_t* g = ctx->h_frames.as<uint8_t>();
-  for (int k = 0; k < kinds; ++k) {
-    if (!host_all[k]) continue;
-    for (size_t i = 0; i < n_total; ++i)
-      memcpy(host_all[k] + i * width, g + (i % N) * per_rank + ((size_t)k * rpr + i / N) * width, width);
-  }
-  return MPVSS_OK;
-}
-
 int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, size_t secret_len,
                const uint8_t* coeffs, const uint8_t* witnesses, const uint8_t* publickeys, uint8_t* commitments_out,
                uint8_t* shares_out, uint8_t* challenge_out, uint8_t* responses_out, uint8_t* u_out, uint8_t* x_out) {
@@ -821,7 +779,8 @@ int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, 
   }
   const void* dev_rows[3] = {dY.p, dR.p, dX.p};
   uint8_t* host_rows[3] = {shares_out, responses_out, x_out};
-  MPVSS_TRY(gather_rows(ctx, dev_rows, host_rows, x_out ? 3 : 2, n, n_total, EB));
+  const size_t widths[3] = {EB, EB, EB};
+  MPVSS_TRY(transcript::gather_rows(ctx, dev_rows, host_rows, widths, x_out ? 3 : 2, n, n_total));
   uint8_t gs[EB];
   MPVSS_TRY(d2h(ctx, commitments_out, dC, t * EB));
   MPVSS_TRY(d2h(ctx, gs, dGs, EB));

@@ -92,3 +92,45 @@ inline int fetch_and_hash(mpvss_ctx* ctx, const uint8_t* dev_rows, size_t n_tota
 // without a communicator
 int comm_allgather(mpvss_ctx* ctx, const void* src, void* dst, size_t bytes);
 void comm_release(mpvss_ctx* ctx);
+
+namespace transcript {
+// Bring this rank's n local rows of `kinds` row sets (device, widths[k] bytes per row) to the host in
+// `publickeys` order for all n_total participants: plain copies without a communicator, else ONE all-gather of
+// all row sets ([rank][kind][rows_per_rank][width]) and a scatter on the host.  host_all[k] may be null.
+inline int gather_rows(mpvss_ctx* ctx, const void* const* dev_local, uint8_t* const* host_all, const size_t* widths,
+                       int kinds, size_t n, size_t n_total) {
+  if (ctx->nranks <= 1) {
+    for (int k = 0; k < kinds; ++k)
+      if (host_all[k])
+        MPVSS_CUDA(ctx, cudaMemcpyAsync(host_all[k], dev_local[k], n * widths[k], cudaMemcpyDeviceToHost, ctx->stream));
+    MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPVSS_OK;
+  }
+  const size_t rpr = rows_per_rank(n_total, ctx->nranks), N = (size_t)ctx->nranks;
+  size_t per_rank = 0, off[8] = {0};
+  for (int k = 0; k < kinds; ++k) {
+    off[k] = per_rank;
+    per_rank += ((rpr * widths[k] + 15) / 16) * 16;
+  }
+  DevBuf& loc = ctx->buf(22);
+  MPVSS_CUDA(ctx, loc.ensure(per_rank));
+  MPVSS_CUDA(ctx, ctx->v_gather.ensure(N * per_rank));
+  MPVSS_CUDA(ctx, cudaMemsetAsync(loc.p, 0, per_rank, ctx->stream));
+  for (int k = 0; k < kinds; ++k)
+    if (n)
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(loc.as<uint8_t>() + off[k], dev_local[k], n * widths[k], cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+  int st = comm_allgather(ctx, loc.p, ctx->v_gather.p, per_rank);
+  if (st != MPVSS_OK) return st;
+  MPVSS_CUDA(ctx, ctx->h_frames.ensure(N * per_rank));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(ctx->h_frames.p, ctx->v_gather.p, N * per_rank, cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint8_t* g = ctx->h_frames.as<uint8_t>();
+  for (int k = 0; k < kinds; ++k) {
+    if (!host_all[k]) continue;
+    for (size_t i = 0; i < n_total; ++i)
+      memcpy(host_all[k] + i * widths[k], g + (i % N) * per_rank + off[k] + (i / N) * widths[k], widths[k]);
+  }
+  return MPVSS_OK;
+}
+}  // namespace transcript
