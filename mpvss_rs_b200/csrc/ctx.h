@@ -79,7 +79,8 @@ struct mpvss_ctx {
   DevBuf comb[2];            // fixed-base tables of the two generators (built on first use, 16.8 MB each)
   int modp_comb = 1;         // use them ("modp_comb")
   int modp_msm = 2;          // multi_exp / reconstruct by buckets: 0 never, 1 always, 2 from msm_threshold bases on
-  int msm_threshold = 8192;
+  int msm_threshold = 512;   // measured on B200: buckets 9.0 / 9.8 / 12.4 / 22.5 ms against 9.2 / 13.4 / 33.1 / 119.6 ms direct
+                             // at k = 683 / 2731 / 10923 / 43691 (profiles/msm_r02.json)
   bool validate = false;     // range / subgroup check of ModpGroup elements entering the verify calls
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----

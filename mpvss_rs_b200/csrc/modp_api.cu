@@ -436,10 +436,10 @@ int multi_exp(mpvss_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, size
   DevBuf &db = ctx->buf(0), &de = ctx->buf(1), &dout = ctx->buf(2), &tmp = ctx->buf(3);
   MPVSS_TRY(h2d(ctx, db, bases, n * EB));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
-  // One exponentiation per base + product tree has a depth of ~2560 products whatever n is, as long as all
-  // n / 4 warps are resident at once; the bucket method does 8x less work but is just as deep (2040 sequential
-  // squarings in its final fold), so it takes over once the direct form needs several waves ("modp_msm":
-  // 0 never, 1 always, 2 = automatic).
+  // One exponentiation per base + product tree is ~2560 products deep whatever n is; the bucket method does
+  // 8x less work but is nearly as deep (the 2040 sequential squarings of its final fold, which no method
+  // avoids for fresh bases), so it wins by 1.4x at k = 2731 and by 5x at k = 43691 where the direct form
+  // runs in several waves ("modp_msm": 0 never, 1 always, 2 = from msm_threshold bases on).
   const bool buckets = ctx->modp_msm == 1 || (ctx->modp_msm == 2 && n >= (size_t)ctx->msm_threshold);
   MPVSS_TRY(h2d(ctx, de, scalars, n * EB));
   timing_begin(ctx);

@@ -41,4 +41,4 @@ for name, n, t in CONFIGS:
     assert timed(f"reconstruct (k={t})", lambda: d.reconstruct(sbs, box)) == 123456789
     out.append(row)
     print(json.dumps(row), flush=True)
-json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "phases.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "phases_r02.json"), "w"), indent=1)

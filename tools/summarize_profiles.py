@@ -4,7 +4,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-RND = sys.argv[1] if len(sys.argv) > 1 else "r01"
+RND = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 WANT = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__occupancy_limit', 'launch__waves_per_multiprocessor', 'sm__warps_active.avg.pct_of_peak_sustained_active',
@@ -34,9 +34,9 @@ def launches():
         f.write("%-62s %6s %12s %7s\n" % ("kernel", "count", "total ms", "share"))
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-62s %6d %12.3f %6.1f%%\n" % (k[:62], v[0], v[1], 100 * v[1] / tot))
-        f.write("\nlast timed step (mul_kernel = Montgomery conversion of the commitments, horner_kernel = X_i,\nexp2_kernel x2 = a2 = y^r Y^c and a1 = g^r X^c with the fixed-base table):\n")
+        f.write("\nlast timed step (mul_kernel = Montgomery conversion of the commitments, horner_kernel = X_i,\nexp2_kernel x2 = a2 = y^r Y^c and a1 = g^r X^c with the fixed-base table, frame_kernel = transcript rows):\n")
         own = [r for r in rows if 'modp::' in r[4] or 'ec::' in r[4]]
-        for r in own[-4:]:
+        for r in own[-5:]:
             f.write("  %-58s grid %-14s block %-12s %10.3f ms\n" % (r[4][:58], r[8], r[7], float(r[-1]) / 1e6))
     shutil.copy(src, os.path.join(P, f"launches_{RND}.csv"))
 
@@ -58,13 +58,16 @@ def full(rep, out, title):
 
 
 launches()
-full("prof_horner_final.ncu-rep", f"horner_{RND}_ncu.txt",
+full(f"prof_horner_{RND}.ncu-rep", f"horner_{RND}_ncu.txt",
      "ncu --set full --clock-control none --import-source on -k regex:horner_kernel -s 1 -c 1 python tools/profile_verify.py --n 4096 --t 2731\n"
      "modp::horner_kernel<8, true> at the bench configuration (n = 4096, t = 2731); selected raw metrics")
-full("prof_ec_horner_secp.ncu-rep", f"ec_horner_secp256k1_{RND}_ncu.txt",
+full(f"prof_ec_horner_secp_{RND}.ncu-rep", f"ec_horner_secp256k1_{RND}_ncu.txt",
      "ncu --set full --clock-control none -k regex:horner_kernel -c 1 python bench.py --group secp256k1 --steps 1 --warmup 0\n"
-     "ec::horner_kernel<secp::SecpCurve> (n = 4096, t = 2731, 16 chunks); selected raw metrics")
-full("prof_ec_horner_rist.ncu-rep", f"ec_horner_ristretto255_{RND}_ncu.txt",
+     "ec::horner_kernel<secp::SecpCurve> (n = 4096, t = 2731, 18 chunks: one wave); selected raw metrics")
+full(f"prof_ec_horner_rist_{RND}.ncu-rep", f"ec_horner_ristretto255_{RND}_ncu.txt",
      "ncu --set full --clock-control none -k regex:horner_kernel -s 1 -c 1 python bench.py --group ristretto255 --steps 1 --warmup 1\n"
-     "ec::horner_kernel<rist::RistCurve> (n = 4096, t = 2731, 16 chunks); selected raw metrics")
+     "ec::horner_kernel<rist::RistCurve> (n = 4096, t = 2731, 18 chunks: one wave); selected raw metrics")
+full(f"prof_ec_exp2_secp_{RND}.ncu-rep", f"ec_exp2_comb_secp256k1_{RND}_ncu.txt",
+     "ncu --set full --clock-control none -k regex:exp2_comb_kernel -c 1 python bench.py --group secp256k1 --steps 1 --warmup 1\n"
+     "ec::exp2_comb_kernel<secp::SecpCurve>: a1 = r*G + c*X with the generator table staged through shared memory; selected raw metrics")
 print(open(os.path.join(P, f"launches_{RND}_summary.txt")).read())
