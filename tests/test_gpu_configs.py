@@ -194,3 +194,34 @@ def test_two_gpu_sharded_calls_match_single_gpu():
     for rank in (0, 1):
         for gname, v in res[rank].items():
             assert v == (True, True, True, True, False), (rank, gname, v)
+
+
+def test_two_gpu_threads_in_one_process():
+    """The Rust-shaped use: ONE process, one context per GPU, one thread per
+    context; the collective verify returns the single-GPU digest and verdict on both threads."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from mpvss_rs_b200.lib import comm_unique_id
+    og = GROUPS["modp"]()
+    n, t = 23, 8
+    g1 = m.Group("modp", device=0)
+    sks = synth.private_keys(31, n, "modp", og.order(), og.q)
+    pks = g1.fixed_base_exp(sks)
+    box = m.Participant(g1).distribute_secret(SECRET, pks, t, coeffs=synth.coefficients(31, t, og.order()),
+                                              witnesses=synth.witnesses(31, n, og.q))
+    ref = {}
+    assert m.Participant(g1).verify_distribution_shares(box, trace=ref) is True
+    uid, groups, out = comm_unique_id(), [m.Group("modp", device=r) for r in range(2)], [None, None]
+
+    def worker(r):
+        groups[r].ctx.comm_init(uid, 2, r)
+        tr = {}
+        out[r] = (m.Participant(groups[r]).verify_distribution_shares(box, trace=tr), tr["digest"])
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(300)
+    assert out[0] == out[1] == (True, ref["digest"])
