@@ -427,6 +427,7 @@ def main():
     ap.add_argument("--group", default="modp", choices=["modp", "secp256k1", "ristretto255"])
     ap.add_argument("--ec-threads", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0, 2 or 3)")
+    ap.add_argument("--wpc", type=int, default=0, help="override warps per CTA of the MODP Horner launch (1..4)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5", action="store_true", help="also time BASELINE config 5 (n=65536 t=43691) [default at 8 GPUs]")
@@ -469,6 +470,8 @@ def main():
             g.ctx.set_int("ec_threads", args.ec_threads)
         if args.overlap >= 0 and name == "modp":
             g.ctx.set_int("modp_overlap", args.overlap)
+        if args.wpc and name == "modp":
+            g.ctx.set_int("modp_wpc", args.wpc)
         if joined and world > 1:
             g.join(rank, world, dist)           # NCCL communicator inside the library
         return g

@@ -146,6 +146,11 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->modp_overlap = value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "modp_wpc") {
+    if (value < 0 || value > 4) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_wpc must be 0 (automatic) .. 4");
+    ctx->modp_wpc = value;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "modp_msm") {
     if (value < 0 || value > 2) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_msm must be 0, 1 or 2");
     ctx->modp_msm = value;

@@ -70,6 +70,8 @@ struct mpvss_ctx {
   int modp_tpi = 8;
   bool modp_tpi_auto = true;  // Horner launches pick 4 lanes per value when a launch has >= 32768 positions
   int v_tpi = 8;              // lanes per value of the staged Horner plan
+  int v_wpc = 1;              // warps per CTA of the staged Horner plan
+  int modp_wpc = 0;           // "modp_wpc": force warps per CTA of the Horner launch (0 = automatic)
   size_t exp2_filler_ctas = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs
   int modp_overlap = 3;  // a2 = y^r Y^c (independent of X): 0 before the Horner launch on the main stream; 2 regular launch on a
                          // side stream after it; 3 (default) persistent one-warp CTAs, one per SM, on a side stream after it

@@ -380,14 +380,31 @@ struct Ec {
     MPVSS_TRY(d2h(ctx, out, dout, n * EB));
     return sync(ctx);
   }
+  // `undecodable`: when given, instances whose elements or scalars do not decode are flagged there (and get
+  // an arbitrary a1 / a2) instead of failing the whole call -- verify_share returns false for them
   static int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2,
                                 const uint8_t* h2, const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n,
-                                uint8_t* a1, uint8_t* a2) {
+                                uint8_t* a1, uint8_t* a2, std::vector<uint8_t>* undecodable = nullptr) {
     MPVSS_TRY(bad(ctx, g1 && h1 && g2 && h2 && r && c && a1 && a2 && n > 0 && (c_stride == 0 || c_stride == SB),
                   "dleq_verify_commit: bad arguments"));
     std::vector<uint32_t> rl, cl;
-    MPVSS_TRY(scalars_in(ctx, r, n, rl));
-    MPVSS_TRY(scalars_in(ctx, c, c_stride ? n : 1, cl));
+    if (undecodable) {
+      undecodable->assign(n, 0);
+      rl.assign(n * 8, 0);
+      cl.assign((c_stride ? n : 1) * 8, 0);
+      for (size_t i = 0; i < n; ++i) {  // per-instance: a non-canonical scalar only spoils its own share
+        std::vector<uint32_t> one;
+        if (scalars_in(ctx, r + i * SB, 1, one) != MPVSS_OK) (*undecodable)[i] = 1;
+        else memcpy(&rl[i * 8], one.data(), 32);
+        if (c_stride || i == 0) {
+          if (scalars_in(ctx, c + i * c_stride, 1, one) != MPVSS_OK) (*undecodable)[i] = 1;
+          else memcpy(&cl[i * 8], one.data(), 32);
+        }
+      }
+    } else {
+      MPVSS_TRY(scalars_in(ctx, r, n, rl));
+      MPVSS_TRY(scalars_in(ctx, c, c_stride ? n : 1, cl));
+    }
     DevBuf &dg1 = ctx->buf(0), &dh1 = ctx->buf(1), &dg2 = ctx->buf(2), &dh2 = ctx->buf(3), &dr = ctx->buf(4),
            &dc = ctx->buf(5), &da1 = ctx->buf(6), &da2 = ctx->buf(7), &ds1 = ctx->buf(8), &ds2 = ctx->buf(9);
     MPVSS_TRY(h2d(ctx, dg1, g1, EB));
@@ -406,8 +423,17 @@ struct Ec {
     MPVSS_TRY(dev_exp2(ctx, dg2.as<uint8_t>(), EB, dr.as<uint32_t>(), dh2.as<uint8_t>(), EB, dc.as<uint32_t>(), cs, n,
                        da2.as<uint8_t>(), nullptr, ds2.as<uint32_t>()));
     MPVSS_TRY(timing_end(ctx));
-    MPVSS_TRY(check_status(ctx, ds1, n, "dleq_verify_commit (g1/h1)"));
-    MPVSS_TRY(check_status(ctx, ds2, n, "dleq_verify_commit (g2/h2)"));
+    if (undecodable) {
+      std::vector<uint32_t> s1(n), s2(n);
+      MPVSS_TRY(d2h(ctx, s1.data(), ds1, n * 4));
+      MPVSS_TRY(d2h(ctx, s2.data(), ds2, n * 4));
+      MPVSS_TRY(sync(ctx));
+      for (size_t i = 0; i < n; ++i)
+        if (s1[i] == 1 || s2[i] == 1) (*undecodable)[i] = 1;
+    } else {
+      MPVSS_TRY(check_status(ctx, ds1, n, "dleq_verify_commit (g1/h1)"));
+      MPVSS_TRY(check_status(ctx, ds2, n, "dleq_verify_commit (g2/h2)"));
+    }
     MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
     MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
     return sync(ctx);
@@ -467,7 +493,8 @@ struct Ec {
                   "verify_distribution: bad arguments"));
     // every rank checks ALL positions and scalars, so that a malformed box is rejected by all ranks alike
     std::vector<uint32_t> pos_all, rl_all, cl;
-    MPVSS_TRY(positions_u32(ctx, positions, n_total, pos_all));
+    if (positions_u32(ctx, positions, n_total, pos_all) != MPVSS_OK)   // box content: verifies as false
+      return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "verify_distribution: position out of range [1, 2^31)");
     MPVSS_TRY(scalars_in(ctx, responses, n_total, rl_all));
     MPVSS_TRY(scalars_in(ctx, challenge, 1, cl));
     const size_t n = transcript::local_count(n_total, ctx->nranks, ctx->rank), N = (size_t)ctx->nranks;
@@ -785,16 +812,17 @@ struct Ec {
                            int* ok_out) {
     MPVSS_TRY(bad(ctx, n > 0 && publickeys && shares && enc_shares && challenges && responses && ok_out,
                   "verify_shares: bad arguments"));
-    std::vector<uint8_t> a1(n * EB), a2(n * EB);
+    std::vector<uint8_t> a1(n * EB), a2(n * EB), undecodable;
     MPVSS_TRY(dleq_verify_commit(ctx, ctx->ec_gen.data(), publickeys, shares, enc_shares, responses, challenges, SB, n,
-                                 a1.data(), a2.data()));
+                                 a1.data(), a2.data(), &undecodable));
     for (size_t i = 0; i < n; ++i) {
       sha2::Sha256 h;
       framed(h, publickeys + i * EB);
       framed(h, enc_shares + i * EB);
       framed(h, a1.data() + i * EB);
       framed(h, a2.data() + i * EB);
-      ok_out[i] = big::cmp(challenge_of(ctx, h, nullptr), scalar_big(challenges + i * SB)) == 0;
+      // a share box that does not decode is simply not valid (bytes_to_element -> None in the reference)
+      ok_out[i] = !undecodable[i] && big::cmp(challenge_of(ctx, h, nullptr), scalar_big(challenges + i * SB)) == 0;
     }
     return MPVSS_OK;
   }

@@ -7,10 +7,10 @@ namespace modp {
 
 
 template <int TPI, bool NP1>
-__global__ void __launch_bounds__(HORNER_WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
+__global__ void __launch_bounds__(HORNER_MAX_WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
-  horner_body<TPI, NP1>(A, blockIdx.x * HORNER_WARPS_PER_CTA + w, smem + w * horner_smem_words<TPI>,
+  horner_body<TPI, NP1>(A, blockIdx.x * (blockDim.x >> 5) + w, smem + w * horner_smem_words<TPI>,
                         A.nops ? A.nops[blockIdx.x] : A.nops_all);
 }
 
@@ -121,19 +121,20 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
   }
 
 cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStream_t s) {
-  if (A.n == 0 || A.t == 0) return cudaErrorInvalidValue;
+  if (A.n == 0 || A.t == 0 || A.warps_per_cta > (uint32_t)HORNER_MAX_WARPS_PER_CTA) return cudaErrorInvalidValue;
   MODP_DISPATCH(tpi, {
-    size_t sm = HORNER_WARPS_PER_CTA * horner_smem_words<T> * 4;
-    uint32_t per_cta = HORNER_WARPS_PER_CTA * (32 / T);
+    const uint32_t wpc = A.warps_per_cta ? A.warps_per_cta : 1u;
+    size_t sm = wpc * horner_smem_words<T> * 4;
+    uint32_t per_cta = wpc * (32 / T);
     uint32_t grid = (A.n + per_cta - 1) / per_cta;
     if (np_is_one) {
       cudaError_t e = set_smem(horner_kernel<T, true>, sm);
       if (e != cudaSuccess) return e;
-      horner_kernel<T, true><<<grid, HORNER_WARPS_PER_CTA * 32, sm, s>>>(A);
+      horner_kernel<T, true><<<grid, wpc * 32, sm, s>>>(A);
     } else {
       cudaError_t e = set_smem(horner_kernel<T, false>, sm);
       if (e != cudaSuccess) return e;
-      horner_kernel<T, false><<<grid, HORNER_WARPS_PER_CTA * 32, sm, s>>>(A);
+      horner_kernel<T, false><<<grid, wpc * 32, sm, s>>>(A);
     }
   });
   return cudaGetLastError();

@@ -246,8 +246,17 @@ static int horner_tpi(const mpvss_ctx* ctx, size_t n) {
   return ctx->modp_tpi;
 }
 
+// warps per CTA of the Horner launch ("modp_wpc" tunable; default one warp per CTA)
+static int horner_wpc(const mpvss_ctx* ctx, size_t n, int tpi) {
+  if (ctx->modp_wpc) return ctx->modp_wpc;
+  (void)n;
+  (void)tpi;
+  return 1;  // measured: 4 warps per CTA change nothing at 8 .. 16 warps per SM (tools/wpc_sweep.sh)
+}
+
 struct PosPlan {
   int tpi = 8;
+  int wpc = 1;                  // warps per CTA of the Horner launch
   std::vector<uint32_t> slot;   // padded instance array: output row of the instance, 0xffffffff = padding
   std::vector<uint16_t> ops;    // HC_OPS ops per instance: one Horner step (modp_chain.h)
   std::vector<uint32_t> nops;   // ops per step, per CTA
@@ -283,7 +292,8 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
     by[ops[i].size()].push_back((uint32_t)i);
   }
   plan.tpi = horner_tpi(ctx, n);
-  const size_t per_cta = modp::HORNER_WARPS_PER_CTA * (32 / plan.tpi);
+  plan.wpc = horner_wpc(ctx, n, plan.tpi);
+  const size_t per_cta = (size_t)plan.wpc * (32 / plan.tpi);
   plan.slot.clear(); plan.ops.clear(); plan.nops.clear();
   plan.nops_max = 1;
   for (uint32_t len = modp_chain::OPS_MAX; len >= 1; --len) {
@@ -303,12 +313,12 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
 }
 
 // commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
-static int dev_horner(mpvss_ctx* ctx, int tpi, const uint32_t* comm, DevBuf& cm, size_t t, const uint16_t* ops,
+static int dev_horner(mpvss_ctx* ctx, int tpi, int wpc, const uint32_t* comm, DevBuf& cm, size_t t, const uint16_t* ops,
                       const uint32_t* slot, const uint32_t* nops, size_t n_padded, uint32_t* x) {
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
   MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
   modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), ops, slot, nops, x, (uint32_t)t,
-                     (uint32_t)n_padded, 0};
+                     (uint32_t)n_padded, 0, (uint32_t)wpc};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
   MPVSS_CUDA(ctx, modp::launch_horner(tpi, A, ctx->modp_np1, ctx->stream));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
@@ -330,7 +340,7 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
   MPVSS_TRY(h2d(ctx, dno, plan.nops.data(), plan.nops.size() * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
   timing_begin(ctx);
-  MPVSS_TRY(dev_horner(ctx, plan.tpi, dc.as<uint32_t>(), dcm, t, dops.as<uint16_t>(), dsl.as<uint32_t>(),
+  MPVSS_TRY(dev_horner(ctx, plan.tpi, plan.wpc, dc.as<uint32_t>(), dcm, t, dops.as<uint16_t>(), dsl.as<uint32_t>(),
                        dno.as<uint32_t>(), np, dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   ctx->horner_sqr = plan.sqr * (t - 1);
@@ -533,11 +543,15 @@ int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commit
     const size_t i = (size_t)ctx->rank + j * (size_t)ctx->nranks;
     pos[j] = positions ? positions[i] : (int64_t)i + 1;
   }
+  for (size_t i = 0; i < n_total; ++i)   // box content, checked alike by every rank: verifies as false
+    if (positions && (positions[i] < 1 || positions[i] > 0x7fffffff))
+      return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "verify_distribution: position out of range [1, 2^31)");
   PosPlan plan;
   if (n) MPVSS_TRY(prep_positions(ctx, pos.data(), n, plan));
   ctx->v_np = plan.slot.size();
   ctx->v_nops_max = plan.nops_max;
   ctx->v_tpi = plan.tpi;
+  ctx->v_wpc = plan.wpc;
   ctx->horner_sqr = plan.sqr * (t - 1);
   ctx->horner_mul = plan.mul * (t - 1);
   std::vector<uint8_t> tpk, ty, tr;
@@ -607,11 +621,18 @@ static int verify_kernels(mpvss_ctx* ctx) {
     const double filler = (double)rounds * (5.0 * (ctx->v_rwin + ctx->v_cwin) + 30.0);
     const double horner = (double)(t > 1 ? t - 1 : 0) * (double)ctx->v_nops_max;
     if (filler > 0.6 * horner) overlap = 0;
+    // ... and only when the Horner launch leaves a hole: W one-warp CTAs fill the 4 schedulers of every SM
+    // evenly when W is a multiple of 4 * SMs; the filler warp then becomes a third warp on one scheduler per SM
+    // and slows its two Horner warps for the whole launch (n = 4736 = 8 warps per SM: 308 instead of 261 ms)
+    const size_t slots = (size_t)4 * (size_t)ctx->sm_count;
+    const size_t hw = ctx->v_np / (32 / (size_t)ctx->v_tpi);
+    const size_t holes = (slots - hw % slots) % slots;
+    if (holes < (size_t)ctx->sm_count) overlap = 0;
   }
   const bool side = overlap == 2 || overlap == 3;
   if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
-  MPVSS_TRY(dev_horner(ctx, ctx->v_tpi, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_ops.as<uint16_t>(),
+  MPVSS_TRY(dev_horner(ctx, ctx->v_tpi, ctx->v_wpc, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_ops.as<uint16_t>(),
                        ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
   if (side) {
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));

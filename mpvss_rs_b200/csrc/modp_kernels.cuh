@@ -130,6 +130,7 @@ struct HornerArgs {
                            // ptxas needs no WARPSYNC around the shuffles); nullptr: `nops_all` everywhere
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
   uint32_t t, n, nops_all;
+  uint32_t warps_per_cta;  // launch shape (0 = 1); nops is indexed by CTA
 };
 
 constexpr int HC_SLOTS = 6;   // == modp_chain::SLOTS; slot 6 = Montgomery one, slot 7 = C_j

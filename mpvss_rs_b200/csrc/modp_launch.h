@@ -5,8 +5,10 @@
 
 namespace modp {
 constexpr int WARPS_PER_CTA = 4;     // exponentiation / multiplication kernels
-constexpr int HORNER_WARPS_PER_CTA = 1;  // Horner kernels: one warp per CTA keeps the per-CTA digit classes
-                                         // fine-grained and lets the block scheduler spread warps evenly
+// Horner launches use one warp per CTA (fine-grained op-count classes; the block scheduler then leaves one warp
+// slot per SM free for the a2 filler at n = 4096); up to 4 warps per CTA through the "modp_wpc" tunable, which
+// measured no different at 8 .. 16 warps per SM.
+constexpr int HORNER_MAX_WARPS_PER_CTA = 4;
 cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStream_t s);
 cudaError_t launch_exp2(int tpi, const Exp2Args& A, cudaStream_t s);
 cudaError_t launch_exp2_filler(int tpi, const Exp2Args& A, size_t ctas, cudaStream_t s);

@@ -131,3 +131,43 @@ def test_noncanonical_scalars():
     gen = gr.fixed_base_exp([1])[0]
     assert gr.ctx.lib.mpvss_batch_exp(gr.ctx.h, ptr(buf(gen)), 32, ptr(big), 1, ptr(out)) == L.OK
     assert bytes(out) == og.element_to_bytes(og.exp(og.generator(), 5))
+
+
+@pytest.mark.parametrize("gname", ["secp256k1", "ristretto255"])
+def test_malformed_box_contents_verify_as_false(gname):
+    """Untrusted box contents that do not decode -- an invalid point, a non-canonical response, a position out
+    of range -- make verify_distribution_shares / verify_share return False like the reference
+    (bytes_to_element -> None, participant.rs:415-420), never raise."""
+    import copy
+    from oracle.groups import GROUPS, SECP_N
+    og = GROUPS[gname]()
+    g = m.Group(gname)
+    n, t = 5, 3
+    sks = synth.private_keys(12, n, gname, og.order())
+    pks = g.fixed_base_exp(sks)
+    d = m.Participant(g)
+    box = d.distribute_secret(SECRET, pks, t, coeffs=synth.coefficients(12, t, og.order()),
+                              witnesses=synth.witnesses(12, n, og.order()))
+    assert d.verify_distribution_shares(box) is True
+    bad_point = (b"\x05" + b"\x11" * 32) if gname == "secp256k1" else b"\xff" * 32
+    for where in ("share", "commitment", "position"):
+        evil = copy.copy(box)
+        if where == "share":
+            evil.shares = dict(box.shares)
+            evil.shares[pks[1]] = bad_point
+        elif where == "commitment":
+            evil.commitments = [box.commitments[0], bad_point] + box.commitments[2:]
+        else:
+            evil.positions = dict(box.positions)
+            evil.positions[pks[2]] = 1 << 40
+        assert d.verify_distribution_shares(evil) is False, where
+    sbs = d.extract_secret_shares(box, sks, synth.witnesses(13, n, og.order()))
+    assert all(d.verify_shares(sbs, box, pks))
+    sbs[1] = m.ShareBox(sbs[1].publickey, bad_point, sbs[1].challenge, sbs[1].response)
+    assert d.verify_shares(sbs, box, pks) == [True, False, True, True, True]
+    if gname == "secp256k1":                      # a response >= n cannot be a k256 Scalar
+        c = g.codec
+        ok = (ctypes.c_int * 1)()
+        st = g.ctx.lib.mpvss_verify_shares(g.ctx.h, 1, ptr(buf(pks[0])), ptr(buf(sbs[0].share)), ptr(buf(box.shares[pks[0]])),
+                                           ptr(buf(c.enc_scalar(sbs[0].challenge))), ptr(buf(SECP_N.to_bytes(32, "big"))), ok)
+        assert st == L.OK and ok[0] == 0
