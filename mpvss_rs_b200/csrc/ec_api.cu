@@ -42,12 +42,6 @@ void fill_modulus(fp256::Modulus& M, const big::Int& m) {
   for (int i = 0; i < 5; ++i) inv *= 2u - m0 * inv;
   M.np = 0u - inv;
 }
-void put_mont(uint32_t* dst, const big::Int& v, const big::Int& m) {
-  big::Int R(9, 0);
-  R[8] = 1;
-  put8(dst, big::mulmod(big::mod(v, m), big::mod(R, m), m));
-}
-
 // Field multiplications / squarings of the point operations as the kernels execute them (secp.cuh /
 // rist.cuh); used only to count the algorithmic work of a Horner launch for the roofline figure.
 struct OpCost {

@@ -95,11 +95,6 @@ uint32_t windows_for(const uint8_t* scalars, size_t stride, size_t n) {
   uint32_t w = (uint32_t)(top * 2);
   return w ? w : 1;
 }
-uint32_t ndigits_for(uint64_t maxpos) {
-  uint32_t d = 1;
-  while (maxpos >> (2 * d)) ++d;
-  return d;
-}
 
 int h2d(mpvss_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   MPVSS_CUDA(ctx, b.ensure(bytes));

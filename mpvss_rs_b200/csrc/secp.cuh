@@ -28,16 +28,18 @@ MP_DEV Fe dbl(const Fe& a, const Modulus&) { return fpsp::add_p<fpsp::SecpP>(a, 
 // Operands by value: a non-inlined callee that reads its operands through references keeps ptxas
 // from pairing mad.lo.cc / madc.hi.cc into IMAD.WIDE (twice the instructions); by value they arrive
 // in registers.
-MP_NOINLINE Fe mul(Fe a, Fe b) {
+MP_DEV Fe mul_inl(const Fe& a, const Fe& b) {
   uint32_t t[16];
   fpsp::mul_wide(t, a, b);
   return fpsp::secp_reduce(t);
 }
-MP_NOINLINE Fe sqr(Fe a) {
+MP_DEV Fe sqr_inl(const Fe& a) {
   uint32_t t[16];
   fpsp::sqr_wide(t, a);
   return fpsp::secp_reduce(t);
 }
+MP_NOINLINE Fe mul(Fe a, Fe b) { return mul_inl(a, b); }
+MP_NOINLINE Fe sqr(Fe a) { return sqr_inl(a); }
 MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus&) { return mul(a, b); }
 MP_DEV Fe sqr(const Fe& a, const Modulus&) { return sqr(a); }
 MP_DEV Fe to_mont(const Fe& a, const Modulus&) { return a; }
@@ -106,6 +108,18 @@ MP_NOINLINE Fe sqrt_candidate(const Fe& a, const Modulus&) {
 }
 }  // namespace F
 
+// Field products inside the point doubling / mixed addition: called (default) or inlined (EC_INLINE_FIELD:
+// no argument moves and CALL/RET, the scheduler sees across products, at 3x the code size).
+namespace FX {
+#ifdef EC_INLINE_FIELD
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus&) { return F::mul_inl(a, b); }
+MP_DEV Fe sqr(const Fe& a, const Modulus&) { return F::sqr_inl(a); }
+#else
+MP_DEV Fe mul(const Fe& a, const Fe& b, const Modulus& P) { return F::mul(a, b, P); }
+MP_DEV Fe sqr(const Fe& a, const Modulus& P) { return F::sqr(a, P); }
+#endif
+}  // namespace FX
+
 // Device-resident constants (built on the host in secp_api.cu).
 struct Consts {
   Modulus P;             // base field  2^256 - 2^32 - 977
@@ -149,16 +163,16 @@ MP_DEV Jac jac_neg(const Jac& p, const Modulus& P) {
 MP_NOINLINE Jac jac_dbl(Jac p, const Modulus& P) {
   using namespace F;
   if (jac_is_inf(p)) return p;
-  Fe A = F::sqr(p.X, P), B = F::sqr(p.Y, P), C = F::sqr(B, P);
+  Fe A = FX::sqr(p.X, P), B = FX::sqr(p.Y, P), C = FX::sqr(B, P);
   Fe t = F::add(p.X, B, P);
-  Fe D = F::dbl(F::sub(F::sub(F::sqr(t, P), A, P), C, P), P);
+  Fe D = F::dbl(F::sub(F::sub(FX::sqr(t, P), A, P), C, P), P);
   Fe E = F::add(F::dbl(A, P), A, P);
-  Fe E2 = F::sqr(E, P);
+  Fe E2 = FX::sqr(E, P);
   Jac r;
   r.X = F::sub(E2, F::dbl(D, P), P);
   Fe C8 = F::dbl(F::dbl(F::dbl(C, P), P), P);
-  r.Y = F::sub(F::mul(E, F::sub(D, r.X, P), P), C8, P);
-  r.Z = F::dbl(F::mul(p.Y, p.Z, P), P);
+  r.Y = F::sub(FX::mul(E, F::sub(D, r.X, P), P), C8, P);
+  r.Z = F::dbl(FX::mul(p.Y, p.Z, P), P);
   return r;
 }
 
@@ -189,18 +203,18 @@ MP_NOINLINE Jac jac_madd(Jac p, Aff q, const Modulus& P) {
   using namespace F;
   if (q.inf) return p;
   if (jac_is_inf(p)) return jac_from_aff(q, P);
-  Fe Z1Z1 = F::sqr(p.Z, P);
-  Fe U2 = F::mul(q.x, Z1Z1, P), S2 = F::mul(F::mul(q.y, p.Z, P), Z1Z1, P);
+  Fe Z1Z1 = FX::sqr(p.Z, P);
+  Fe U2 = FX::mul(q.x, Z1Z1, P), S2 = FX::mul(FX::mul(q.y, p.Z, P), Z1Z1, P);
   Fe H = F::sub(U2, p.X, P), rr = F::sub(S2, p.Y, P);
   if (is_zero(H)) {
     if (is_zero(rr)) return jac_dbl(p, P);
     return jac_infinity(P);
   }
-  Fe HH = F::sqr(H, P), I = F::dbl(F::dbl(HH, P), P), J = F::mul(H, I, P), r2 = F::dbl(rr, P), V = F::mul(p.X, I, P);
+  Fe HH = FX::sqr(H, P), I = F::dbl(F::dbl(HH, P), P), J = FX::mul(H, I, P), r2 = F::dbl(rr, P), V = FX::mul(p.X, I, P);
   Jac r;
-  r.X = F::sub(F::sub(F::sqr(r2, P), J, P), F::dbl(V, P), P);
-  r.Y = F::sub(F::mul(r2, F::sub(V, r.X, P), P), F::dbl(F::mul(p.Y, J, P), P), P);
-  r.Z = F::sub(F::sub(F::sqr(F::add(p.Z, H, P), P), Z1Z1, P), HH, P);
+  r.X = F::sub(F::sub(FX::sqr(r2, P), J, P), F::dbl(V, P), P);
+  r.Y = F::sub(FX::mul(r2, F::sub(V, r.X, P), P), F::dbl(FX::mul(p.Y, J, P), P), P);
+  r.Z = F::sub(F::sub(FX::sqr(F::add(p.Z, H, P), P), Z1Z1, P), HH, P);
   return r;
 }
 
