@@ -71,6 +71,9 @@ struct mpvss_ctx {
   bool modp_tpi_auto = true;  // Horner launches pick 4 lanes per value when a launch has >= 32768 positions
   int v_tpi = 8;              // lanes per value of the staged Horner plan
   int v_wpc = 1;              // warps per CTA of the staged Horner plan
+  std::vector<int64_t> v_plan_pos;  // positions the cached Horner plan (v_ops / v_slot / v_nd) was made for
+  int v_plan_tpi = 0, v_plan_wpc = 0;
+  uint64_t v_plan_sqr = 0, v_plan_mul = 0;
   int modp_wpc = 0;           // "modp_wpc": force warps per CTA of the Horner launch (0 = automatic)
   size_t exp2_filler_ctas = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs
   int modp_overlap = 3;  // a2 = y^r Y^c (independent of X): 0 before the Horner launch on the main stream; 2 regular launch on a
@@ -102,7 +105,8 @@ struct mpvss_ctx {
   std::vector<uint32_t> v_hpos;  // staged positions (elliptic-curve groups: roofline accounting)
   size_t ec_chunks = 1;          // chunks per position of the last elliptic-curve Horner launch
   const uint32_t* v_comb = nullptr;  // fixed-base table of g for a1 = g^r * X^c
-  DevBuf v_slot, v_nd, v_ops, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2, v_st;
+  DevBuf v_slot, v_nd, v_ops, v_comm, v_cm, v_pos, v_pk, v_y, v_r, v_c, v_x, v_a1, v_a2;
+  DevBuf v_st, v_cst;  // elliptic curves: decode status of the DLEQ inputs / of the commitments
   // framed transcript rows (dleq.rs:58-61, 87-99): per participant 4 x (u64 BE length || bytes), written by the
   // device in the rank's local order; v_gather holds the rows of all ranks after the all-gather
   DevBuf v_frames, v_gather;

@@ -537,7 +537,7 @@ struct Ec {
     uint8_t* X = ctx->v_x.as<uint8_t>();
     uint32_t* st = ctx->v_st.as<uint32_t>();
     MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint8_t>(), t, ctx->v_pos.as<uint32_t>(), n, ctx->v_cm, ctx->v_nd,
+    MPVSS_TRY(dev_horner(ctx, ctx->v_comm.as<uint8_t>(), t, ctx->v_pos.as<uint32_t>(), n, ctx->v_cm, ctx->v_cst,
                          ctx->buf(12), X));
     count_horner(ctx, ctx->v_hpos, t);
     // a2 = r*y + c*Y does not depend on X: a small grid (one thread per share) on a side stream, issued
@@ -558,7 +558,7 @@ struct Ec {
     MPVSS_TRY(timing_end(ctx));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[0], ctx->ev0, ctx->ev_mid));
     MPVSS_CUDA(ctx, cudaEventElapsedTime(&ctx->phase_ms[1], ctx->ev_mid, ctx->ev1));
-    int s1 = check_status(ctx, ctx->v_nd, t, "verify_distribution (commitments)");
+    int s1 = check_status(ctx, ctx->v_cst, t, "verify_distribution (commitments)");
     int s2 = s1 == MPVSS_OK ? check_status(ctx, ctx->v_st, 2 * n, "verify_distribution (public keys / shares)") : s1;
     if (s2 == MPVSS_ERR_ENCODING) {
       *decoded = false;

@@ -174,7 +174,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->comb[0], &ctx->comb[1], &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_st})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_st, &ctx->v_cst})
     b->release();
 }
 
@@ -541,24 +541,39 @@ int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commit
   for (size_t i = 0; i < n_total; ++i)   // box content, checked alike by every rank: verifies as false
     if (positions && (positions[i] < 1 || positions[i] > 0x7fffffff))
       return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "verify_distribution: position out of range [1, 2^31)");
+  // The op lists depend on the positions only: a context that verifies boxes over the same positions again
+  // (the usual case: 1..n) keeps the plan and its device copy from the previous call.
   PosPlan plan;
-  if (n) MPVSS_TRY(prep_positions(ctx, pos.data(), n, plan));
-  ctx->v_np = plan.slot.size();
-  ctx->v_nops_max = plan.nops_max;
-  ctx->v_tpi = plan.tpi;
-  ctx->v_wpc = plan.wpc;
-  ctx->horner_sqr = plan.sqr * (t - 1);
-  ctx->horner_mul = plan.mul * (t - 1);
+  const bool replan = n && !(ctx->v_plan_pos == pos && ctx->v_plan_tpi == horner_tpi(ctx, n) &&
+                             ctx->v_plan_wpc == horner_wpc(ctx, n, horner_tpi(ctx, n)));
+  if (replan) {
+    ctx->v_plan_pos.clear();
+    MPVSS_TRY(prep_positions(ctx, pos.data(), n, plan));
+    ctx->v_np = plan.slot.size();
+    ctx->v_nops_max = plan.nops_max;
+    ctx->v_tpi = plan.tpi;
+    ctx->v_wpc = plan.wpc;
+    ctx->v_plan_sqr = plan.sqr;
+    ctx->v_plan_mul = plan.mul;
+  }
+  ctx->horner_sqr = ctx->v_plan_sqr * (t - 1);
+  ctx->horner_mul = ctx->v_plan_mul * (t - 1);
   std::vector<uint8_t> tpk, ty, tr;
   const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
   const uint8_t* y = slice_rows(ctx, shares, n_total, EB, ty);
   const uint8_t* r = slice_rows(ctx, responses, n_total, EB, tr);
   MPVSS_TRY(h2d(ctx, ctx->v_comm, commitments, t * EB));
   MPVSS_TRY(h2d(ctx, ctx->v_c, challenge, EB));
-  if (n) {
+  if (replan) {
     MPVSS_TRY(h2d(ctx, ctx->v_ops, plan.ops.data(), plan.ops.size() * 2));
     MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
     MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nops.data(), plan.nops.size() * 4));
+    MPVSS_TRY(sync(ctx));  // `plan` is about to go out of use; the cache key is set once the copies are queued and done
+    ctx->v_plan_pos = pos;
+    ctx->v_plan_tpi = plan.tpi;
+    ctx->v_plan_wpc = plan.wpc;
+  }
+  if (n) {
     MPVSS_TRY(h2d(ctx, ctx->v_pk, pk, n * EB));
     MPVSS_TRY(h2d(ctx, ctx->v_y, y, n * EB));
     MPVSS_TRY(h2d(ctx, ctx->v_r, r, n * EB));
