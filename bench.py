@@ -379,6 +379,11 @@ class Runner:
                 "e2e_ms": statistics.mean(r[0] for r in e2e) * 1e3, "launches": launches, "sqr": sq, "mul": ml}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch at n = 4096, t = 2731 on one GPU, from the
+# ncu --set full captures summarised under profiles/ (horner_r02_ncu.txt, ec_horner_*_r02_ncu.txt)
+NCU_TRAFFIC = {"modp": 1277952, "secp256k1": 307200 + 780032, "ristretto255": 275456 + 21468160}
+
+
 def modp_roofline(m, n_local, imad_lo, imad_wide, peak_src, traffic=None):
     hm = m["sqr"] * SQR_MACS + m["mul"] * MUL_MACS
     achieved = 2.0 * hm / (m["horner_ms"] * 1e-3) / 1e12        # TIMAD/s, 1 MAC = 2 IMAD issues
@@ -401,14 +406,15 @@ def modp_roofline(m, n_local, imad_lo, imad_wide, peak_src, traffic=None):
                        "what": "all kernels of the step (Horner + both DLEQ launches; g^r from the fixed-base table)"}}
 
 
-def ec_roofline(m, group_name, imad_lo, imad_wide, peak_src):
+def ec_roofline(m, group_name, imad_lo, imad_wide, peak_src, traffic=None):
     macs = m["sqr"] * EC_SQR_MACS[group_name] + m["mul"] * EC_MUL_MACS[group_name]
     achieved = 2.0 * macs / (m["horner_ms"] * 1e-3) / 1e12
     return {"bound": "imad", "kernel": f"ec::horner_kernel<{group_name}> (chunked X_i Horner incl. chunk scaling)",
             "achieved": achieved, "peak": imad_lo, "unit": "TIMAD/s", "frac": achieved / imad_lo if imad_lo else None,
             "peak_source": peak_src, "frac_of_wide_mac_peak": (achieved / 2) / imad_wide if imad_wide else None,
             "algorithmic_macs_per_launch": macs, "field_sqr_per_launch": m["sqr"], "field_mul_per_launch": m["mul"],
-            "kernel_ms": m["horner_ms"], "traffic": None,
+            "kernel_ms": m["horner_ms"], "traffic": traffic,
+            "traffic_note": "dram bytes read+written by the Horner launch, ncu --set full (profiles/)",
             "note": "field products executed by the Horner launches (library counter) x 72 / 44 MACs "
                     "(8x8 limb product or 36 distinct squaring products + 8 for the special-form fold)"}
 
@@ -563,12 +569,15 @@ def main():
         "clocks": clocks,
         "e2e": {"value": n_total / (meas["e2e_ms"] * 1e-3), "unit": "shares/s", "ms_per_step": meas["e2e_ms"],
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "mpvss_verify_distribution (pinned host buffers in, verdict out; collective at N>1)"},
+                "call": "mpvss_verify_distribution (pinned host buffers in, verdict out; collective at N>1); the "
+                        "addition-chain plan of positions 1..n is cached in the context, every box input is copied "
+                        "each step"},
     }
+    traffic = NCU_TRAFFIC[args.group] if (world == 1 and n == 4096 and t == 2731) else None
     if args.group == "modp":
-        line["roofline"] = modp_roofline(meas, n_loc, imad_lo, imad_wide, peak_src)
+        line["roofline"] = modp_roofline(meas, n_loc, imad_lo, imad_wide, peak_src, traffic)
     else:
-        line["roofline"] = ec_roofline(meas, args.group, imad_lo, imad_wide, peak_src)
+        line["roofline"] = ec_roofline(meas, args.group, imad_lo, imad_wide, peak_src, traffic)
         line["phase_ms"] = {"x_horner": meas["horner_ms"], "dleq": meas["kernel_ms"] - meas["horner_ms"]}
     if not args.no_cpu_baseline and world == 1 and args.group in CPU_PROXY:
         sample = spread_sample(n_total, min(cores, n_total))
