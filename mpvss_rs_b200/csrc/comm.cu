@@ -68,6 +68,27 @@ int comm_allgather(mpvss_ctx* ctx, const void* src, void* dst, size_t bytes) {
   return MPVSS_OK;
 }
 
+namespace {
+// one warp per row; rows are multiples of 4 bytes (1056 / 164 / 160)
+__global__ void reorder_rows_kernel(const uint32_t* in, uint32_t* out, uint32_t n_total, uint32_t nranks, uint32_t rpr,
+                                    uint32_t row_words) {
+  const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_total) return;
+  const uint32_t* src = in + ((size_t)(i % nranks) * rpr + i / nranks) * row_words;
+  uint32_t* dst = out + (size_t)i * row_words;
+  for (uint32_t k = threadIdx.x & 31u; k < row_words; k += 32) dst[k] = src[k];
+}
+}  // namespace
+
+int comm_reorder_rows(mpvss_ctx* ctx, const void* gathered, void* ordered, size_t n_total, size_t row_bytes) {
+  const uint32_t rpr = (uint32_t)transcript::rows_per_rank(n_total, ctx->nranks);
+  reorder_rows_kernel<<<(unsigned)((n_total + 7) / 8), 256, 0, ctx->stream>>>(
+      static_cast<const uint32_t*>(gathered), static_cast<uint32_t*>(ordered), (uint32_t)n_total, (uint32_t)ctx->nranks, rpr,
+      (uint32_t)(row_bytes / 4));
+  MPVSS_CUDA(ctx, cudaGetLastError());
+  return MPVSS_OK;
+}
+
 void comm_release(mpvss_ctx* ctx) {
   if (ctx->comm) {
     nccl()->CommDestroy(static_cast<ncclComm_t>(ctx->comm));

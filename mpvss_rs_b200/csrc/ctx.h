@@ -109,7 +109,7 @@ struct mpvss_ctx {
   DevBuf v_st, v_cst;  // elliptic curves: decode status of the DLEQ inputs / of the commitments
   // framed transcript rows (dleq.rs:58-61, 87-99): per participant 4 x (u64 BE length || bytes), written by the
   // device in the rank's local order; v_gather holds the rows of all ranks after the all-gather
-  DevBuf v_frames, v_gather;
+  DevBuf v_frames, v_gather, v_ordered;  // local rows, all ranks' rows as gathered, the same in participant order
   PinBuf h_frames;
   size_t v_n_total = 0;          // participants of the whole box (== v_n without a communicator)
   uint64_t horner_sqr = 0, horner_mul = 0;  // modular squarings / multiplications of the last X_i launch

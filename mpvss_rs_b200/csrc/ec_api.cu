@@ -593,14 +593,16 @@ struct Ec {
     const uint8_t* rows = ctx->v_frames.as<uint8_t>();
     if (ctx->nranks > 1) {
       MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * g.row()));
-      rows = ctx->v_gather.as<uint8_t>();
+      MPVSS_CUDA(ctx, ctx->v_ordered.ensure(n_total * g.row()));
+      MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, g.row()));
+      rows = ctx->v_ordered.as<uint8_t>();
     }
     sha2::Sha256 h;
-    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h));
+    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h, true));
     big::Int c = challenge_of(ctx, h, digest_out);
     *ok = big::cmp(c, scalar_big(ctx->v_challenge.data())) == 0;
-    for (int r = 0; r < ctx->nranks; ++r)  // a rank whose slice did not decode marked its first row
-      if (ctx->h_frames.as<uint8_t>()[(size_t)r * rpr * g.row()] == 0xff) *ok = 0;
+    for (size_t r = 0; r < std::min<size_t>((size_t)ctx->nranks, n_total); ++r)  // a rank whose slice did not decode
+      if (ctx->h_frames.as<uint8_t>()[r * g.row()] == 0xff) *ok = 0;      // marked its first row = participant r
     if (!decoded) *ok = 0;
     if (x_out) MPVSS_TRY(d2h(ctx, x_out, ctx->v_x, n * EB));
     if (a1_out) MPVSS_TRY(d2h(ctx, a1_out, ctx->v_a1, n * EB));
@@ -706,12 +708,14 @@ struct Ec {
     const uint8_t* rows = ctx->v_frames.as<uint8_t>();
     if (ctx->nranks > 1) {
       MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * g.row()));
-      rows = ctx->v_gather.as<uint8_t>();
+      MPVSS_CUDA(ctx, ctx->v_ordered.ensure(n_total * g.row()));
+      MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, g.row()));
+      rows = ctx->v_ordered.as<uint8_t>();
     }
     sha2::Sha256 h;  // participant.rs:1205-1212: (X, Y, a1, a2) in publickeys order
-    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h));
-    for (int r = 0; r < ctx->nranks; ++r)
-      if (ctx->h_frames.as<uint8_t>()[(size_t)r * rpr * g.row()] == 0xff)
+    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h, true));
+    for (size_t r = 0; r < std::min<size_t>((size_t)ctx->nranks, n_total); ++r)
+      if (ctx->h_frames.as<uint8_t>()[r * g.row()] == 0xff)
         return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "distribute: invalid public key encoding");
     big::Int c = challenge_of(ctx, h, nullptr);
     scalar_out(c, challenge_out);

@@ -174,7 +174,7 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->comb[0], &ctx->comb[1], &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_st, &ctx->v_cst})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_ordered, &ctx->v_st, &ctx->v_cst})
     b->release();
 }
 
@@ -691,16 +691,18 @@ int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t
   if (ctx->nranks > 1) {
     MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p,
                              transcript::rows_per_rank(n_total, ctx->nranks) * GEOM.row()));
-    rows = ctx->v_gather.as<uint8_t>();
+    MPVSS_CUDA(ctx, ctx->v_ordered.ensure(n_total * GEOM.row()));
+    MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, GEOM.row()));
+    rows = ctx->v_ordered.as<uint8_t>();
   }
   sha2::Sha256 h;
-  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h));
+  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h, true));
   uint8_t digest[32], c[EB];
   h.finalize(digest);
   challenge_from_digest(ctx, digest, c);
   *ok = memcmp(c, ctx->v_challenge.data(), EB) == 0;  // participant.rs:451-454
-  for (int r = 0; r < ctx->nranks; ++r)  // a rank whose slice failed validation marked its first row
-    if (ctx->h_frames.as<uint8_t>()[(size_t)r * transcript::rows_per_rank(n_total, ctx->nranks) * GEOM.row()] == 0xff) *ok = 0;
+  for (size_t r = 0; r < std::min<size_t>((size_t)ctx->nranks, n_total); ++r)  // a rank whose slice failed validation
+    if (ctx->h_frames.as<uint8_t>()[r * GEOM.row()] == 0xff) *ok = 0;               // marked its first row = participant r
   if (digest_out) memcpy(digest_out, digest, 32);
   if (x_out) MPVSS_TRY(d2h(ctx, x_out, ctx->v_x, n * EB));
   if (a1_out) MPVSS_TRY(d2h(ctx, a1_out, ctx->v_a1, n * EB));
@@ -793,10 +795,12 @@ int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, 
   const uint8_t* rows = ctx->v_frames.as<uint8_t>();
   if (ctx->nranks > 1) {
     MPVSS_TRY(comm_allgather(ctx, ctx->v_frames.p, ctx->v_gather.p, rpr * GEOM.row()));
-    rows = ctx->v_gather.as<uint8_t>();
+    MPVSS_CUDA(ctx, ctx->v_ordered.ensure(n_total * GEOM.row()));
+    MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, GEOM.row()));
+    rows = ctx->v_ordered.as<uint8_t>();
   }
   sha2::Sha256 h;
-  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h));
+  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h, true));
   uint8_t digest[32];
   h.finalize(digest);
   challenge_from_digest(ctx, digest, challenge_out);

@@ -223,6 +223,7 @@ MP_NOINLINE bool decode(Aff& a, const uint8_t* in, const Consts& C) {
   t.v[0] = simt::sub_cc(s.v[0], P.m[0]);
 #pragma unroll
   for (int i = 1; i < 8; ++i) t.v[i] = simt::subc_cc(s.v[i], P.m[i]);
+  (void)t;  // only the borrow matters
   if (simt::subc(0, 0) == 0) return false;
   if (s.v[0] & 1u) return false;
   Fe sm = F::to_mont(s, P), one = F::mont_one(P);

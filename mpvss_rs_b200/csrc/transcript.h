@@ -58,14 +58,57 @@ inline void hash_range(sha2::Sha256& h, const uint8_t* gathered, size_t i0, size
   for (size_t i = i0; i < i1; ++i) hash_row(h, gathered + ((i % (size_t)nranks) * rpr + i / (size_t)nranks) * row, g);
 }
 
-// Copy the gathered rows from the device (ctx->stream, after everything queued there) in chunks of local
-// rows and hash them in participant order while later chunks are still copying.
+// hash participants [i0, i1) of a buffer that is already in participant order: contiguous runs of rows whose
+// frames are all full-length go to SHA-256 in one call (a 1056-byte update per row costs 20 % in partial-block
+// handling), a row with a short frame is hashed frame by frame
+inline void hash_ordered(sha2::Sha256& h, const uint8_t* rows, size_t i0, size_t i1, const Geom& g) {
+  const size_t row = g.row(), f = g.frame();
+  if (!g.minimal) {
+    h.update(rows + i0 * row, (i1 - i0) * row);
+    return;
+  }
+  size_t run = i0;
+  for (size_t i = i0; i < i1; ++i) {
+    const uint8_t* r = rows + i * row;
+    bool full = true;
+    for (int k = 0; k < 4; ++k) full = full && ((((size_t)r[k * f + 6] << 8) | r[k * f + 7]) == g.eb);
+    if (!full) {
+      if (i > run) h.update(rows + run * row, (i - run) * row);
+      hash_row(h, r, g);
+      run = i + 1;
+    }
+  }
+  if (i1 > run) h.update(rows + run * row, (i1 - run) * row);
+}
+
+// Copy the transcript rows from the device (ctx->stream, after everything queued there) in chunks and hash them
+// in participant order while later chunks are still copying.  `dev_rows` is in participant order
+// (ordered = true: a single rank, or after reorder_rows) or in the all-gather layout [rank][local row].
 inline int fetch_and_hash(mpvss_ctx* ctx, const uint8_t* dev_rows, size_t n_total, int nranks, const Geom& g,
-                          sha2::Sha256& h) {
+                          sha2::Sha256& h, bool ordered = false) {
   const size_t rpr = rows_per_rank(n_total, nranks), row = g.row();
-  MPVSS_CUDA(ctx, ctx->h_frames.ensure((size_t)nranks * rpr * row));
+  if (nranks == 1) ordered = true;
+  const size_t total_rows = ordered ? n_total : (size_t)nranks * rpr;
+  MPVSS_CUDA(ctx, ctx->h_frames.ensure(total_rows * row));
   uint8_t* host = ctx->h_frames.as<uint8_t>();
   constexpr size_t NCH = sizeof(ctx->ev_chunk) / sizeof(ctx->ev_chunk[0]);
+  if (ordered) {
+    // about 2 MiB per chunk, at most NCH chunks
+    const size_t rows_per_chunk = std::max<size_t>((2u << 20) / row, (n_total + NCH - 1) / NCH);
+    const size_t nchunks = (n_total + rows_per_chunk - 1) / rows_per_chunk;
+    for (size_t c = 0; c < nchunks; ++c) {
+      const size_t i0 = c * rows_per_chunk, i1 = std::min(n_total, i0 + rows_per_chunk);
+      MPVSS_CUDA(ctx, cudaMemcpyAsync(host + i0 * row, dev_rows + i0 * row, (i1 - i0) * row, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+      MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+      const size_t i0 = c * rows_per_chunk, i1 = std::min(n_total, i0 + rows_per_chunk);
+      MPVSS_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[c]));
+      hash_ordered(h, host, i0, i1, g);
+    }
+    return MPVSS_OK;
+  }
   // about 1 MiB per chunk and rank, at most NCH chunks
   size_t rows_per_chunk = std::max<size_t>((1u << 20) / row, (rpr + NCH - 1) / NCH);
   size_t nchunks = (rpr + rows_per_chunk - 1) / rows_per_chunk;
@@ -92,6 +135,9 @@ inline int fetch_and_hash(mpvss_ctx* ctx, const uint8_t* dev_rows, size_t n_tota
 // without a communicator
 int comm_allgather(mpvss_ctx* ctx, const void* src, void* dst, size_t bytes);
 void comm_release(mpvss_ctx* ctx);
+// gathered rows [rank][rows_per_rank][row_bytes] -> participant order (row i = rank i % N, local row i / N), on the
+// device at HBM speed, so that the host receives and hashes one contiguous transcript
+int comm_reorder_rows(mpvss_ctx* ctx, const void* gathered, void* ordered, size_t n_total, size_t row_bytes);
 
 namespace transcript {
 // Bring this rank's n local rows of `kinds` row sets (device, widths[k] bytes per row) to the host in
