@@ -73,7 +73,10 @@ const char* mpvss_last_error(const mpvss_ctx* ctx);
  * the two generators); "modp_overlap" (where the X-independent a2 = y^r Y^c runs during
  * verify_distribution: 0 before the X_i launch, 2 beside it on a side stream, 3 (default) beside it as
  * one persistent one-warp CTA per SM, which takes the warp slot the X_i launch leaves idle);
- * "ec_threads" (thread target of the chunked elliptic-curve Horner launch); "validate" (0/1, default 0:
+ * "modp_chunks" (contiguous chunks per position of the X_i launch, 0 = automatic: more than one only when the
+ * launch would leave most of the chip idle); "modp_wpc" (warps per CTA of that launch); "modp_msm" /
+ * "msm_threshold" (bucket method for multi_exp / reconstruct); "ec_threads" (thread target of the chunked
+ * elliptic-curve Horner launch); "validate" (0/1, default 0:
  * ModpGroup elements entering verify_distribution / verify_shares are checked for range 0 < x < q and
  * subgroup membership x^g = 1 -- the reference's bytes_to_element accepts anything, modp.rs:154-156;
  * a box that fails verifies as false) */

@@ -146,6 +146,11 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->modp_overlap = value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "modp_chunks") {
+    if (value < 0 || value > 64) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_chunks must be 0 (automatic) .. 64");
+    ctx->modp_chunks = value;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "modp_wpc") {
     if (value < 0 || value > 4) return mpvss_fail(ctx, MPVSS_ERR_ARG, "modp_wpc must be 0 (automatic) .. 4");
     ctx->modp_wpc = value;

@@ -73,6 +73,10 @@ struct mpvss_ctx {
   int v_wpc = 1;              // warps per CTA of the staged Horner plan
   std::vector<int64_t> v_plan_pos;  // positions the cached Horner plan (v_ops / v_slot / v_nd) was made for
   int v_plan_tpi = 0, v_plan_wpc = 0;
+  size_t v_plan_t = 0;
+  uint32_t v_plan_kreq = 0, v_k = 1;  // requested / actual chunks per position of the staged plan
+  DevBuf v_first, v_steps, v_e, v_h, v_t2;  // per-CTA chunk bounds, chunk exponents, chunk results, their powers
+  int modp_chunks = 0;                // "modp_chunks": chunks per position of the MODP Horner launch (0 = automatic)
   uint64_t v_plan_sqr = 0, v_plan_mul = 0;
   int modp_wpc = 0;           // "modp_wpc": force warps per CTA of the Horner launch (0 = automatic)
   size_t exp2_filler_ctas = 0;  // non-zero: the next dev_exp2 uses the persistent one-warp 'filler' launch with this many CTAs

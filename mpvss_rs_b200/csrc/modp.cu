@@ -11,7 +11,8 @@ __global__ void __launch_bounds__(HORNER_MAX_WARPS_PER_CTA * 32) horner_kernel(H
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
   horner_body<TPI, NP1>(A, blockIdx.x * (blockDim.x >> 5) + w, smem + w * horner_smem_words<TPI>,
-                        A.nops ? A.nops[blockIdx.x] : A.nops_all);
+                        A.nops ? A.nops[blockIdx.x] : A.nops_all, A.cfirst ? A.cfirst[blockIdx.x] : A.t - 1,
+                        A.csteps ? A.csteps[blockIdx.x] : A.t - 1);
 }
 
 template <int TPI>

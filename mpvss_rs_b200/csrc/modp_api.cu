@@ -174,7 +174,8 @@ int init(mpvss_ctx* ctx) {
 
 void destroy(mpvss_ctx* ctx) {
   for (DevBuf* b : {&ctx->consts_q, &ctx->consts_g, &ctx->gens, &ctx->comb[0], &ctx->comb[1], &ctx->v_comm, &ctx->v_cm, &ctx->v_pos, &ctx->v_pk,
-                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_ordered, &ctx->v_st, &ctx->v_cst})
+                    &ctx->v_y, &ctx->v_r, &ctx->v_c, &ctx->v_x, &ctx->v_a1, &ctx->v_a2, &ctx->v_slot, &ctx->v_nd, &ctx->v_ops, &ctx->v_frames, &ctx->v_gather, &ctx->v_ordered, &ctx->v_st, &ctx->v_cst, &ctx->v_first, &ctx->v_steps,
+                    &ctx->v_e, &ctx->v_h, &ctx->v_t2})
     b->release();
 }
 
@@ -249,9 +250,28 @@ static int horner_wpc(const mpvss_ctx* ctx, size_t n, int tpi) {
   return 1;  // measured: 4 warps per CTA change nothing at 8 .. 16 warps per SM (tools/wpc_sweep.sh)
 }
 
+// Chunks per position.  With few positions the launch is a handful of warps per SM and every chain is
+// latency-bound; cutting the polynomial into K contiguous chunks gives K times the lane groups with chains
+// 1/K as long, at the price of one 2048-bit exponentiation per extra chunk for the combination
+// X = prod_k H_k^(pos^(k B)) (6.5 % of a chain at t = 2731) -- free while the chip is mostly idle
+// (one box split over many GPUs, small boxes).  "modp_chunks": 0 = automatic.
+static uint32_t horner_chunks(const mpvss_ctx* ctx, size_t n, size_t t) {
+  uint32_t K = 1;
+  if (ctx->modp_chunks > 0) {
+    K = (uint32_t)ctx->modp_chunks;
+  } else {
+    const size_t warps = (n + 3) / 4, full = (size_t)8 * (size_t)ctx->sm_count;  // two warps per scheduler
+    while (K < 8 && warps * (K * 2) <= full) K *= 2;
+  }
+  while (K > 1 && t / K < 32) K /= 2;  // at least 32 coefficients per chunk
+  return K;
+}
+
 struct PosPlan {
   int tpi = 8;
   int wpc = 1;                  // warps per CTA of the Horner launch
+  uint32_t K = 1, B = 0;        // chunks per position, coefficients per chunk
+  std::vector<uint32_t> first, steps;  // per CTA: top coefficient of its chunk, Horner steps
   std::vector<uint32_t> slot;   // padded instance array: output row of the instance, 0xffffffff = padding
   std::vector<uint16_t> ops;    // HC_OPS ops per instance: one Horner step (modp_chain.h)
   std::vector<uint32_t> nops;   // ops per step, per CTA
@@ -265,7 +285,7 @@ static std::mutex g_tree_mu;
 // a whole number of CTAs, so all lane groups of a CTA run the same number of products per step while
 // one launch covers every class; shorter lists inside a class do not occur, padding instances repeat
 // the last live one.
-static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, PosPlan& plan) {
+static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, size_t t, PosPlan& plan) {
   static_assert(modp_chain::SLOTS == modp::HC_SLOTS && modp_chain::OPS_MAX == modp::HC_OPS, "kernel / host op format");
   uint32_t maxp = 1;
   for (size_t i = 0; i < n; ++i) {
@@ -277,47 +297,115 @@ static int prep_positions(mpvss_ctx* ctx, const int64_t* positions, size_t n, Po
   g_tree.build(std::min<uint32_t>(maxp, modp_chain::TREE_LIMIT));
   std::vector<std::vector<uint16_t>> ops(n);
   std::vector<std::vector<uint32_t>> by(modp_chain::OPS_MAX + 1);
-  plan.sqr = plan.mul = 0;
+  std::vector<uint32_t> sq(n), ml(n);
   for (size_t i = 0; i < n; ++i) {
-    uint32_t sq, ml;
-    if (!modp_chain::step_ops((uint32_t)(positions ? positions[i] : (int64_t)i + 1), g_tree, ops[i], &sq, &ml))
+    if (!modp_chain::step_ops((uint32_t)(positions ? positions[i] : (int64_t)i + 1), g_tree, ops[i], &sq[i], &ml[i]))
       return mpvss_fail(ctx, MPVSS_ERR_UNSUPPORTED, "no addition chain within the kernel's slot budget");
-    plan.sqr += sq;
-    plan.mul += ml;
     by[ops[i].size()].push_back((uint32_t)i);
   }
-  plan.tpi = horner_tpi(ctx, n);
+  plan.K = horner_chunks(ctx, n, t);
+  plan.B = (uint32_t)((t + plan.K - 1) / plan.K);
+  plan.K = (uint32_t)((t + plan.B - 1) / plan.B);
+  plan.tpi = plan.K > 1 ? ctx->modp_tpi : horner_tpi(ctx, n);
   plan.wpc = horner_wpc(ctx, n, plan.tpi);
   const size_t per_cta = (size_t)plan.wpc * (32 / plan.tpi);
-  plan.slot.clear(); plan.ops.clear(); plan.nops.clear();
+  plan.slot.clear(); plan.ops.clear(); plan.nops.clear(); plan.first.clear(); plan.steps.clear();
   plan.nops_max = 1;
-  for (uint32_t len = modp_chain::OPS_MAX; len >= 1; --len) {
-    if (by[len].empty()) continue;
-    plan.nops_max = std::max(plan.nops_max, len);
-    auto emit = [&](uint32_t i, uint32_t slot) {
-      plan.slot.push_back(slot);
-      size_t base = plan.ops.size();
-      plan.ops.resize(base + modp_chain::OPS_MAX, (uint16_t)modp_chain::B_ONE);
-      std::copy(ops[i].begin(), ops[i].end(), plan.ops.begin() + base);
-    };
-    for (uint32_t i : by[len]) emit(i, i);
-    while (plan.slot.size() % per_cta) emit(by[len].back(), 0xffffffffu);
-    plan.nops.resize(plan.slot.size() / per_cta, len);
+  plan.sqr = plan.mul = 0;
+  for (uint32_t k = 0; k < plan.K; ++k) {  // chunk k: coefficients [k B, min((k+1) B, t)), results in rows k n + i
+    const uint32_t lo = k * plan.B, hi = (uint32_t)std::min<size_t>(t, (size_t)lo + plan.B);
+    for (uint32_t len = modp_chain::OPS_MAX; len >= 1; --len) {
+      if (by[len].empty()) continue;
+      plan.nops_max = std::max(plan.nops_max, len);
+      auto emit = [&](uint32_t i, uint32_t slot) {
+        plan.slot.push_back(slot);
+        size_t base = plan.ops.size();
+        plan.ops.resize(base + modp_chain::OPS_MAX, (uint16_t)modp_chain::B_ONE);
+        std::copy(ops[i].begin(), ops[i].end(), plan.ops.begin() + base);
+      };
+      for (uint32_t i : by[len]) {
+        emit(i, k * (uint32_t)n + i);
+        plan.sqr += (uint64_t)sq[i] * (hi - lo - 1);
+        plan.mul += (uint64_t)ml[i] * (hi - lo - 1);
+      }
+      while (plan.slot.size() % per_cta) emit(by[len].back(), 0xffffffffu);
+      const size_t ctas = plan.slot.size() / per_cta;
+      plan.nops.resize(ctas, len);
+      plan.first.resize(ctas, hi - 1);
+      plan.steps.resize(ctas, hi - lo - 1);
+    }
   }
   return MPVSS_OK;
 }
 
-// commitments (device, normal form) -> X (device), via Montgomery conversion + Horner
-static int dev_horner(mpvss_ctx* ctx, int tpi, int wpc, const uint32_t* comm, DevBuf& cm, size_t t, const uint16_t* ops,
-                      const uint32_t* slot, const uint32_t* nops, size_t n_padded, uint32_t* x) {
+// e_i = pos_i^E mod (q-1) for the chunk combination: q-1 = 2g, so by CRT e_i is the representative of
+// pos_i^E mod g (device modexp with the constants of modulus g) that has the parity of pos_i (E >= 1).
+static int dev_chunk_exponents(mpvss_ctx* ctx, const int64_t* positions, size_t n, uint32_t E, uint32_t* e_out_dev) {
+  std::vector<uint8_t> base(n * EB, 0), bexp(EB, 0), e(n * EB);
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t p = (uint32_t)(positions ? positions[i] : (int64_t)i + 1);
+    memcpy(base.data() + i * EB, &p, 4);
+  }
+  memcpy(bexp.data(), &E, 4);
+  DevBuf &db = ctx->buf(20), &dx = ctx->buf(21);
+  MPVSS_TRY(h2d(ctx, db, base.data(), n * EB));
+  MPVSS_TRY(h2d(ctx, dx, bexp.data(), EB));
+  MPVSS_TRY(dev_exp2(ctx, ctx->consts_g.as<uint32_t>(), db.as<uint32_t>(), EW, dx.as<uint32_t>(), 0,
+                     windows_for(bexp.data(), EB, 1), nullptr, 0, nullptr, 0, 0, n, e_out_dev));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(e.data(), e_out_dev, n * EB, cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_TRY(sync(ctx));
+  for (size_t i = 0; i < n; ++i) {
+    if ((e[i * EB] & 1u) != (base[i * EB] & 1u)) {
+      big::Int v = big::add(big::from_le(e.data() + i * EB, EB), ctx->g);
+      big::to_le(v, e.data() + i * EB, EB);
+    }
+  }
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(e_out_dev, e.data(), n * EB, cudaMemcpyHostToDevice, ctx->stream));
+  return sync(ctx);
+}
+// all chunk exponents of a plan: rows (k-1) n + i = pos_i^(k B) mod (q-1), k = 1 .. K-1
+static int plan_chunk_exponents(mpvss_ctx* ctx, const int64_t* positions, size_t n, const PosPlan& plan, DevBuf& e) {
+  if (plan.K <= 1) return MPVSS_OK;
+  MPVSS_CUDA(ctx, e.ensure((size_t)(plan.K - 1) * n * EB));
+  for (uint32_t k = 1; k < plan.K; ++k)
+    MPVSS_TRY(dev_chunk_exponents(ctx, positions, n, k * plan.B, e.as<uint32_t>() + (size_t)(k - 1) * n * EW));
+  return MPVSS_OK;
+}
+
+// Device side of a plan: everything the Horner launch and the chunk combination read.
+struct PlanDev {
+  const uint16_t* ops;
+  const uint32_t *slot, *nops, *first, *steps;
+  const uint32_t* e;  // chunk exponents (K > 1)
+  size_t n_padded;
+  uint32_t K;
+  int tpi, wpc;
+};
+// commitments (device, normal form) -> X (device): Montgomery conversion, Horner over every chunk, and for
+// K > 1 the combination X = H_0 * prod_{k >= 1} H_k^(pos^(k B)) (one exponentiation launch + K-1 products)
+static int dev_horner(mpvss_ctx* ctx, const PlanDev& P, const uint32_t* comm, DevBuf& cm, size_t t, size_t n, DevBuf& hbuf,
+                      DevBuf& tbuf, uint32_t* x) {
+  const uint32_t* Kq = ctx->consts_q.as<uint32_t>();
   MPVSS_CUDA(ctx, cm.ensure(t * EB));
-  MPVSS_TRY(dev_mul(ctx, ctx->consts_q.as<uint32_t>(), comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
-  modp::HornerArgs A{ctx->consts_q.as<uint32_t>(), cm.as<uint32_t>(), ops, slot, nops, x, (uint32_t)t,
-                     (uint32_t)n_padded, 0, (uint32_t)wpc};
+  MPVSS_TRY(dev_mul(ctx, Kq, comm, EW, nullptr, 0, 1, t, cm.as<uint32_t>()));
+  uint32_t* h = x;
+  if (P.K > 1) {
+    MPVSS_CUDA(ctx, hbuf.ensure((size_t)P.K * n * EB));
+    MPVSS_CUDA(ctx, tbuf.ensure((size_t)(P.K - 1) * n * EB));
+    h = hbuf.as<uint32_t>();
+  }
+  modp::HornerArgs A{Kq, cm.as<uint32_t>(), P.ops, P.slot, P.nops, h, (uint32_t)t, (uint32_t)P.n_padded, 0,
+                     (uint32_t)P.wpc, P.first, P.steps};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
-  MPVSS_CUDA(ctx, modp::launch_horner(tpi, A, ctx->modp_np1, ctx->stream));
+  MPVSS_CUDA(ctx, modp::launch_horner(P.tpi, A, ctx->modp_np1, ctx->stream));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));
   timing_launch(ctx);
+  if (P.K > 1) {
+    uint32_t* T = tbuf.as<uint32_t>();
+    MPVSS_TRY(dev_exp2(ctx, Kq, h + n * EW, EW, P.e, EW, 512, nullptr, 0, nullptr, 0, 0, (size_t)(P.K - 1) * n, T));
+    MPVSS_TRY(dev_mul(ctx, Kq, h, EW, T, EW, 0, n, x));
+    for (uint32_t k = 2; k < P.K; ++k) MPVSS_TRY(dev_mul(ctx, Kq, x, EW, T + (size_t)(k - 1) * n * EW, EW, 0, n, x));
+  }
   return MPVSS_OK;
 }
 
@@ -325,21 +413,25 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
                   uint8_t* out) {
   MPVSS_TRY(check_args(ctx, commitments && out && n > 0 && t > 0, "poly_eval_exp: bad arguments"));
   PosPlan plan;
-  MPVSS_TRY(prep_positions(ctx, positions, n, plan));
+  MPVSS_TRY(prep_positions(ctx, positions, n, t, plan));
   DevBuf &dc = ctx->buf(0), &dops = ctx->buf(1), &dout = ctx->buf(2), &dcm = ctx->buf(3), &dsl = ctx->buf(4),
-         &dno = ctx->buf(5);
+         &dno = ctx->buf(5), &dfi = ctx->buf(6), &dstp = ctx->buf(7), &de = ctx->buf(8);
   const size_t np = plan.slot.size();
   MPVSS_TRY(h2d(ctx, dc, commitments, t * EB));
   MPVSS_TRY(h2d(ctx, dops, plan.ops.data(), plan.ops.size() * 2));
   MPVSS_TRY(h2d(ctx, dsl, plan.slot.data(), np * 4));
   MPVSS_TRY(h2d(ctx, dno, plan.nops.data(), plan.nops.size() * 4));
+  MPVSS_TRY(h2d(ctx, dfi, plan.first.data(), plan.first.size() * 4));
+  MPVSS_TRY(h2d(ctx, dstp, plan.steps.data(), plan.steps.size() * 4));
   MPVSS_CUDA(ctx, dout.ensure(n * EB));
+  MPVSS_TRY(plan_chunk_exponents(ctx, positions, n, plan, de));
+  PlanDev P{dops.as<uint16_t>(), dsl.as<uint32_t>(), dno.as<uint32_t>(), dfi.as<uint32_t>(), dstp.as<uint32_t>(),
+            de.as<uint32_t>(), np, plan.K, plan.tpi, plan.wpc};
   timing_begin(ctx);
-  MPVSS_TRY(dev_horner(ctx, plan.tpi, plan.wpc, dc.as<uint32_t>(), dcm, t, dops.as<uint16_t>(), dsl.as<uint32_t>(),
-                       dno.as<uint32_t>(), np, dout.as<uint32_t>()));
+  MPVSS_TRY(dev_horner(ctx, P, dc.as<uint32_t>(), dcm, t, n, ctx->buf(9), ctx->buf(10), dout.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
-  ctx->horner_sqr = plan.sqr * (t - 1);
-  ctx->horner_mul = plan.mul * (t - 1);
+  ctx->horner_sqr = plan.sqr;
+  ctx->horner_mul = plan.mul;
   MPVSS_TRY(d2h(ctx, out, dout, n * EB));
   return sync(ctx);
 }
@@ -541,23 +633,26 @@ int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commit
   for (size_t i = 0; i < n_total; ++i)   // box content, checked alike by every rank: verifies as false
     if (positions && (positions[i] < 1 || positions[i] > 0x7fffffff))
       return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "verify_distribution: position out of range [1, 2^31)");
-  // The op lists depend on the positions only: a context that verifies boxes over the same positions again
-  // (the usual case: 1..n) keeps the plan and its device copy from the previous call.
+  // The plan depends on the positions and t only: a context that verifies boxes of the same shape again (the
+  // usual case: positions 1..n) keeps the plan and its device copy from the previous call.
   PosPlan plan;
-  const bool replan = n && !(ctx->v_plan_pos == pos && ctx->v_plan_tpi == horner_tpi(ctx, n) &&
-                             ctx->v_plan_wpc == horner_wpc(ctx, n, horner_tpi(ctx, n)));
+  const uint32_t want_k = n ? horner_chunks(ctx, n, t) : 1;
+  const bool replan = n && !(ctx->v_plan_pos == pos && ctx->v_plan_t == t && ctx->v_plan_kreq == want_k &&
+                             ctx->v_plan_tpi == (want_k > 1 ? ctx->modp_tpi : horner_tpi(ctx, n)) &&
+                             ctx->v_plan_wpc == horner_wpc(ctx, n, ctx->v_plan_tpi));
   if (replan) {
     ctx->v_plan_pos.clear();
-    MPVSS_TRY(prep_positions(ctx, pos.data(), n, plan));
+    MPVSS_TRY(prep_positions(ctx, pos.data(), n, t, plan));
     ctx->v_np = plan.slot.size();
     ctx->v_nops_max = plan.nops_max;
     ctx->v_tpi = plan.tpi;
     ctx->v_wpc = plan.wpc;
+    ctx->v_k = plan.K;
     ctx->v_plan_sqr = plan.sqr;
     ctx->v_plan_mul = plan.mul;
   }
-  ctx->horner_sqr = ctx->v_plan_sqr * (t - 1);
-  ctx->horner_mul = ctx->v_plan_mul * (t - 1);
+  ctx->horner_sqr = ctx->v_plan_sqr;
+  ctx->horner_mul = ctx->v_plan_mul;
   std::vector<uint8_t> tpk, ty, tr;
   const uint8_t* pk = slice_rows(ctx, publickeys, n_total, EB, tpk);
   const uint8_t* y = slice_rows(ctx, shares, n_total, EB, ty);
@@ -568,8 +663,13 @@ int verify_stage(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* commit
     MPVSS_TRY(h2d(ctx, ctx->v_ops, plan.ops.data(), plan.ops.size() * 2));
     MPVSS_TRY(h2d(ctx, ctx->v_slot, plan.slot.data(), ctx->v_np * 4));
     MPVSS_TRY(h2d(ctx, ctx->v_nd, plan.nops.data(), plan.nops.size() * 4));
-    MPVSS_TRY(sync(ctx));  // `plan` is about to go out of use; the cache key is set once the copies are queued and done
+    MPVSS_TRY(h2d(ctx, ctx->v_first, plan.first.data(), plan.first.size() * 4));
+    MPVSS_TRY(h2d(ctx, ctx->v_steps, plan.steps.data(), plan.steps.size() * 4));
+    MPVSS_TRY(plan_chunk_exponents(ctx, pos.data(), n, plan, ctx->v_e));
+    MPVSS_TRY(sync(ctx));  // the cache key is set once the copies are done
     ctx->v_plan_pos = pos;
+    ctx->v_plan_t = t;
+    ctx->v_plan_kreq = want_k;
     ctx->v_plan_tpi = plan.tpi;
     ctx->v_plan_wpc = plan.wpc;
   }
@@ -629,7 +729,7 @@ static int verify_kernels(mpvss_ctx* ctx) {
     const size_t nwarps = (n + groups_per_warp - 1) / groups_per_warp;
     const size_t rounds = (nwarps + (size_t)ctx->sm_count - 1) / (size_t)ctx->sm_count;
     const double filler = (double)rounds * (5.0 * (ctx->v_rwin + ctx->v_cwin) + 30.0);
-    const double horner = (double)(t > 1 ? t - 1 : 0) * (double)ctx->v_nops_max;
+    const double horner = (double)(t > 1 ? t - 1 : 0) / (double)ctx->v_k * (double)ctx->v_nops_max;
     if (filler > 0.6 * horner) overlap = 0;
     // ... and only when the Horner launch leaves a hole: W one-warp CTAs fill the 4 schedulers of every SM
     // evenly when W is a multiple of 4 * SMs; the filler warp then becomes a third warp on one scheduler per SM
@@ -642,8 +742,9 @@ static int verify_kernels(mpvss_ctx* ctx) {
   const bool side = overlap == 2 || overlap == 3;
   if (!side) MPVSS_TRY(launch_a2(ctx->stream));
   // X_i from the commitments (participant.rs:423-434)
-  MPVSS_TRY(dev_horner(ctx, ctx->v_tpi, ctx->v_wpc, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, ctx->v_ops.as<uint16_t>(),
-                       ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_np, X));
+  PlanDev P{ctx->v_ops.as<uint16_t>(), ctx->v_slot.as<uint32_t>(), ctx->v_nd.as<uint32_t>(), ctx->v_first.as<uint32_t>(),
+            ctx->v_steps.as<uint32_t>(), ctx->v_e.as<uint32_t>(), ctx->v_np, ctx->v_k, ctx->v_tpi, ctx->v_wpc};
+  MPVSS_TRY(dev_horner(ctx, P, ctx->v_comm.as<uint32_t>(), ctx->v_cm, t, n, ctx->v_h, ctx->v_t2, X));
   if (side) {
     MPVSS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
     // 3: persistent one-warp CTAs, one per SM, into the warp slot the Horner CTAs leave empty

@@ -131,6 +131,11 @@ struct HornerArgs {
   uint32_t* out;           // results, canonical, 64 limbs each, indexed by slot
   uint32_t t, n, nops_all;
   uint32_t warps_per_cta;  // launch shape (0 = 1); nops is indexed by CTA
+  // Chunked evaluation (few positions: the polynomial is cut into K contiguous chunks so that K times as many
+  // lane groups run chains 1/K as long; the host combines X = prod_k H_k^(pos^(k B))).  Per CTA: index of the
+  // chunk's top coefficient and its number of Horner steps; nullptr = the whole polynomial (t-1, t-1).
+  const uint32_t* cfirst;
+  const uint32_t* csteps;
 };
 
 constexpr int HC_SLOTS = 6;   // == modp_chain::SLOTS; slot 6 = Montgomery one, slot 7 = C_j
@@ -143,7 +148,8 @@ constexpr int horner_smem_words = (32 / TPI) * (HC_GSTRIDE + HC_OPS / 2);
 // NP1: the modulus satisfies -q^-1 = 1 mod 2^32 (true for the RFC 3526 prime, whose low 64 bits are all
 // ones), so the Montgomery digit is the low limb itself and one multiply leaves the per-digit critical path.
 template <int TPI, bool NP1 = false>
-MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t nops) {
+MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t nops, uint32_t first,
+                        uint32_t steps) {
   constexpr int L = Cfg<TPI>::L;
   constexpr int GPW = 32 / TPI;
   Lane ln = make_lane<TPI>();
@@ -160,9 +166,9 @@ MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_
   uint32_t acc[L];
   load_slice<TPI>(acc, A.consts + C_ONE, ln);
   stage<TPI>(gbase + HC_SLOTS * 64, acc, ln);
-  load_slice<TPI>(acc, A.cm + (size_t)(A.t - 1) * 64, ln);
+  load_slice<TPI>(acc, A.cm + (size_t)first * 64, ln);
   simt::syncwarp();
-  for (int j = (int)A.t - 2; j >= 0; --j) {
+  for (int j = (int)first - 1; j >= (int)first - (int)steps; --j) {
     {
       uint32_t cj[L];
       load_slice<TPI>(cj, A.cm + (size_t)j * 64, ln);

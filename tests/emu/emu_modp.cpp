@@ -36,13 +36,15 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
     default: return -1;            \
   }
 
+// `first` / `steps`: the chunk of the polynomial to evaluate (top coefficient index, Horner steps); the whole
+// polynomial is (t - 1, t - 1)
 extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint16_t* ops,
-                               uint32_t n, uint32_t nops, uint32_t* out) {
+                               uint32_t n, uint32_t nops, uint32_t* out, uint32_t first, uint32_t steps) {
   const bool np1 = consts[modp::C_NP] == 1u;
-  modp::HornerArgs A{consts, cm, ops, nullptr, nullptr, out, t, n, nops, 1};
+  modp::HornerArgs A{consts, cm, ops, nullptr, nullptr, out, t, n, nops, 1, nullptr, nullptr};
   DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, nops);
-                            else modp::horner_body<T, false>(A, w, s, nops); }));
+                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, nops, first, steps);
+                            else modp::horner_body<T, false>(A, w, s, nops, first, steps); }));
   return 0;
 }
 

@@ -174,9 +174,14 @@ def test_horner_kernel_equals_reference_schedule(lib, tpi):
     n = len(positions)
     out = np.zeros(64 * n, dtype=np.uint32)
     assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, ops.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint16)),
-                               n, nops, eu.P(out)) == 0
+                               n, nops, eu.P(out), t - 1, t - 1) == 0
     for i in range(n):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.x_reference_schedule(G, comm, positions[i]), (tpi, i)
+    # a chunk of the polynomial: coefficients 1..2 only, H = C_1 * C_2^pos (what the chunked launch computes)
+    assert lib.emu_modp_horner(tpi, eu.P(C), eu.P(cm), t, ops.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint16)),
+                               n, nops, eu.P(out), 2, 1) == 0
+    for i in range(n):
+        assert eu.from_limbs(out[64 * i:64 * i + 64]) == comm[1] * pow(comm[2], positions[i], Q) % Q, (tpi, i)
 
 
 def test_frame_kernel_minimal_big_endian():

@@ -246,7 +246,8 @@ def test_overlap_modes_and_lane_counts_agree(modp_group):
     box = dealer.distribute_secret(SECRET, pks, t, coeffs=co, witnesses=ws)
     ref = None
     try:
-        for key, values in (("modp_overlap", (0, 2, 3)), ("modp_tpi", (4, 16, 8))):
+        for key, values in (("modp_overlap", (0, 2, 3)), ("modp_tpi", (4, 16, 8)), ("modp_chunks", (2, 3, 8, 0)),
+                            ("modp_wpc", (4, 0))):
             for v in values:
                 modp_group.ctx.set_int(key, v)
                 tr = {}
@@ -257,6 +258,26 @@ def test_overlap_modes_and_lane_counts_agree(modp_group):
     finally:
         modp_group.ctx.set_int("modp_overlap", 3)
         modp_group.ctx.set_int("modp_tpi", 8)
+        modp_group.ctx.set_int("modp_chunks", 0)
+        modp_group.ctx.set_int("modp_wpc", 0)
+
+
+def test_chunked_horner_small_boxes(modp_group):
+    """Few positions: the polynomial is evaluated in K contiguous chunks and recombined as
+    X = prod_k H_k^(pos^(k B) mod (q-1)); same X as the single chain, the dealer's g^P(i) and the oracle, for
+    even and odd positions (the CRT parity fix of the chunk exponents) and chunk counts that do not divide t."""
+    n, t = 9, 70
+    co = synth.coefficients(44, t, OG.order())
+    comm = modp_group.fixed_base_exp(co, generator=1)
+    pos = [1, 2, 3, 4, 7, 100, 4095, 4096, 65537]
+    want = modp_group.fixed_base_exp([pvss.poly_eval_mod(co, p, OG.order()) for p in pos], generator=1)
+    try:
+        for k in (1, 2, 3, 5, 0):
+            modp_group.ctx.set_int("modp_chunks", k)
+            assert modp_group.poly_eval_exp(comm, pos) == want, k
+    finally:
+        modp_group.ctx.set_int("modp_chunks", 0)
+    assert want[0] == pvss.x_reference_schedule(OG, comm, 1) and want[5] == pvss.x_horner_schedule(OG, comm, 100)
 
 
 def test_bucket_multi_exp_equals_direct(modp_group):
