@@ -317,6 +317,7 @@ class Runner:
         self.ok = ctypes.c_int(0)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         self.modp = box["group"] == "modp"
+        self.check = True
 
     def P(self, key):
         return ctypes.cast(self.host[key].data_ptr(), ctypes.POINTER(ctypes.c_uint8))
@@ -368,11 +369,11 @@ class Runner:
         """resident steps, then full calls; returns a dict of means (max over ranks per step)"""
         self.stage()
         res = self.timed(self.run, steps, warmup)
-        assert all(r[1][0] == 1 for r in res), "synthetic box did not verify"
+        assert not self.check or all(r[1][0] == 1 for r in res), "synthetic box did not verify"
         launches = self.g.ctx.last_kernel_launches * steps * self.world
         sq, ml = self.g.ctx.last_horner_products()
         e2e = self.timed(self.full, steps, warmup)
-        assert all(r[1] == 1 for r in e2e)
+        assert not self.check or all(r[1] == 1 for r in e2e)
         return {"ms": statistics.mean(r[0] for r in res) * 1e3,
                 "kernel_ms": statistics.mean(self.maxr(r[1][1]) for r in res),
                 "horner_ms": statistics.mean(self.maxr(r[1][2]) for r in res),
@@ -434,6 +435,9 @@ def main():
     ap.add_argument("--ec-threads", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="override modp_overlap (0, 2 or 3)")
     ap.add_argument("--wpc", type=int, default=0, help="override warps per CTA of the MODP Horner launch (1..4)")
+    ap.add_argument("--chunks", type=int, default=0, help="override chunks per position of the MODP Horner launch")
+    ap.add_argument("--subset", type=int, default=0, help="kernel experiments: verify only the first M participants of "
+                    "the box (the verdict is then false by construction and not asserted; not a reportable number)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5", action="store_true", help="also time BASELINE config 5 (n=65536 t=43691) [default at 8 GPUs]")
@@ -478,6 +482,8 @@ def main():
             g.ctx.set_int("modp_overlap", args.overlap)
         if args.wpc and name == "modp":
             g.ctx.set_int("modp_wpc", args.wpc)
+        if args.chunks and name == "modp":
+            g.ctx.set_int("modp_chunks", args.chunks)
         if joined and world > 1:
             g.join(rank, world, dist)           # NCCL communicator inside the library
         return g
@@ -485,6 +491,15 @@ def main():
     group = make_group(args.group, True)
     eb = group.codec.eb
     box = build_box(group, n_total, t, args.seed)
+    if args.subset:      # kernel experiment: the first M participants only (transcript no longer matches)
+        box = dict(box, n=args.subset)
+        runner = Runner(group, box, torch, dist, rank, world)
+        runner.check = False
+        m_ = runner.measure(args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps({"experiment": f"first {args.subset} participants of a box of {n_total}, t={t}", "ms": m_["ms"],
+                              "kernel_ms": m_["kernel_ms"], "horner_ms": m_["horner_ms"], "chunks": args.chunks}))
+        return 0
     runner = Runner(group, box, torch, dist, rank, world)
 
     # correctness gates before timing: the box verifies; the verifier's X equals the dealer's g^P(i); at N>1 the
