@@ -9,7 +9,7 @@ CU        := $(CSRC)/api.cu $(CSRC)/comm.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu 
 OBJ       := $(CU:.cu=.o) $(CSRC)/sha256_ni.o
 HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/mpvss_b200.h
 
-all: $(LIB) emu
+all: $(LIB) emu cppmirror
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -24,10 +24,15 @@ emu: tests/emu/libemu_modp.so tests/emu/libemu_ec.so
 tests/emu/libemu_%.so: tests/emu/emu_%.cpp $(HDR)
 	$(CXX) -std=c++20 -O2 -DMPVSS_SIMT_EMU -shared -fPIC -pthread -o $@ $<
 
+# the reference's protocol tests over the C++ mirror of Participant<G> (include/mpvss_b200.hpp); runs on a GPU only
+cppmirror: tests/cpp/test_participant
+tests/cpp/test_participant: tests/cpp/test_participant.cpp include/mpvss_b200.hpp include/mpvss_b200.h $(LIB)
+	$(CXX) -std=c++17 -O1 -Wall -Wextra -Iinclude -o $@ $< -Lmpvss_rs_b200 -lmpvss_b200 -Wl,-rpath,'$$ORIGIN/../../mpvss_rs_b200'
+
 clean:
 	rm -f $(OBJ) $(LIB) tests/emu/*.so
 
-.PHONY: all emu clean
+.PHONY: all emu cppmirror clean
 
 # The reference itself (Rust) as the oracle's anchor: builds oracle/ref_harness against /root/reference and
 # regenerates tests/golden/ref_vectors.json.  Needs cargo + the crates of /root/reference/Cargo.toml;

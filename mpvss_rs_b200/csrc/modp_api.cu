@@ -263,7 +263,11 @@ static uint32_t horner_chunks(const mpvss_ctx* ctx, size_t n, size_t t) {
     const size_t warps = (n + 3) / 4, full = (size_t)8 * (size_t)ctx->sm_count;  // two warps per scheduler
     while (K < 8 && warps * (K * 2) <= full) K *= 2;
   }
-  while (K > 1 && t / K < 32) K /= 2;  // at least 32 coefficients per chunk
+  // The combination is not free: measured (tools/chunk_sweep.sh) 9 / 13 / 26 ms for K = 2 / 4 / 8 at 1024
+  // positions, against 2.3 us per sequential product of a chain.  At t = 683 every K > 1 loses
+  // (35.4 -> 39.5 / 38.2 ms), at t = 2731 K = 4 wins 28 % at 1024 positions and K = 8 42 % at 512.
+  if (ctx->modp_chunks <= 0 && t < 1366) K = 1;
+  while (K > 1 && t / K < (ctx->modp_chunks > 0 ? 32u : 340u)) K /= 2;
   return K;
 }
 
