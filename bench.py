@@ -136,6 +136,54 @@ def build_box(group, n_total, t, seed):
             "group": c.name, "U": int.from_bytes(bytes(u), "big")}
 
 
+def other_phases(group, box, seed, reps=2):
+    """The other four entry points of the path at the box's (n, t) -- distribute_secret, extract_secret_share x t,
+    verify_share x t, reconstruct from the first t shares (SURVEY.md 8d asks for them beside the verify metric).
+    Each figure is one C-ABI call with host buffers (copies inside); wall_ms by the host clock around the call,
+    kernel_ms by CUDA events on the library's stream; one untimed call first.  Results are checked: the shares
+    verify and the secret comes back."""
+    from mpvss_rs_b200 import synth
+    from mpvss_rs_b200.lib import buf, ptr
+    c, lib, h = group.codec, group.ctx.lib, group.ctx.h
+    n, t, eb, sb = box["n"], box["t"], c.eb, c.sb
+    secret = b"Hello MPVSS Example."
+    sks = buf(c.enc_scalars(synth.private_keys(seed, n, c.name, c.order, c.key_bound)[:t]))
+    ws_all = synth.witnesses(seed, n, c.key_bound)
+    ws, wt = buf(c.enc_scalars(ws_all)), buf(c.enc_scalars(ws_all[:t]))
+    coeffs = buf(c.enc_scalars(synth.coefficients(seed, t, c.order)))
+    pk, ys = buf(box["publickeys"]), buf(box["shares"][:t * eb])
+    comm, shares, chal, resp, u = buf(size=t * eb), buf(size=n * eb), buf(size=sb), buf(size=n * sb), buf(size=eb)
+    pko, so, co, ro = buf(size=t * eb), buf(size=t * eb), buf(size=t * sb), buf(size=t * sb)
+    st, ok = (ctypes.c_int * t)(), (ctypes.c_int * t)()
+    pos = (ctypes.c_int64 * t)(*range(1, t + 1))
+    ub, sec = buf(box["U"].to_bytes(eb, "big")), buf(size=eb)
+    calls = [
+        ("distribute_secret", n, lambda: lib.mpvss_distribute(h, n, t, ptr(buf(secret)), len(secret), ptr(coeffs), ptr(ws), ptr(pk),
+                                                             ptr(comm), ptr(shares), ptr(chal), ptr(resp), ptr(u), None)),
+        ("extract_secret_share", t, lambda: lib.mpvss_extract_shares(h, t, ptr(sks), ptr(wt), ptr(ys), ptr(pko), ptr(so), ptr(co),
+                                                                     ptr(ro), st)),
+        ("verify_share", t, lambda: lib.mpvss_verify_shares(h, t, ptr(pko), ptr(so), ptr(ys), ptr(co), ptr(ro), ok)),
+        ("reconstruct", t, lambda: lib.mpvss_reconstruct(h, t, pos, ptr(so), ptr(ub), ptr(sec), None)),
+    ]
+    out = {}
+    for name, units, fn in calls:
+        group.ctx.check(fn())
+        wall, kern = [], []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            group.ctx.check(fn())
+            wall.append((time.perf_counter() - t0) * 1e3)
+            kern.append(group.ctx.last_kernel_ms)
+        out[name] = {"units": units, "wall_ms": statistics.mean(wall), "kernel_ms": statistics.mean(kern),
+                     "units_per_s": units / (statistics.mean(wall) * 1e-3)}
+    assert bytes(shares) == box["shares"] and bytes(chal) == box["challenge"], "dealer is not deterministic"
+    assert all(x == 0 for x in st) and all(x == 1 for x in ok), "extracted shares do not verify"
+    assert bytes(sec).lstrip(b"\0") == secret, "reconstruct did not return the secret"
+    out["note"] = (f"one C-ABI call each with host buffers at n={n}, t={t}: distribute over n participants; extract / "
+                   "verify_share / reconstruct over the first t; outputs checked (shares verify, secret recovered)")
+    return out
+
+
 def participant_box(group, box):
     """The flat box as the reference-shaped DistributionSharesBox (tests)."""
     import mpvss_rs_b200 as m
@@ -608,6 +656,8 @@ def main():
                       CPU_PROXY[args.group] + ", one participant per thread",
             "same_algorithm_value": len(sample) / dt_h,
             "same_algorithm_note": "CPU running the GPU's Horner schedule (baseline B, BASELINE.md section 3)"}
+    if world == 1 and not args.no_also:
+        also["phases"] = other_phases(group, box, args.seed)
     if args.group == "modp" and world == 1 and not args.no_also:
         # the metric names MODP + secp256k1: the same step for Secp256k1Group, reported alongside
         try:
@@ -618,6 +668,7 @@ def main():
             sec = json.loads(out.stdout.strip().splitlines()[-1])
             also["secp256k1"] = {k: sec.get(k) for k in ("metric", "value", "unit", "ms_per_step", "kernel_ms_per_step",
                                                         "e2e", "roofline", "cpu_baseline", "phase_ms", "gpu_launches")}
+            also["secp256k1"]["phases"] = (sec.get("also") or {}).get("phases")
         except Exception as ex:  # the primary line stands on its own
             also["secp256k1"] = {"error": str(ex)[:200]}
     if also:
