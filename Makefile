@@ -5,7 +5,7 @@ CXX       ?= g++
 CSRC      := mpvss_rs_b200/csrc
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread
 LIB       := mpvss_rs_b200/libmpvss_b200.so
-CU        := $(CSRC)/api.cu $(CSRC)/comm.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu $(CSRC)/ec_api.cu $(CSRC)/ec.cu
+CU        := $(CSRC)/api.cu $(CSRC)/comm.cu $(CSRC)/modp_api.cu $(CSRC)/modp.cu $(CSRC)/ec_api.cu $(CSRC)/ec.cu $(CSRC)/hash.cu
 OBJ       := $(CU:.cu=.o) $(CSRC)/sha256_ni.o
 HDR       := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/mpvss_b200.h
 

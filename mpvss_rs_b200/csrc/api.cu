@@ -206,6 +206,10 @@ int mpvss_poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, co
 int mpvss_dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2,
                              const uint8_t* h2, const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n,
                              uint8_t* a1, uint8_t* a2) {
+  if (ctx && (!a1 || !a2)) {  // only internal callers may leave the results on the device
+    Guard g(ctx);
+    return mpvss_fail(ctx, MPVSS_ERR_ARG, "dleq_verify_commit: bad arguments");
+  }
   DISPATCH(ctx, dleq_verify_commit, g1, h1, g2, h2, r, c, c_stride, n, a1, a2);
 }
 int mpvss_dleq_prove_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* g2, const uint8_t* w, size_t n,

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(TPB) frame_kernel(FrameArgs A) { frame_body(A,
 __global__ void __launch_bounds__(TPB) poly_kernel(PolyArgs A) { poly_body(A, TID); }
 __global__ void __launch_bounds__(TPB) lagrange_kernel(LagrangeArgs A) { lagrange_body(A, TID); }
 __global__ void __launch_bounds__(TPB) inv_kernel(InvArgs A) { inv_body(A, TID); }
+__global__ void __launch_bounds__(TPB) proof_kernel(ProofArgs A) { proof_body(A, TID); }
 
 template <class Cv> cudaError_t launch_exp2(const Exp2Args<Cv>& A, cudaStream_t s) {
   if (A.n == 0) return cudaErrorInvalidValue;
@@ -96,6 +97,12 @@ cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s) {
 cudaError_t launch_inv(const InvArgs& A, cudaStream_t s) {
   if (A.n == 0) return cudaErrorInvalidValue;
   inv_kernel<<<blocks(A.n), TPB, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_proof(const ProofArgs& A, cudaStream_t s) {
+  if (A.n == 0) return cudaErrorInvalidValue;
+  proof_kernel<<<blocks(A.n), TPB, 0, s>>>(A);
   return cudaGetLastError();
 }
 

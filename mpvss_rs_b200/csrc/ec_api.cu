@@ -11,6 +11,7 @@
 //   Lagrange sign handling        participant.rs:1518-1557 / 1955-2002
 #include "ctx.h"
 #include "ec_launch.h"
+#include "hash_launch.h"
 #include "sha2.h"
 #include "transcript.h"
 
@@ -158,7 +159,23 @@ struct Ec {
   // boundary scalars -> device limb layout (8 little-endian u32 per scalar)
   static int scalars_in(mpvss_ctx* ctx, const uint8_t* s, size_t n, std::vector<uint32_t>& out) {
     out.resize(n * 8);
+    uint32_t ord[8];
+    put8(ord, ctx->ec_order);
     for (size_t i = 0; i < n; ++i) {
+      // fast path, no allocation: canonical values (below the order) are just re-packed
+      uint32_t* o = out.data() + i * 8;
+      for (int k = 0; k < 8; ++k) {
+        const uint8_t* q = s + i * SB + (T::SCALAR_BE ? 4 * (7 - k) : 4 * k);
+        o[k] = T::SCALAR_BE ? ((uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3])
+                            : ((uint32_t)q[3] << 24 | (uint32_t)q[2] << 16 | (uint32_t)q[1] << 8 | q[0]);
+      }
+      bool below = false;
+      for (int k = 7; k >= 0; --k)
+        if (o[k] != ord[k]) {
+          below = o[k] < ord[k];
+          break;
+        }
+      if (below) continue;
       big::Int v = T::SCALAR_BE ? big::from_be(s + i * SB, SB) : big::from_le(s + i * SB, SB);
       if (big::cmp(v, ctx->ec_order) >= 0) {
         if (T::SCALAR_BE)  // k256 Scalar::from_repr rejects non-canonical values
@@ -379,15 +396,16 @@ struct Ec {
   static int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2,
                                 const uint8_t* h2, const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n,
                                 uint8_t* a1, uint8_t* a2, std::vector<uint8_t>* undecodable = nullptr) {
-    MPVSS_TRY(bad(ctx, g1 && h1 && g2 && h2 && r && c && a1 && a2 && n > 0 && (c_stride == 0 || c_stride == SB),
+    MPVSS_TRY(bad(ctx, g1 && h1 && g2 && h2 && r && c && ((a1 && a2) || undecodable) && n > 0 &&
+                           (c_stride == 0 || c_stride == SB),
                   "dleq_verify_commit: bad arguments"));
     std::vector<uint32_t> rl, cl;
     if (undecodable) {
       undecodable->assign(n, 0);
       rl.assign(n * 8, 0);
       cl.assign((c_stride ? n : 1) * 8, 0);
+      std::vector<uint32_t> one;
       for (size_t i = 0; i < n; ++i) {  // per-instance: a non-canonical scalar only spoils its own share
-        std::vector<uint32_t> one;
         if (scalars_in(ctx, r + i * SB, 1, one) != MPVSS_OK) (*undecodable)[i] = 1;
         else memcpy(&rl[i * 8], one.data(), 32);
         if (c_stride || i == 0) {
@@ -428,8 +446,8 @@ struct Ec {
       MPVSS_TRY(check_status(ctx, ds1, n, "dleq_verify_commit (g1/h1)"));
       MPVSS_TRY(check_status(ctx, ds2, n, "dleq_verify_commit (g2/h2)"));
     }
-    MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
-    MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
+    if (a1) MPVSS_TRY(d2h(ctx, a1, da1, n * EB));  // nullptr: the caller continues on the device (verify_shares)
+    if (a2) MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
     return sync(ctx);
   }
   static int dleq_prove_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* g2, const uint8_t* w, size_t n,
@@ -747,6 +765,35 @@ struct Ec {
     return sync(ctx);
   }
 
+  // Per-share Fiat-Shamir step on device-resident encodings: frame the rows F(h1) F(h2) F(a1) F(a2), hash them
+  // (sha2_dev.cuh) and finish in the scalar field (ec::proof_body).  Prover (sk, w given): challenge and response
+  // in the boundary encoding; verifier (c_in given): ok[i] = recomputed challenge == c_in[i].  The launches are
+  // added to the kernel time of the call.
+  static int share_transcripts(mpvss_ctx* ctx, const uint8_t* h1, const uint8_t* h2, const uint8_t* a1, const uint8_t* a2,
+                               size_t n, const uint32_t* sk, const uint32_t* w, const uint8_t* c_in, uint8_t* c_out,
+                               uint8_t* r_out, uint32_t* ok) {
+    const uint32_t wide = T::SCALAR_BE ? 0u : 1u;  // ristretto255: SHA-512, little-endian, 512-bit reduction
+    const size_t slot = 8 + EB;
+    DevBuf &drows = ctx->buf(12), &dh = ctx->buf(13);
+    MPVSS_CUDA(ctx, drows.ensure(n * 4 * slot));
+    MPVSS_CUDA(ctx, dh.ensure(n * (wide ? 16 : 8) * 4));
+    const float ms0 = ctx->last_ms;
+    const int l0 = ctx->last_launches;
+    timing_begin(ctx);
+    ec::FrameArgs FA{h1, h2, a1, a2, drows.as<uint8_t>(), (uint32_t)n, (uint32_t)EB};
+    MPVSS_CUDA(ctx, ec::launch_frames(FA, ctx->stream));
+    shadev::RowHashArgs HA{drows.as<uint8_t>(), (uint32_t)(4 * slot), (uint32_t)slot, dh.as<uint32_t>(), wide ? 16u : 8u,
+                           nullptr, (uint32_t)n, wide};
+    MPVSS_CUDA(ctx, shadev::launch_row_hash(HA, ctx->stream));
+    ec::ProofArgs PA{KN(ctx), dh.as<uint32_t>(), sk, w, c_in, c_out, r_out, ok, (uint32_t)n, wide, T::SCALAR_BE ? 1u : 0u};
+    MPVSS_CUDA(ctx, ec::launch_proof(PA, ctx->stream));
+    timing_launch(ctx, 3);
+    MPVSS_TRY(timing_end(ctx));
+    ctx->last_ms += ms0;
+    ctx->last_launches += l0;
+    return MPVSS_OK;
+  }
+
   // ---- extract_secret_share (batch) ----------------------------------------------------------------
   static int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const uint8_t* witnesses,
                             const uint8_t* enc_shares, uint8_t* publickeys_out, uint8_t* shares_out,
@@ -779,29 +826,25 @@ struct Ec {
                        nullptr, dst.as<uint32_t>() + n));
     MPVSS_TRY(timing_end(ctx));
     MPVSS_TRY(check_status(ctx, dst, 2 * n, "extract_shares (encrypted shares)"));
-    std::vector<uint8_t> A1(n * EB), A2(n * EB);
+    // Per-share transcript (pk, Y, a1, a2), challenge and response r = w - sk c on the device:
+    // n independent SHA-256 chains, one per thread; a1 / a2 never leave the GPU.
+    DevBuf &dc = ctx->buf(14), &dr = ctx->buf(15);
+    MPVSS_CUDA(ctx, dc.ensure(n * SB));
+    MPVSS_CUDA(ctx, dr.ensure(n * SB));
+    MPVSS_TRY(share_transcripts(ctx, dpk.as<uint8_t>(), dY.as<uint8_t>(), dA1.as<uint8_t>(), dA2.as<uint8_t>(), n,
+                                dsk.as<uint32_t>(), dw.as<uint32_t>(), nullptr, dc.as<uint8_t>(), dr.as<uint8_t>(),
+                                nullptr));
     std::vector<uint32_t> inv_st(n);
     MPVSS_TRY(d2h(ctx, publickeys_out, dpk, n * EB));
     MPVSS_TRY(d2h(ctx, shares_out, dS, n * EB));
-    MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
-    MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
+    MPVSS_TRY(d2h(ctx, challenges_out, dc, n * SB));
+    MPVSS_TRY(d2h(ctx, responses_out, dr, n * SB));
     MPVSS_TRY(d2h(ctx, inv_st.data(), dis, n * 4));
+    // the scratch buffers held secrets (private keys, inverses, witnesses)
+    for (DevBuf* b : {&dsk, &dinv, &dw}) MPVSS_CUDA(ctx, cudaMemsetAsync(b->p, 0, b->cap, ctx->stream));
     MPVSS_TRY(sync(ctx));
-    const big::Int& ord = ctx->ec_order;
-    for (size_t i = 0; i < n; ++i) {
-      sha2::Sha256 h;  // (pk, Y, a1, a2)
-      framed(h, publickeys_out + i * EB);
-      framed(h, enc_shares + i * EB);
-      framed(h, A1.data() + i * EB);
-      framed(h, A2.data() + i * EB);
-      big::Int c = challenge_of(ctx, h, nullptr);
-      scalar_out(c, challenges_out + i * SB);
-      big::Int ski(sk.begin() + i * 8, sk.begin() + i * 8 + 8), wi(wl.begin() + i * 8, wl.begin() + i * 8 + 8);
-      big::trim(ski);
-      big::trim(wi);
-      scalar_out(big::submod(wi, big::mulmod(ski, c, ord), ord), responses_out + i * SB);
-      if (status_out) status_out[i] = inv_st[i] ? MPVSS_ERR_NOT_INVERTIBLE : MPVSS_OK;
-    }
+    if (status_out)
+      for (size_t i = 0; i < n; ++i) status_out[i] = inv_st[i] ? MPVSS_ERR_NOT_INVERTIBLE : MPVSS_OK;
     return MPVSS_OK;
   }
 
@@ -810,18 +853,22 @@ struct Ec {
                            int* ok_out) {
     MPVSS_TRY(bad(ctx, n > 0 && publickeys && shares && enc_shares && challenges && responses && ok_out,
                   "verify_shares: bad arguments"));
-    std::vector<uint8_t> a1(n * EB), a2(n * EB), undecodable;
+    std::vector<uint8_t> undecodable;
+    // a1 = G^r pk^c, a2 = S^r Y^c stay on the device (a1 / a2 == nullptr): buf(1) = pk, buf(3) = Y, buf(6) = a1,
+    // buf(7) = a2 afterwards; the per-share transcript is hashed and compared there
     MPVSS_TRY(dleq_verify_commit(ctx, ctx->ec_gen.data(), publickeys, shares, enc_shares, responses, challenges, SB, n,
-                                 a1.data(), a2.data(), &undecodable));
-    for (size_t i = 0; i < n; ++i) {
-      sha2::Sha256 h;
-      framed(h, publickeys + i * EB);
-      framed(h, enc_shares + i * EB);
-      framed(h, a1.data() + i * EB);
-      framed(h, a2.data() + i * EB);
-      // a share box that does not decode is simply not valid (bytes_to_element -> None in the reference)
-      ok_out[i] = !undecodable[i] && big::cmp(challenge_of(ctx, h, nullptr), scalar_big(challenges + i * SB)) == 0;
-    }
+                                 nullptr, nullptr, &undecodable));
+    DevBuf &dcin = ctx->buf(14), &dok = ctx->buf(15);
+    MPVSS_TRY(h2d(ctx, dcin, challenges, n * SB));
+    MPVSS_CUDA(ctx, dok.ensure(n * 4));
+    MPVSS_TRY(share_transcripts(ctx, ctx->buf(1).as<uint8_t>(), ctx->buf(3).as<uint8_t>(), ctx->buf(6).as<uint8_t>(),
+                                ctx->buf(7).as<uint8_t>(), n, nullptr, nullptr, dcin.as<uint8_t>(), nullptr, nullptr,
+                                dok.as<uint32_t>()));
+    std::vector<uint32_t> okv(n);
+    MPVSS_TRY(d2h(ctx, okv.data(), dok, n * 4));
+    MPVSS_TRY(sync(ctx));
+    // a share box that does not decode is simply not valid (bytes_to_element -> None in the reference)
+    for (size_t i = 0; i < n; ++i) ok_out[i] = !undecodable[i] && okv[i] == 1;
     return MPVSS_OK;
   }
 

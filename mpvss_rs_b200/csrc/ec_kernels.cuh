@@ -404,4 +404,73 @@ MP_DEV void inv_body(const InvArgs& A, uint32_t tid) {
   store(A.out + (size_t)tid * 8, from_mont(inv(to_mont(x, *A.N), *A.N), *A.N));
 }
 
+// ------------------------------------------------- per-share DLEQ transcripts ----
+// Second half of a per-share Fiat-Shamir step once shadev::row_hash_body has hashed the share's row
+// (sha2_dev.cuh): reduce hash_to_scalar's integer into the scalar field and either
+//   extract (sk, w given): c and r = w - sk * c  (participant.rs:1323-1333 / 1766-1776; dleq.rs:42-50), or
+//   verify  (c_in given):  ok = (c == c_in)      (dleq.rs:119-126 via participant.rs:1370 / 1813).
+// wide = 0: h is int_be(SHA-256(digest)) < 2^256 < 2n, one conditional subtraction (secp256k1.rs:121-131);
+// wide = 1: h is the 512-bit int_le(SHA-512(digest)), reduced as lo + hi * 2^256 with Montgomery products by
+// R^2 (ristretto255.rs:196-205, Scalar::from_bytes_mod_order_wide).  Scalars leave in the boundary encoding.
+struct ProofArgs {
+  const Modulus* N;
+  const uint32_t* h;       // n x (wide ? 16 : 8) limbs
+  const uint32_t *sk, *w;  // extract: n x 8 limbs each
+  const uint8_t* c_in;     // verify: n x 32 bytes
+  uint8_t *c_out, *r_out;  // extract: n x 32 bytes each
+  uint32_t* ok;            // verify
+  uint32_t n, wide, big_endian;
+};
+MP_DEV void scalar_bytes_out(uint8_t* o, const fp256::Fe& v, bool big_endian) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t x = v.v[i];
+    if (big_endian) {
+      uint8_t* q = o + 4 * (7 - i);
+      q[0] = (uint8_t)(x >> 24); q[1] = (uint8_t)(x >> 16); q[2] = (uint8_t)(x >> 8); q[3] = (uint8_t)x;
+    } else {
+      uint8_t* q = o + 4 * i;
+      q[0] = (uint8_t)x; q[1] = (uint8_t)(x >> 8); q[2] = (uint8_t)(x >> 16); q[3] = (uint8_t)(x >> 24);
+    }
+  }
+}
+MP_DEV fp256::Fe scalar_bytes_in(const uint8_t* p, bool big_endian) {
+  fp256::Fe v;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (big_endian) {
+      const uint8_t* q = p + 4 * (7 - i);
+      v.v[i] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
+    } else {
+      const uint8_t* q = p + 4 * i;
+      v.v[i] = (uint32_t)q[3] << 24 | (uint32_t)q[2] << 16 | (uint32_t)q[1] << 8 | q[0];
+    }
+  }
+  return v;
+}
+MP_DEV void proof_body(const ProofArgs& A, uint32_t tid) {
+  if (tid >= A.n) return;
+  using namespace fp256;
+  const Modulus& N = *A.N;
+  Fe c;
+  if (A.wide) {
+    const uint32_t* h = A.h + (size_t)tid * 16;
+    const Fe r2 = load(N.r2);
+    Fe lo = mul(load(h), r2, N);               // lo * R
+    Fe hi = mul(mul(load(h + 8), r2, N), r2, N);  // hi * R * R = (hi * 2^256) * R
+    c = from_mont(add(lo, hi, N), N);
+  } else {
+    c = cond_sub(load(A.h + (size_t)tid * 8), 0, N);
+  }
+  const bool be = A.big_endian != 0;
+  if (A.c_in) {
+    A.ok[tid] = eq(c, scalar_bytes_in(A.c_in + (size_t)tid * 32, be)) ? 1u : 0u;
+  } else {
+    Fe sk = load(A.sk + (size_t)tid * 8), w = load(A.w + (size_t)tid * 8);
+    Fe r = sub(w, mul(sk, to_mont(c, N), N), N);  // mont(sk, c R) = sk c
+    scalar_bytes_out(A.c_out + (size_t)tid * 32, c, be);
+    scalar_bytes_out(A.r_out + (size_t)tid * 32, r, be);
+  }
+}
+
 }  // namespace ec

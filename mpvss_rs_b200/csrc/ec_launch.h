@@ -23,4 +23,5 @@ cudaError_t launch_frames(const FrameArgs& A, cudaStream_t s);
 cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s);
 cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s);
 cudaError_t launch_inv(const InvArgs& A, cudaStream_t s);
+cudaError_t launch_proof(const ProofArgs& A, cudaStream_t s);
 }  // namespace ec

@@ -6,13 +6,12 @@
 namespace modp {
 
 
-template <int TPI, bool NP1>
+template <int TPI, bool NP1, bool CHUNKED>
 __global__ void __launch_bounds__(HORNER_MAX_WARPS_PER_CTA * 32) horner_kernel(HornerArgs A) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t w = threadIdx.x >> 5;
-  horner_body<TPI, NP1>(A, blockIdx.x * (blockDim.x >> 5) + w, smem + w * horner_smem_words<TPI>,
-                        A.nops ? A.nops[blockIdx.x] : A.nops_all, A.cfirst ? A.cfirst[blockIdx.x] : A.t - 1,
-                        A.csteps ? A.csteps[blockIdx.x] : A.t - 1);
+  horner_body<TPI, NP1, CHUNKED>(A, blockIdx.x * (blockDim.x >> 5) + w, smem + w * horner_smem_words<TPI>,
+                                 A.nops ? A.nops[blockIdx.x] : A.nops_all, blockIdx.x);
 }
 
 template <int TPI>
@@ -121,6 +120,13 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     default: return cudaErrorInvalidValue;                 \
   }
 
+template <int TPI, bool NP1, bool CHUNKED>
+static cudaError_t horner_go(const HornerArgs& A, uint32_t grid, uint32_t wpc, size_t sm, cudaStream_t s) {
+  cudaError_t e = set_smem(horner_kernel<TPI, NP1, CHUNKED>, sm);
+  if (e != cudaSuccess) return e;
+  horner_kernel<TPI, NP1, CHUNKED><<<grid, wpc * 32, sm, s>>>(A);
+  return cudaSuccess;
+}
 cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStream_t s) {
   if (A.n == 0 || A.t == 0 || A.warps_per_cta > (uint32_t)HORNER_MAX_WARPS_PER_CTA) return cudaErrorInvalidValue;
   MODP_DISPATCH(tpi, {
@@ -128,15 +134,10 @@ cudaError_t launch_horner(int tpi, const HornerArgs& A, bool np_is_one, cudaStre
     size_t sm = wpc * horner_smem_words<T> * 4;
     uint32_t per_cta = wpc * (32 / T);
     uint32_t grid = (A.n + per_cta - 1) / per_cta;
-    if (np_is_one) {
-      cudaError_t e = set_smem(horner_kernel<T, true>, sm);
-      if (e != cudaSuccess) return e;
-      horner_kernel<T, true><<<grid, wpc * 32, sm, s>>>(A);
-    } else {
-      cudaError_t e = set_smem(horner_kernel<T, false>, sm);
-      if (e != cudaSuccess) return e;
-      horner_kernel<T, false><<<grid, wpc * 32, sm, s>>>(A);
-    }
+    const bool chunked = A.cfirst && A.csteps;
+    cudaError_t e = np_is_one ? (chunked ? horner_go<T, true, true>(A, grid, wpc, sm, s) : horner_go<T, true, false>(A, grid, wpc, sm, s))
+                              : (chunked ? horner_go<T, false, true>(A, grid, wpc, sm, s) : horner_go<T, false, false>(A, grid, wpc, sm, s));
+    if (e != cudaSuccess) return e;
   });
   return cudaGetLastError();
 }

@@ -14,6 +14,7 @@
 #include "modp_chain.h"
 #include "modp_launch.h"
 #include "sha2.h"
+#include "hash_launch.h"
 #include "transcript.h"
 
 namespace {
@@ -442,7 +443,8 @@ int poly_eval_exp(mpvss_ctx* ctx, const uint8_t* commitments, size_t t, const in
 
 int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, const uint8_t* g2, const uint8_t* h2,
                        const uint8_t* r, const uint8_t* c, size_t c_stride, size_t n, uint8_t* a1, uint8_t* a2) {
-  MPVSS_TRY(check_args(ctx, g1 && h1 && g2 && h2 && r && c && a1 && a2 && n > 0 && (c_stride == 0 || c_stride == EB),
+  // a1 == a2 == nullptr (internal callers): the results stay on the device in buf(6) / buf(7)
+  MPVSS_TRY(check_args(ctx, g1 && h1 && g2 && h2 && r && c && (!a1 == !a2) && n > 0 && (c_stride == 0 || c_stride == EB),
                        "dleq_verify_commit: bad arguments"));
   DevBuf &dg1 = ctx->buf(0), &dh1 = ctx->buf(1), &dg2 = ctx->buf(2), &dh2 = ctx->buf(3), &dr = ctx->buf(4),
          &dc = ctx->buf(5), &da1 = ctx->buf(6), &da2 = ctx->buf(7);
@@ -468,8 +470,8 @@ int dleq_verify_commit(mpvss_ctx* ctx, const uint8_t* g1, const uint8_t* h1, con
   MPVSS_TRY(dev_exp2(ctx, K, dg2.as<uint32_t>(), EW, dr.as<uint32_t>(), EW, rw, dh2.as<uint32_t>(), EW,
                      dc.as<uint32_t>(), cs, cw, n, da2.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
-  MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
-  MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
+  if (a1) MPVSS_TRY(d2h(ctx, a1, da1, n * EB));
+  if (a2) MPVSS_TRY(d2h(ctx, a2, da2, n * EB));
   return sync(ctx);
 }
 
@@ -938,6 +940,29 @@ int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, 
 }
 
 // ------------------------------------------------------------------ extract ----
+// Per-share Fiat-Shamir transcripts on the device: frame (h1, h2, a1, a2) per share, one SHA-256
+// chain per thread, and hash_to_scalar's second SHA-256 (modp.rs:142-148; 256 < 2047 bits, so no reduction):
+// challenges as `stride`-limb little-endian scalars (64 = boundary scalars, 8 = just the hash).  The launches are
+// added to the kernel time of the call.
+static int share_challenges(mpvss_ctx* ctx, const uint32_t* h1, const uint32_t* h2, const uint32_t* a1, const uint32_t* a2,
+                            size_t n, uint32_t* c_out, uint32_t stride) {
+  DevBuf& drows = ctx->buf(14);
+  MPVSS_CUDA(ctx, drows.ensure(n * 4 * modp::FRAME_BYTES));
+  const float ms0 = ctx->last_ms;
+  const int l0 = ctx->last_launches;
+  timing_begin(ctx);
+  modp::FrameArgs FA{h1, h2, a1, a2, drows.as<uint8_t>(), (uint32_t)n};
+  MPVSS_CUDA(ctx, modp::launch_frames(FA, ctx->stream));
+  shadev::RowHashArgs HA{drows.as<uint8_t>(), 4u * modp::FRAME_BYTES, (uint32_t)modp::FRAME_BYTES, c_out, stride, nullptr,
+                         (uint32_t)n, 0u};
+  MPVSS_CUDA(ctx, shadev::launch_row_hash(HA, ctx->stream));
+  timing_launch(ctx, 2);
+  MPVSS_TRY(timing_end(ctx));
+  ctx->last_ms += ms0;
+  ctx->last_launches += l0;
+  return MPVSS_OK;
+}
+
 int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const uint8_t* witnesses,
                    const uint8_t* enc_shares, uint8_t* publickeys_out, uint8_t* shares_out, uint8_t* challenges_out,
                    uint8_t* responses_out, int* status_out) {
@@ -997,34 +1022,24 @@ int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const 
   MPVSS_TRY(timing_end(ctx));
   ctx->last_ms += ms0;
   ctx->last_launches += l0;
-  std::vector<uint8_t> A1(n * EB), A2(n * EB);
-  MPVSS_TRY(d2h(ctx, publickeys_out, dpk, n * EB));
-  MPVSS_TRY(d2h(ctx, shares_out, dS, n * EB));
-  MPVSS_TRY(d2h(ctx, A1.data(), dA1, n * EB));
-  MPVSS_TRY(d2h(ctx, A2.data(), dA2, n * EB));
-  MPVSS_TRY(sync(ctx));
-  for (size_t i = 0; i < n; ++i) {
-    sha2::Sha256 h;  // participant.rs:330-340: (pk, Y, a1, a2)
-    framed_update(h, publickeys_out + i * EB);
-    framed_update(h, enc_shares + i * EB);
-    framed_update(h, A1.data() + i * EB);
-    framed_update(h, A2.data() + i * EB);
-    uint8_t digest[32];
-    h.finalize(digest);
-    challenge_from_digest(ctx, digest, challenges_out + i * EB);
-  }
   {
-    // r = w - sk*c mod (q-1) on the device (dleq.rs:42-50 with modp.rs:180-192)
+    // challenge per share from the transcript (pk, Y, a1, a2) (participant.rs:330-340) and the response
+    // r = w - sk*c mod (q-1) (dleq.rs:42-50 with modp.rs:180-192), both on the device: a1 / a2 stay there
     std::vector<uint32_t> order(EW, 0);
     for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
     DevBuf &dord = ctx->buf(11), &dch = ctx->buf(12), &dR = ctx->buf(13);
     MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
-    MPVSS_TRY(h2d(ctx, dch, challenges_out, n * EB));
+    MPVSS_CUDA(ctx, dch.ensure(n * EB));
     MPVSS_CUDA(ctx, dR.ensure(n * EB));
+    MPVSS_TRY(share_challenges(ctx, dpk.as<uint32_t>(), dY.as<uint32_t>(), dA1.as<uint32_t>(), dA2.as<uint32_t>(), n,
+                               dch.as<uint32_t>(), EW));
     modp::RespArgs RA{dord.as<uint32_t>(), dsk.as<uint32_t>(), dw.as<uint32_t>(), dch.as<uint32_t>(), dR.as<uint32_t>(),
                       (uint32_t)n, EW, EW};
     MPVSS_CUDA(ctx, modp::launch_resp(RA, ctx->stream));
     ctx->last_launches += 1;
+    MPVSS_TRY(d2h(ctx, publickeys_out, dpk, n * EB));
+    MPVSS_TRY(d2h(ctx, shares_out, dS, n * EB));
+    MPVSS_TRY(d2h(ctx, challenges_out, dch, n * EB));
     MPVSS_TRY(d2h(ctx, responses_out, dR, n * EB));
     // the scratch buffers held secrets (private keys, inverses, witnesses)
     for (DevBuf* b : {&dsk, &dskg, &dinv, &dw}) MPVSS_CUDA(ctx, cudaMemsetAsync(b->p, 0, b->cap, ctx->stream));
@@ -1039,20 +1054,25 @@ int verify_shares(mpvss_ctx* ctx, size_t n, const uint8_t* publickeys, const uin
                   const uint8_t* enc_shares, const uint8_t* challenges, const uint8_t* responses, int* ok_out) {
   MPVSS_TRY(check_args(ctx, n > 0 && publickeys && shares && enc_shares && challenges && responses && ok_out,
                        "verify_shares: bad arguments"));
-  std::vector<uint8_t> a1(n * EB), a2(n * EB), gen(EB, 0);
+  std::vector<uint8_t> gen(EB, 0);
   gen[0] = 2;  // DLEQ(G, pk, S, Y)  participant.rs:378-385
-  MPVSS_TRY(dleq_verify_commit(ctx, gen.data(), publickeys, shares, enc_shares, responses, challenges, EB, n,
-                               a1.data(), a2.data()));
+  // a1 / a2 stay on the device (nullptr outputs): buf(1) = pk, buf(3) = Y, buf(6) = a1, buf(7) = a2 afterwards
+  MPVSS_TRY(dleq_verify_commit(ctx, gen.data(), publickeys, shares, enc_shares, responses, challenges, EB, n, nullptr,
+                               nullptr));
+  // dleq.rs:275-302: per share, the transcript (h1, h2, a1, a2) = (pk, Y, a1, a2) hashed on the device; the
+  // 256-bit challenges come back (32 bytes per share) and are compared here
+  DevBuf& dch = ctx->buf(12);
+  MPVSS_CUDA(ctx, dch.ensure(n * 32));
+  MPVSS_TRY(share_challenges(ctx, ctx->buf(1).as<uint32_t>(), ctx->buf(3).as<uint32_t>(), ctx->buf(6).as<uint32_t>(),
+                             ctx->buf(7).as<uint32_t>(), n, dch.as<uint32_t>(), 8));
+  std::vector<uint8_t> c(n * 32);
+  MPVSS_TRY(d2h(ctx, c.data(), dch, n * 32));
+  MPVSS_TRY(sync(ctx));
   for (size_t i = 0; i < n; ++i) {
-    sha2::Sha256 h;  // dleq.rs:275-302: (h1, h2, a1, a2) = (pk, Y, a1, a2)
-    framed_update(h, publickeys + i * EB);
-    framed_update(h, enc_shares + i * EB);
-    framed_update(h, a1.data() + i * EB);
-    framed_update(h, a2.data() + i * EB);
-    uint8_t digest[32], c[EB];
-    h.finalize(digest);
-    challenge_from_digest(ctx, digest, c);
-    ok_out[i] = memcmp(c, challenges + i * EB, EB) == 0;
+    const uint8_t* given = challenges + i * EB;
+    bool same = memcmp(c.data() + i * 32, given, 32) == 0;
+    for (size_t k = 32; k < EB && same; ++k) same = given[k] == 0;
+    ok_out[i] = same;
   }
   return MPVSS_OK;
 }

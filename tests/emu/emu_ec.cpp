@@ -3,6 +3,7 @@
 #include "../../mpvss_rs_b200/csrc/secp.cuh"
 #include "../../mpvss_rs_b200/csrc/rist.cuh"
 #include "../../mpvss_rs_b200/csrc/ec_kernels.cuh"
+#include "../../mpvss_rs_b200/csrc/sha2_dev.cuh"
 #include <vector>
 
 namespace {
@@ -90,6 +91,24 @@ int emu_ec_lagrange(const void* modN, const uint32_t* pos, uint32_t k, uint32_t*
 int emu_ec_inv(const void* modN, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* status) {
   ec::InvArgs A{(const fp256::Modulus*)modN, in, out, status, n};
   for (uint32_t i = 0; i < n; ++i) ec::inv_body(A, i);
+  return 0;
+}
+// per-share transcripts on the device: rows -> hash_to_scalar's integer (sha2_dev.cuh), then the scalar-field half
+int emu_row_hash(const uint8_t* rows, uint32_t row_stride, uint32_t slot_stride, uint32_t* out, uint32_t out_stride,
+                 uint8_t* digest_out, uint32_t n, uint32_t wide) {
+  shadev::RowHashArgs A{rows, row_stride, slot_stride, out, out_stride, digest_out, n, wide};
+  for (uint32_t i = 0; i < n; ++i) shadev::row_hash_body(A, i);
+  return 0;
+}
+int emu_box_hash(const uint8_t* rows, uint32_t row_stride, uint32_t slot_stride, uint32_t n, uint8_t* digest_out) {
+  shadev::BoxHashArgs A{rows, row_stride, slot_stride, n, digest_out};
+  for (uint32_t i = 0; i < 2; ++i) shadev::box_hash_body(A, i);
+  return 0;
+}
+int emu_ec_proof(const void* modN, const uint32_t* h, const uint32_t* sk, const uint32_t* w, const uint8_t* c_in,
+                 uint8_t* c_out, uint8_t* r_out, uint32_t* ok, uint32_t n, uint32_t wide, uint32_t big_endian) {
+  ec::ProofArgs A{(const fp256::Modulus*)modN, h, sk, w, c_in, c_out, r_out, ok, n, wide, big_endian};
+  for (uint32_t i = 0; i < n; ++i) ec::proof_body(A, i);
   return 0;
 }
 // special-form fields: out_mul = a*b mod p, out_sqr = a*a mod p (which: 0 secp256k1, 1 curve25519)

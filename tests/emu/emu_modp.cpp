@@ -41,10 +41,19 @@ template <int TPI> uint32_t warps_for(uint32_t n) { return (n + 32 / TPI - 1) / 
 extern "C" int emu_modp_horner(int tpi, const uint32_t* consts, const uint32_t* cm, uint32_t t, const uint16_t* ops,
                                uint32_t n, uint32_t nops, uint32_t* out, uint32_t first, uint32_t steps) {
   const bool np1 = consts[modp::C_NP] == 1u;
-  modp::HornerArgs A{consts, cm, ops, nullptr, nullptr, out, t, n, nops, 1, nullptr, nullptr};
-  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>,
-                          [&](uint32_t w, uint32_t* s) { if (np1) modp::horner_body<T, true>(A, w, s, nops, first, steps);
-                            else modp::horner_body<T, false>(A, w, s, nops, first, steps); }));
+  // the whole polynomial runs the unchunked instantiation, anything else the chunked one (one chunk for all CTAs)
+  const bool chunked = !(first == t - 1 && steps == t - 1);
+  modp::HornerArgs A{consts, cm, ops, nullptr, nullptr, out, t, n, nops, 1, chunked ? &first : nullptr,
+                     chunked ? &steps : nullptr};
+  DISPATCH(tpi, run_warps(warps_for<T>(n), modp::horner_smem_words<T>, [&](uint32_t w, uint32_t* s) {
+             if (chunked) {
+               if (np1) modp::horner_body<T, true, true>(A, w, s, nops, 0);
+               else modp::horner_body<T, false, true>(A, w, s, nops, 0);
+             } else {
+               if (np1) modp::horner_body<T, true, false>(A, w, s, nops, 0);
+               else modp::horner_body<T, false, false>(A, w, s, nops, 0);
+             }
+           }));
   return 0;
 }
 

@@ -51,7 +51,7 @@ ED_L = 2**252 + 27742317777372353535851937790883648493
 
 
 def build_ec(force=False):
-    deps = [EC_SRC] + [os.path.join(CSRC, f) for f in ("simt.h", "fp256.cuh", "fpspecial.cuh", "secp.cuh", "rist.cuh", "ec_kernels.cuh")]
+    deps = [EC_SRC] + [os.path.join(CSRC, f) for f in ("simt.h", "fp256.cuh", "fpspecial.cuh", "secp.cuh", "rist.cuh", "ec_kernels.cuh", "sha2_dev.cuh")]
     if force or not os.path.exists(EC_SO) or any(os.path.getmtime(d) > os.path.getmtime(EC_SO) for d in deps):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-DMPVSS_SIMT_EMU", "-shared", "-fPIC", "-pthread",
                                "-o", EC_SO, EC_SRC])

@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 mkdir -p variants/obj_$name
 C=mpvss_rs_b200/csrc
-for f in api comm modp_api modp ec_api ec; do
+for f in api comm modp_api modp ec_api ec hash; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-pthread "$@" -c $C/$f.cu -o variants/obj_$name/$f.o &
 done
 wait
