@@ -486,6 +486,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="override chunks per position of the MODP Horner launch")
     ap.add_argument("--subset", type=int, default=0, help="kernel experiments: verify only the first M participants of "
                     "the box (the verdict is then false by construction and not asserted; not a reportable number)")
+    ap.add_argument("--device-hash", action="store_true", help="experiment: whole-box transcript hashed by one device "
+                    "thread (device_hash tunable) instead of the host's SHA-NI")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5", action="store_true", help="also time BASELINE config 5 (n=65536 t=43691) [default at 8 GPUs]")
@@ -532,6 +534,8 @@ def main():
             g.ctx.set_int("modp_wpc", args.wpc)
         if args.chunks and name == "modp":
             g.ctx.set_int("modp_chunks", args.chunks)
+        if args.device_hash:
+            g.ctx.set_int("device_hash", 1)
         if joined and world > 1:
             g.join(rank, world, dist)           # NCCL communicator inside the library
         return g

@@ -76,7 +76,10 @@ const char* mpvss_last_error(const mpvss_ctx* ctx);
  * "modp_chunks" (contiguous chunks per position of the X_i launch, 0 = automatic: more than one only when the
  * launch would leave most of the chip idle); "modp_wpc" (warps per CTA of that launch); "modp_msm" /
  * "msm_threshold" (bucket method for multi_exp / reconstruct); "ec_threads" (thread target of the chunked
- * elliptic-curve Horner launch); "validate" (0/1, default 0:
+ * elliptic-curve Horner launch); "device_hash" (0/1, default 0: hash the whole-box transcript of
+ * verify_distribution as one SHA-256 chain on one device thread instead of on the host -- a measured alternative,
+ * two orders of magnitude slower than the host's SHA-NI; the per-share transcripts of extract_shares /
+ * verify_shares are always hashed on the device, one chain per thread); "validate" (0/1, default 0:
  * ModpGroup elements entering verify_distribution / verify_shares are checked for range 0 < x < q and
  * subgroup membership x^g = 1 -- the reference's bytes_to_element accepts anything, modp.rs:154-156;
  * a box that fails verifies as false) */

@@ -165,6 +165,10 @@ int mpvss_ctx_set_int(mpvss_ctx* ctx, const char* key, int value) {
     ctx->msm_threshold = value;
     return MPVSS_OK;
   }
+  if (std::string(key) == "device_hash") {
+    ctx->device_hash = value != 0;
+    return MPVSS_OK;
+  }
   if (std::string(key) == "validate") {
     ctx->validate = value != 0;
     return MPVSS_OK;

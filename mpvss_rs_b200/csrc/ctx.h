@@ -90,6 +90,7 @@ struct mpvss_ctx {
   int modp_msm = 2;          // multi_exp / reconstruct by buckets: 0 never, 1 always, 2 from msm_threshold bases on
   int msm_threshold = 512;   // measured on B200: buckets 9.0 / 9.8 / 12.4 / 22.5 ms against 9.2 / 13.4 / 33.1 / 119.6 ms direct
                              // at k = 683 / 2731 / 10923 / 43691 (profiles/msm_r02.json)
+  bool device_hash = false;  // whole-box transcript as one SHA-256 chain on one device thread (measured alternative)
   bool validate = false;     // range / subgroup check of ModpGroup elements entering the verify calls
   bool modp_np1 = false;     // -q^-1 = 1 mod 2^32: Horner kernels skip the Montgomery-digit multiply
   // ---- elliptic-curve groups ----

@@ -615,9 +615,17 @@ struct Ec {
       MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, g.row()));
       rows = ctx->v_ordered.as<uint8_t>();
     }
-    sha2::Sha256 h;
-    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h, true));
-    big::Int c = challenge_of(ctx, h, digest_out);
+    big::Int c;
+    if (ctx->device_hash) {  // measured alternative: the one sequential chain on one device thread
+      uint8_t digest[32];
+      MPVSS_TRY(transcript::device_digest(ctx, rows, n_total, ctx->nranks, g, digest));
+      if (digest_out) memcpy(digest_out, digest, 32);
+      c = T::hash_to_scalar(digest, 32, ctx->ec_order);
+    } else {
+      sha2::Sha256 h;
+      MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, g, h, true));
+      c = challenge_of(ctx, h, digest_out);
+    }
     *ok = big::cmp(c, scalar_big(ctx->v_challenge.data())) == 0;
     for (size_t r = 0; r < std::min<size_t>((size_t)ctx->nranks, n_total); ++r)  // a rank whose slice did not decode
       if (ctx->h_frames.as<uint8_t>()[r * g.row()] == 0xff) *ok = 0;      // marked its first row = participant r

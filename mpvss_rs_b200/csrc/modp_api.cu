@@ -802,10 +802,14 @@ int verify_run(mpvss_ctx* ctx, int* ok, uint8_t* x_out, uint8_t* a1_out, uint8_t
     MPVSS_TRY(comm_reorder_rows(ctx, ctx->v_gather.p, ctx->v_ordered.p, n_total, GEOM.row()));
     rows = ctx->v_ordered.as<uint8_t>();
   }
-  sha2::Sha256 h;
-  MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h, true));
   uint8_t digest[32], c[EB];
-  h.finalize(digest);
+  if (ctx->device_hash) {  // measured alternative: the one sequential chain on one device thread
+    MPVSS_TRY(transcript::device_digest(ctx, rows, n_total, ctx->nranks, GEOM, digest));
+  } else {
+    sha2::Sha256 h;
+    MPVSS_TRY(transcript::fetch_and_hash(ctx, rows, n_total, ctx->nranks, GEOM, h, true));
+    h.finalize(digest);
+  }
   challenge_from_digest(ctx, digest, c);
   *ok = memcmp(c, ctx->v_challenge.data(), EB) == 0;  // participant.rs:451-454
   for (size_t r = 0; r < std::min<size_t>((size_t)ctx->nranks, n_total); ++r)  // a rank whose slice failed validation

@@ -12,9 +12,11 @@
 // The copy to the host is cut into chunks that are hashed while the next chunk is still in flight.
 #pragma once
 #include <stddef.h>
+#include <algorithm>
 #include <stdint.h>
 #include "ctx.h"
 #include "sha2.h"
+#include "hash_launch.h"
 
 namespace transcript {
 
@@ -79,6 +81,26 @@ inline void hash_ordered(sha2::Sha256& h, const uint8_t* rows, size_t i0, size_t
     }
   }
   if (i1 > run) h.update(rows + run * row, (i1 - run) * row);
+}
+
+// The whole-box transcript hashed ON THE DEVICE ("device_hash" tunable): one thread walks the rows in
+// participant order (shadev::box_hash_body) and 32 bytes come back instead of the rows.  SHA-256 is one sequential
+// chain, so this is a single GPU thread against the host's SHA-NI unit: measured slower by two orders of magnitude
+// (DESIGN.md section 5), kept as the checked alternative and never the default.  Also fetches the first byte
+// of the first `nranks` rows, where a rank marks a slice that failed to decode.
+inline int device_digest(mpvss_ctx* ctx, const uint8_t* dev_rows_ordered, size_t n_total, int nranks, const Geom& g,
+                         uint8_t digest[32]) {
+  DevBuf& dd = ctx->buf(20);
+  MPVSS_CUDA(ctx, dd.ensure(32));
+  shadev::BoxHashArgs A{dev_rows_ordered, (uint32_t)g.row(), (uint32_t)g.frame(), (uint32_t)n_total, dd.as<uint8_t>()};
+  MPVSS_CUDA(ctx, shadev::launch_box_hash(A, ctx->stream));
+  const size_t marks = std::min<size_t>((size_t)nranks, n_total);
+  MPVSS_CUDA(ctx, ctx->h_frames.ensure(marks * g.row()));
+  MPVSS_CUDA(ctx, cudaMemcpy2DAsync(ctx->h_frames.as<uint8_t>(), g.row(), dev_rows_ordered, g.row(), 1, marks,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(digest, dd.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPVSS_OK;
 }
 
 // Copy the transcript rows from the device (ctx->stream, after everything queued there) in chunks and hash them

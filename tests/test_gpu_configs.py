@@ -113,6 +113,45 @@ def test_scalar_poly_eval_all_groups():
         assert g.scalar_poly_eval(co, pos) == [pvss.poly_eval_mod(co, p, og.order()) for p in pos]
 
 
+@pytest.mark.parametrize("gname,n,t", [("modp", 700, 5), ("secp256k1", 300, 7), ("ristretto255", 300, 7)])
+def test_device_side_transcripts_match_the_host_hash(gname, n, t):
+    """SURVEY 8 f1.  (a) 'device_hash': the whole-box transcript as one SHA-256 chain on the device gives the digest
+    and verdict of the host pass (n = 700 ModpGroup rows contain frames shorter than 256 bytes with probability
+    1 - (255/256)^2800); (b) the per-share transcripts of extract_secret_share / verify_share are always hashed on
+    the device: a changed challenge, response or share is rejected share by share."""
+    og = GROUPS[gname]()
+    g = m.Group(gname)
+    sks = synth.private_keys(9, n, gname, og.order(), g.codec.key_bound)
+    co = synth.coefficients(9, t, og.order())
+    ws = synth.witnesses(9, n, og.order())
+    d = m.Participant(g)
+    pks = g.fixed_base_exp(sks)
+    box = d.distribute_secret(SECRET, pks, t, coeffs=co, witnesses=ws)
+    host, dev = {}, {}
+    assert d.verify_distribution_shares(box, trace=host) is True
+    bad = copy.copy(box)
+    bad.responses = dict(box.responses)
+    k3 = g.codec.key(pks[3])
+    bad.responses[k3] = (bad.responses[k3] + 1) % og.order()
+    g.ctx.set_int("device_hash", 1)
+    try:
+        assert d.verify_distribution_shares(box, trace=dev) is True
+        assert dev["digest"] == host["digest"]
+        assert d.verify_distribution_shares(bad) is False
+    finally:
+        g.ctx.set_int("device_hash", 0)
+    # per-share proofs (bit-exact against the oracle in test_gpu_*::test_full_round_bit_exact): accepted as dealt,
+    # rejected share by share when the challenge, the response or the share is changed
+    k = 40
+    sbs = d.extract_secret_shares(box, sks[:k], ws[:k])
+    assert all(d.verify_shares(sbs, box, pks[:k]))
+    sbs[1].challenge = (sbs[1].challenge + 1) % og.order()
+    sbs[2].response = (sbs[2].response + 1) % og.order()
+    sbs[4].share = sbs[5].share
+    ok = d.verify_shares(sbs, box, pks[:k])
+    assert ok == [i not in (1, 2, 4) for i in range(k)]
+
+
 def test_modp_input_validation_flag(modp_group):
     """'validate' tunable: elements outside (0, q) or outside the order-g subgroup make the
     box verify as false; the reference (and the default here) checks nothing (modp.rs:154-156)."""
