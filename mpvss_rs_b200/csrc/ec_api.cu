@@ -889,10 +889,14 @@ struct Ec {
     MPVSS_TRY(h2d(ctx, dpos, pos.data(), k * 4));
     MPVSS_CUDA(ctx, dlam.ensure(k * 32));
     ec::LagrangeArgs LA{KN(ctx), dpos.as<uint32_t>(), dlam.as<uint32_t>(), (uint32_t)k};
+    timing_begin(ctx);  // the Lagrange kernel counts towards the kernel time of the call
     MPVSS_CUDA(ctx, ec::launch_lagrange(LA, ctx->stream));
+    MPVSS_TRY(timing_end(ctx));
+    const float ms_lambda = ctx->last_ms;
     uint8_t gs[EB];
     MPVSS_TRY(multi_exp_limbs(ctx, shares, dlam.as<uint32_t>(), nullptr, k, gs));
     ctx->last_launches += 1;
+    ctx->last_ms += ms_lambda;
     big::Int mask;
     if (!T::mask_of(gs, ctx->ec_order, &mask))
       return mpvss_fail(ctx, MPVSS_ERR_ENCODING, "reconstruct: SHA-256(G^s) is not a canonical scalar");

@@ -361,6 +361,16 @@ struct LagrangeArgs {
   uint32_t* out;        // k x 8 limbs
   uint32_t k;
 };
+// acc <- acc * f for a 256-bit plain integer and a 32-bit factor (the caller keeps the product below 2^256)
+MP_DEV void mul_small(uint32_t (&acc)[8], uint32_t f) {
+  uint32_t carry = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint64_t t = (uint64_t)acc[i] * f + carry;
+    acc[i] = (uint32_t)t;
+    carry = (uint32_t)(t >> 32);
+  }
+}
 MP_DEV void lagrange_body(const LagrangeArgs& A, uint32_t tid) {
   if (tid >= A.k) return;
   using namespace fp256;
@@ -368,20 +378,31 @@ MP_DEV void lagrange_body(const LagrangeArgs& A, uint32_t tid) {
   const uint32_t xi = A.pos[tid];
   Fe num = mont_one(N), den = mont_one(N);
   bool negative = false;
+  // The factors are 32-bit numbers: eight of them are multiplied as plain integers (8 MACs each) before one
+  // Montgomery product folds them into the running value -- a quarter of the field products of the
+  // factor-by-factor loop, which was 5 ms of dependent products per thread at k = 2731.
+  Fe na = fe_zero(), da = fe_zero();
+  na.v[0] = da.v[0] = 1;
+  uint32_t pending = 0;
 #pragma unroll 1
   for (uint32_t j = 0; j < A.k; ++j) {
     if (j == tid) continue;
-    uint32_t xj = A.pos[j];
-    Fe a = fe_zero(), d = fe_zero();
-    a.v[0] = xj;
-    if (xj < xi) {
-      negative = !negative;
-      d.v[0] = xi - xj;
-    } else {
-      d.v[0] = xj - xi;
+    const uint32_t xj = A.pos[j];
+    if (xj < xi) negative = !negative;
+    mul_small(na.v, xj);
+    mul_small(da.v, xj < xi ? xi - xj : xj - xi);
+    if (++pending == 8) {
+      num = mul(num, to_mont(na, N), N);
+      den = mul(den, to_mont(da, N), N);
+      na = fe_zero();
+      da = fe_zero();
+      na.v[0] = da.v[0] = 1;
+      pending = 0;
     }
-    num = mul(num, to_mont(a, N), N);
-    den = mul(den, to_mont(d, N), N);
+  }
+  if (pending) {
+    num = mul(num, to_mont(na, N), N);
+    den = mul(den, to_mont(da, N), N);
   }
   Fe lam = mul(num, inv(den, N), N);  // den = 0 (duplicate position) -> lambda = 0, as ristretto255.rs falls back
   if (negative) lam = neg(lam, N);

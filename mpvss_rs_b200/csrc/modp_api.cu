@@ -1112,10 +1112,15 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
   const uint32_t* Kg = ctx->consts_g.as<uint32_t>();
   modp::LagrangeArgs LA{dord.as<uint32_t>(), dpos.as<uint32_t>(), dnum.as<uint32_t>(), dden.as<uint32_t>(),
                         dneg.as<uint32_t>(), (uint32_t)k};
+  timing_begin(ctx);  // the Lagrange part counts towards the kernel time of the call
   MPVSS_CUDA(ctx, modp::launch_lagrange(LA, ctx->stream));
+  timing_launch(ctx);
   MPVSS_TRY(dev_exp2(ctx, Kg, dden.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(gm2.data(), EB, 1), nullptr, 0,
                      nullptr, 0, 0, k, dinv.as<uint32_t>()));
   MPVSS_TRY(dev_mul(ctx, Kg, dnum.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 0, k, dlam.as<uint32_t>()));
+  MPVSS_TRY(timing_end(ctx));
+  const float ms_lambda = ctx->last_ms;
+  const int launches_lambda = ctx->last_launches;
   std::vector<uint32_t> negf(k);
   MPVSS_TRY(d2h(ctx, lam.data(), dlam, k * EB));
   MPVSS_TRY(d2h(ctx, negf.data(), dneg, k * 4));
@@ -1127,6 +1132,8 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
   }
   uint8_t gs[EB];
   MPVSS_TRY(multi_exp(ctx, shares, lam.data(), k, gs));
+  ctx->last_ms += ms_lambda;
+  ctx->last_launches += launches_lambda;
   uint8_t tmp[EB], hs[32];
   size_t len = min_be(gs, tmp);
   sha2::sha256(tmp, len, hs);

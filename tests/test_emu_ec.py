@@ -185,17 +185,26 @@ def test_scalar_kernels(L, order):
     L.emu_ec_poly(eu.P(MN), eu.P(np.concatenate([eu.to_limbs(x, 8) for x in co])), t, eu.P(pos), n, eu.P(o))
     for i in range(n):
         assert eu.from_limbs(o[8 * i:8 * i + 8]) == pvss.poly_get_value(co, positions[i]) % order
-    vals = [1, 3, 5, 6, 40]
-    k = len(vals)
-    o = np.zeros(8 * k, dtype=np.uint32)
-    L.emu_ec_lagrange(eu.P(MN), eu.P(np.array(vals, dtype=np.uint32)), k, eu.P(o))
-    for i, xi in enumerate(vals):
-        num = den = 1
-        for xj in vals:
-            if xj != xi:
-                num = num * xj % order
-                den = den * (xj - xi) % order
-        assert eu.from_limbs(o[8 * i:8 * i + 8]) == num * pow(den, -1, order) % order
+    # Lagrange coefficients: factors are folded eight at a time (plain 256-bit product, then one field product):
+    # cover fewer than 8, exactly 8 + 1, several folds with a remainder, and factors near 2^31 (248-bit products)
+    big = (1 << 31) - 1
+    for vals in ([1, 3, 5, 6, 40], list(range(1, 10)), [big - 7 * j for j in range(18)] + [1, 2],
+                 [rng.randrange(1, 1 << 31) for _ in range(41)], list(range(100, 133))):
+        assert len(set(vals)) == len(vals)
+        k = len(vals)
+        o = np.zeros(8 * k, dtype=np.uint32)
+        L.emu_ec_lagrange(eu.P(MN), eu.P(np.array(vals, dtype=np.uint32)), k, eu.P(o))
+        for i, xi in enumerate(vals):
+            num = den = 1
+            for xj in vals:
+                if xj != xi:
+                    num = num * xj % order
+                    den = den * (xj - xi) % order
+            assert eu.from_limbs(o[8 * i:8 * i + 8]) == num * pow(den, -1, order) % order
+    dup = [4, 9, 4, 11]           # duplicate position: zero denominator, lambda = 0 (ristretto255.rs:1983-1989)
+    o = np.zeros(8 * 4, dtype=np.uint32)
+    L.emu_ec_lagrange(eu.P(MN), eu.P(np.array(dup, dtype=np.uint32)), 4, eu.P(o))
+    assert eu.from_limbs(o[0:8]) == 0 and eu.from_limbs(o[16:24]) == 0
     xs = [rng.randrange(order) for _ in range(5)] + [0]
     o = np.zeros(8 * 6, dtype=np.uint32)
     st = np.zeros(6, dtype=np.uint32)

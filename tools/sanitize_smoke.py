@@ -17,6 +17,9 @@ for name in ("modp", "secp256k1", "ristretto255"):
     sbs = d.extract_secret_shares(box, sks, synth.witnesses(2, n, c.key_bound))
     assert all(d.verify_shares(sbs, box, pks))
     assert d.reconstruct(sbs[:t], box) == 424242
+    g.ctx.set_int("device_hash", 1)     # the whole-box transcript through the device-side SHA-256 as well
+    assert d.verify_distribution_shares(box)
+    g.ctx.set_int("device_hash", 0)
     if name == "modp":
         for tpi in (4, 16, 8):
             g.ctx.set_int("modp_tpi", tpi)
