@@ -10,6 +10,7 @@
 //   U mask                        participant.rs:267-272, 512-518
 //   Lagrange exponents            participant.rs:526-561, util.rs:47-64
 #include <algorithm>
+#include <cstdlib>
 #include "ctx.h"
 #include "modp_chain.h"
 #include "modp_launch.h"
@@ -399,8 +400,14 @@ static int dev_horner(mpvss_ctx* ctx, const PlanDev& P, const uint32_t* comm, De
     MPVSS_CUDA(ctx, tbuf.ensure((size_t)(P.K - 1) * n * EB));
     h = hbuf.as<uint32_t>();
   }
+  // Two instantiations of the launch exist: per-CTA (first, steps) arrays, and loop bounds taken from the kernel
+  // parameter t (K = 1 only).  Measured at n = 4096, t = 2731 on the same box, alternating: arrays 217.4 ms,
+  // parameter bounds 220.2 ms (the code of round 2's first half), so the arrays are used always;
+  // MPVSS_HORNER_UNIFORM=1 selects the other one for comparison runs.
+  static const bool uniform = getenv("MPVSS_HORNER_UNIFORM") != nullptr;
+  const bool arrays = P.K > 1 || !uniform;
   modp::HornerArgs A{Kq, cm.as<uint32_t>(), P.ops, P.slot, P.nops, h, (uint32_t)t, (uint32_t)P.n_padded, 0,
-                     (uint32_t)P.wpc, P.first, P.steps};
+                     (uint32_t)P.wpc, arrays ? P.first : nullptr, arrays ? P.steps : nullptr};
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h0, ctx->stream));
   MPVSS_CUDA(ctx, modp::launch_horner(P.tpi, A, ctx->modp_np1, ctx->stream));
   MPVSS_CUDA(ctx, cudaEventRecord(ctx->ev_h1, ctx->stream));

@@ -148,8 +148,10 @@ constexpr int horner_smem_words = (32 / TPI) * (HC_GSTRIDE + HC_OPS / 2);
 // NP1: the modulus satisfies -q^-1 = 1 mod 2^32 (true for the RFC 3526 prime, whose low 64 bits are all
 // ones), so the Montgomery digit is the low limb itself and one multiply leaves the per-digit critical path.
 // CHUNKED: first / steps come from the per-CTA arrays; otherwise they are t - 1, a kernel parameter, and the
-// loop control stays in uniform registers (passing them in as values loaded from memory moved it to vector
-// registers and cost 2.3 % of the launch: 220.2 -> 225.3 ms at n = 4096).
+// loop control stays in uniform registers.  The shape of this loop moves the launch by a few per cent although
+// it is outside the product: bounds passed in as two values and compared against each other 225.3 ms, bounds
+// from the parameter 220.2 ms, per-CTA arrays with the count-down-to-zero loop on a shifted base (below)
+// 217.4 ms at n = 4096, t = 2731 -- the last one is what the library launches.
 template <int TPI, bool NP1 = false, bool CHUNKED = false>
 MP_DEV void horner_body(const HornerArgs& A, uint32_t wg, uint32_t* wsm, uint32_t nops, uint32_t cta = 0) {
   const uint32_t first = CHUNKED ? A.cfirst[cta] : A.t - 1, steps = CHUNKED ? A.csteps[cta] : A.t - 1;
