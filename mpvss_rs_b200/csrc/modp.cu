@@ -186,7 +186,8 @@ cudaError_t launch_poly(const PolyArgs& A, cudaStream_t s) {
 
 cudaError_t launch_lagrange(const LagrangeArgs& A, cudaStream_t s) {
   if (A.k == 0) return cudaErrorInvalidValue;
-  lagrange_kernel<<<(A.k + 63) / 64, 64, 0, s>>>(A);
+  const uint32_t threads = 2u * (A.parts ? A.parts : 1u) * A.k;
+  lagrange_kernel<<<(threads + 63) / 64, 64, 0, s>>>(A);
   return cudaGetLastError();
 }
 

@@ -1114,25 +1114,33 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
   MPVSS_TRY(h2d(ctx, dpos, pos.data(), k * 4));
   MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
   MPVSS_TRY(h2d(ctx, de, gm2.data(), EB));
-  for (DevBuf* b : {&dnum, &dden, &dinv, &dlam}) MPVSS_CUDA(ctx, b->ensure(k * EB));
-  MPVSS_CUDA(ctx, dneg.ensure(k * 4));
+  // the k-term products are cut into `parts` ranges (more, shorter threads), multiplied together mod g below
+  const size_t parts = k >= 64 ? 8 : 1;
+  for (DevBuf* b : {&dnum, &dden}) MPVSS_CUDA(ctx, b->ensure(parts * k * EB));
+  for (DevBuf* b : {&dinv, &dlam}) MPVSS_CUDA(ctx, b->ensure(k * EB));
+  MPVSS_CUDA(ctx, dneg.ensure(parts * k * 4));
   const uint32_t* Kg = ctx->consts_g.as<uint32_t>();
   modp::LagrangeArgs LA{dord.as<uint32_t>(), dpos.as<uint32_t>(), dnum.as<uint32_t>(), dden.as<uint32_t>(),
-                        dneg.as<uint32_t>(), (uint32_t)k};
+                        dneg.as<uint32_t>(), (uint32_t)k, (uint32_t)parts};
   timing_begin(ctx);  // the Lagrange part counts towards the kernel time of the call
   MPVSS_CUDA(ctx, modp::launch_lagrange(LA, ctx->stream));
   timing_launch(ctx);
+  for (size_t half = parts / 2; half >= 1; half /= 2)  // rows [0, half k) *= rows [half k, 2 half k), mod g
+    for (DevBuf* b : {&dnum, &dden})
+      MPVSS_TRY(dev_mul(ctx, Kg, b->as<uint32_t>(), EW, b->as<uint32_t>() + half * k * EW, EW, 0, half * k,
+                        b->as<uint32_t>()));
   MPVSS_TRY(dev_exp2(ctx, Kg, dden.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(gm2.data(), EB, 1), nullptr, 0,
                      nullptr, 0, 0, k, dinv.as<uint32_t>()));
   MPVSS_TRY(dev_mul(ctx, Kg, dnum.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 0, k, dlam.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   const float ms_lambda = ctx->last_ms;
   const int launches_lambda = ctx->last_launches;
-  std::vector<uint32_t> negf(k);
+  std::vector<uint32_t> negf(parts * k);
   MPVSS_TRY(d2h(ctx, lam.data(), dlam, k * EB));
-  MPVSS_TRY(d2h(ctx, negf.data(), dneg, k * 4));
+  MPVSS_TRY(d2h(ctx, negf.data(), dneg, parts * k * 4));
   MPVSS_TRY(sync(ctx));
   for (size_t i = 0; i < k; ++i) {
+    for (size_t p = 1; p < parts; ++p) negf[i] ^= negf[p * k + i];
     if (!negf[i]) continue;
     big::Int l = big::from_le(lam.data() + i * EB, EB);
     if (!big::is_zero(l)) big::to_le(big::sub(ctx->qm1, l), lam.data() + i * EB, EB);

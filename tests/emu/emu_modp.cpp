@@ -128,9 +128,10 @@ extern "C" int emu_modp_poly(const uint32_t* coeffs, uint32_t t, const uint32_t*
   return 0;
 }
 
+// num / den / negative: parts x k rows (part p of position i in row p * k + i)
 extern "C" int emu_modp_lagrange(const uint32_t* order, const uint32_t* pos, uint32_t k, uint32_t* num, uint32_t* den,
-                                 uint32_t* negative) {
-  modp::LagrangeArgs A{order, pos, num, den, negative, k};
-  for (uint32_t i = 0; i < k; ++i) modp::lagrange_body(A, i);
+                                 uint32_t* negative, uint32_t parts) {
+  modp::LagrangeArgs A{order, pos, num, den, negative, k, parts};
+  for (uint32_t i = 0; i < 2 * (parts ? parts : 1) * k + 3; ++i) modp::lagrange_body(A, i);
   return 0;
 }

@@ -301,21 +301,43 @@ def test_scalar_polynomial_kernel(lib):
         assert eu.from_limbs(out[64 * i:64 * i + 64]) == pvss.poly_get_value(co, x) % order, i
 
 
-def test_lagrange_kernel(lib):
-    """num_i, den_i mod (q-1) and the sign, against util.rs:47-64 (oracle lagrange_coefficient)."""
+@pytest.mark.parametrize("parts", [1, 3, 8])
+def test_lagrange_kernel(lib, parts):
+    """num_i, den_i mod (q-1) and the sign, against util.rs:47-64 (oracle lagrange_coefficient); the products are
+    cut into `parts` ranges of j whose partial products (rows part * k + i) multiply to the full one, the partial
+    signs XOR to the sign.  parts = 8 with k = 11 leaves empty ranges (product 1)."""
     from oracle.groups import lagrange_coefficient
+    _lagrange_case(lib, parts, [1, 3, 4, 9, 200, 4096, 65536, 7, 12345, 2, 77], lagrange_coefficient)
+    # positions near 2^31: the oracle's restatement of util.rs scans 1..max and cannot be asked here
+    _lagrange_case(lib, parts, [(1 << 31) - 1, 5, (1 << 30) + 3, 17, (1 << 31) - 9, 2, 1, 99, 100], None)
+
+
+def _lagrange_case(lib, parts, values, lagrange_coefficient):
     order = Q - 1
-    values = [1, 3, 4, 9, 200, 4096, 65536, 7]
     k = len(values)
-    num, den = np.zeros(64 * k, dtype=np.uint32), np.zeros(64 * k, dtype=np.uint32)
-    neg = np.zeros(k, dtype=np.uint32)
+    num, den = np.zeros(64 * k * parts, dtype=np.uint32), np.zeros(64 * k * parts, dtype=np.uint32)
+    neg = np.zeros(k * parts, dtype=np.uint32)
     assert lib.emu_modp_lagrange(eu.P(eu.to_limbs(order)), eu.P(np.array(values, dtype=np.uint32)), k, eu.P(num),
-                                 eu.P(den), eu.P(neg)) == 0
+                                 eu.P(den), eu.P(neg), parts) == 0
     for i, x in enumerate(values):
-        n_, d_ = lagrange_coefficient(x, values)
-        assert eu.from_limbs(num[64 * i:64 * i + 64]) == abs(n_) % order
-        assert eu.from_limbs(den[64 * i:64 * i + 64]) == abs(d_) % order
-        assert bool(neg[i]) == (n_ * d_ < 0)
+        pn = pd = 1
+        sign = 0
+        for p in range(parts):
+            r = p * k + i
+            pn = pn * eu.from_limbs(num[64 * r:64 * r + 64]) % order
+            pd = pd * eu.from_limbs(den[64 * r:64 * r + 64]) % order
+            sign ^= int(neg[r])
+        # the oracle's pair is reduced by its gcd; compare the quotient instead of the two products
+        full_n = full_d = 1
+        for y in values:
+            if y != x:
+                full_n, full_d = full_n * y, full_d * abs(y - x)
+        assert pn == full_n % order and pd == full_d % order
+        assert bool(sign) == (sum(1 for y in values if y < x) % 2 == 1)
+        if lagrange_coefficient is not None:
+            n_, d_ = lagrange_coefficient(x, values)
+            assert full_n * abs(d_) == full_d * abs(n_)       # same rational number as util.rs returns
+            assert bool(sign) == (n_ * d_ < 0)
 
 
 def test_bucket_multi_exponentiation(lib):
