@@ -204,4 +204,87 @@ inline bool modinv(const Int& a, const Int& m, Int* out) {
   return true;
 }
 
+// a^-1 mod m for an ODD modulus by the binary extended Euclidean algorithm on fixed-width arrays: shifts and
+// subtractions only, no division and no allocation inside the loop (a 2047-bit inverse in well under a
+// millisecond, against several for the division-based modinv above).  Used for the one inversion at the root of a
+// device-side batch inversion.  Returns false when gcd(a, m) != 1.
+inline bool modinv_odd(const Int& a_in, const Int& m, Int* out) {
+  if (m.empty() || !(m[0] & 1u)) return false;
+  const size_t n = m.size() + 1;  // one spare limb for x + m
+  auto is1 = [&](const std::vector<uint32_t>& x) {
+    if (x[0] != 1) return false;
+    for (size_t i = 1; i < n; ++i)
+      if (x[i]) return false;
+    return true;
+  };
+  auto is0 = [&](const std::vector<uint32_t>& x) {
+    for (size_t i = 0; i < n; ++i)
+      if (x[i]) return false;
+    return true;
+  };
+  auto shr = [&](std::vector<uint32_t>& x) {
+    for (size_t i = 0; i + 1 < n; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[n - 1] >>= 1;
+  };
+  auto addv = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) {
+    uint64_t c = 0;
+    for (size_t i = 0; i < n; ++i) {
+      c += (uint64_t)x[i] + y[i];
+      x[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  };
+  auto subv = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) {  // x -= y, returns borrow
+    uint64_t b = 0;
+    for (size_t i = 0; i < n; ++i) {
+      uint64_t d = (uint64_t)x[i] - y[i] - b;
+      x[i] = (uint32_t)d;
+      b = (d >> 32) & 1u;
+    }
+    return b != 0;
+  };
+  auto geq = [&](const std::vector<uint32_t>& x, const std::vector<uint32_t>& y) {
+    for (size_t i = n; i-- > 0;)
+      if (x[i] != y[i]) return x[i] > y[i];
+    return true;
+  };
+  auto fixed = [&](const Int& v) {
+    std::vector<uint32_t> r(n, 0);
+    for (size_t i = 0; i < v.size() && i < n; ++i) r[i] = v[i];
+    return r;
+  };
+  std::vector<uint32_t> M = fixed(m), u = fixed(mod(a_in, m)), v = M, x1(n, 0), x2(n, 0);
+  if (is0(u)) return false;
+  x1[0] = 1;
+  auto halve = [&](std::vector<uint32_t>& x) {  // x / 2 mod m
+    if (x[0] & 1u) addv(x, M);
+    shr(x);
+  };
+  auto submod_v = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) {  // x = x - y mod m (x, y < m)
+    if (subv(x, y)) addv(x, M);
+  };
+  while (!is1(u) && !is1(v)) {
+    while (!(u[0] & 1u)) {
+      shr(u);
+      halve(x1);
+    }
+    while (!(v[0] & 1u)) {
+      shr(v);
+      halve(x2);
+    }
+    if (geq(u, v)) {
+      subv(u, v);
+      submod_v(x1, x2);
+      if (is0(u)) return false;  // u == v > 1: common factor
+    } else {
+      subv(v, u);
+      submod_v(x2, x1);
+    }
+  }
+  Int r(is1(u) ? x1 : x2);
+  trim(r);
+  *out = r;
+  return true;
+}
+
 }  // namespace big

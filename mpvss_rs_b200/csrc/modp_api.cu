@@ -951,6 +951,53 @@ int distribute(mpvss_ctx* ctx, size_t n_total, size_t t, const uint8_t* secret, 
 }
 
 // ------------------------------------------------------------------ extract ----
+// out[i] = v[i]^-1 mod g for n device values, none of them 0 mod g (Montgomery's trick as a tree): products of
+// pairs (m, m + h) level by level on the device, ONE inversion of the root on the host (big::modinv_odd), and the
+// tree walked back down with two products per node.  3 n products and 36 small launches instead of n
+// exponentiations by g - 2, each 2560 products deep (6 - 8 ms at n = 2731 for a launch that is one warp per
+// scheduler and therefore latency-bound).  v and out may not overlap.
+static int dev_batch_inverse_g(mpvss_ctx* ctx, const uint32_t* v, size_t n, uint32_t* out) {
+  const uint32_t* Kg = ctx->consts_g.as<uint32_t>();
+  size_t N = 1, L = 0;
+  while (N < n) N *= 2, ++L;
+  DevBuf &tree = ctx->buf(21), &ia = ctx->buf(22), &ib = ctx->buf(23);
+  MPVSS_CUDA(ctx, tree.ensure(2 * N * EB));
+  MPVSS_CUDA(ctx, ia.ensure(N * EB));
+  MPVSS_CUDA(ctx, ib.ensure(N * EB));
+  uint32_t* T = tree.as<uint32_t>();
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(T, v, n * EB, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (N > n) {  // pad with ones
+    std::vector<uint32_t> ones((N - n) * EW, 0);
+    for (size_t i = 0; i < N - n; ++i) ones[i * EW] = 1;
+    MPVSS_CUDA(ctx, cudaMemcpyAsync(T + n * EW, ones.data(), (N - n) * EB, cudaMemcpyHostToDevice, ctx->stream));
+    MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `ones` is pageable and goes out of scope
+  }
+  std::vector<size_t> off(L + 1, 0);
+  for (size_t l = 1; l <= L; ++l) off[l] = off[l - 1] + (N >> (l - 1));
+  for (size_t l = 1; l <= L; ++l) {
+    const size_t h = N >> l;
+    MPVSS_TRY(dev_mul(ctx, Kg, T + off[l - 1] * EW, EW, T + (off[l - 1] + h) * EW, EW, 0, h, T + off[l] * EW));
+  }
+  uint8_t root[EB];
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(root, T + off[L] * EW, EB, cudaMemcpyDeviceToHost, ctx->stream));
+  MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  big::Int inv;
+  if (!big::modinv_odd(big::from_le(root, EB), ctx->g, &inv))
+    return mpvss_fail(ctx, MPVSS_ERR_ARG, "batch inversion: an element is 0 modulo the subgroup order");
+  big::to_le(inv, root, EB);
+  uint32_t *cur = ia.as<uint32_t>(), *nxt = ib.as<uint32_t>();
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(cur, root, EB, cudaMemcpyHostToDevice, ctx->stream));
+  MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t l = L; l >= 1; --l) {  // inverse of a child = inverse of the parent * the sibling
+    const size_t h = N >> l;
+    MPVSS_TRY(dev_mul(ctx, Kg, cur, EW, T + (off[l - 1] + h) * EW, EW, 0, h, nxt));
+    MPVSS_TRY(dev_mul(ctx, Kg, cur, EW, T + off[l - 1] * EW, EW, 0, h, nxt + h * EW));
+    std::swap(cur, nxt);
+  }
+  MPVSS_CUDA(ctx, cudaMemcpyAsync(out, cur, n * EB, cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPVSS_OK;
+}
+
 // Per-share Fiat-Shamir transcripts on the device: frame (h1, h2, a1, a2) per share, one SHA-256
 // chain per thread, and hash_to_scalar's second SHA-256 (modp.rs:142-148; 256 < 2047 bits, so no reduction):
 // challenges as `stride`-limb little-endian scalars (64 = boundary scalars, 8 = just the hash).  The launches are
@@ -985,26 +1032,26 @@ int extract_shares(mpvss_ctx* ctx, size_t n, const uint8_t* private_keys, const 
   const uint32_t* G = ctx->gens.as<uint32_t>();
   // sk^-1 mod (q-1), q-1 = 2g (util.rs:33-41 via participant.rs:314): by CRT it is the odd
   // representative of sk^(g-2) mod g; it exists iff sk is odd and not a multiple of g.
-  std::vector<uint8_t> skg(n * EB), e(EB);
+  std::vector<uint8_t> skg(n * EB);
   std::vector<int> st(n, MPVSS_OK);
   for (size_t i = 0; i < n; ++i) {
     big::Int sk = big::mod(big::from_le(private_keys + i * EB, EB), ctx->qm1);
     big::Int r = big::mod(sk, ctx->g);
-    if (!big::is_odd(sk) || big::is_zero(r)) st[i] = MPVSS_ERR_NOT_INVERTIBLE;
+    if (!big::is_odd(sk) || big::is_zero(r)) {
+      st[i] = MPVSS_ERR_NOT_INVERTIBLE;
+      r = big::from_u64(1);  // keeps the batch inversion below defined; this instance's outputs are not used
+    }
     big::to_le(r, skg.data() + i * EB, EB);
   }
-  big::to_le(big::sub(ctx->g, big::from_u64(2)), e.data(), EB);
-  DevBuf &dsk = ctx->buf(0), &dskg = ctx->buf(1), &de = ctx->buf(2), &dinv = ctx->buf(3), &dw = ctx->buf(4),
+  DevBuf &dsk = ctx->buf(0), &dskg = ctx->buf(1), &dinv = ctx->buf(3), &dw = ctx->buf(4),
          &dY = ctx->buf(5), &dpk = ctx->buf(6), &dS = ctx->buf(7), &dA1 = ctx->buf(8), &dA2 = ctx->buf(9);
   MPVSS_TRY(h2d(ctx, dsk, private_keys, n * EB));
   MPVSS_TRY(h2d(ctx, dskg, skg.data(), n * EB));
-  MPVSS_TRY(h2d(ctx, de, e.data(), EB));
   MPVSS_TRY(h2d(ctx, dw, witnesses, n * EB));
   MPVSS_TRY(h2d(ctx, dY, enc_shares, n * EB));
   for (DevBuf* b : {&dinv, &dpk, &dS, &dA1, &dA2}) MPVSS_CUDA(ctx, b->ensure(n * EB));
   timing_begin(ctx);
-  MPVSS_TRY(dev_exp2(ctx, Kg, dskg.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(e.data(), EB, 1), nullptr, 0,
-                     nullptr, 0, 0, n, dinv.as<uint32_t>()));
+  MPVSS_TRY(dev_batch_inverse_g(ctx, dskg.as<uint32_t>(), n, dinv.as<uint32_t>()));  // one inversion for all n
   MPVSS_TRY(timing_end(ctx));
   std::vector<uint8_t> inv(n * EB);
   MPVSS_TRY(d2h(ctx, inv.data(), dinv, n * EB));
@@ -1107,13 +1154,11 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
       return mpvss_fail(ctx, MPVSS_ERR_ARG, "duplicate position");
   }
   for (size_t i = 0; i < ctx->qm1.size(); ++i) order[i] = ctx->qm1[i];
-  std::vector<uint8_t> gm2(EB), lam(k * EB);
-  big::to_le(big::sub(ctx->g, big::from_u64(2)), gm2.data(), EB);
+  std::vector<uint8_t> lam(k * EB);
   DevBuf &dpos = ctx->buf(12), &dord = ctx->buf(13), &dnum = ctx->buf(14), &dden = ctx->buf(15), &dneg = ctx->buf(16),
-         &de = ctx->buf(17), &dinv = ctx->buf(18), &dlam = ctx->buf(19);
+         &dinv = ctx->buf(18), &dlam = ctx->buf(19);
   MPVSS_TRY(h2d(ctx, dpos, pos.data(), k * 4));
   MPVSS_TRY(h2d(ctx, dord, order.data(), EB));
-  MPVSS_TRY(h2d(ctx, de, gm2.data(), EB));
   // the k-term products are cut into `parts` ranges (more, shorter threads), multiplied together mod g below
   const size_t parts = k >= 64 ? 8 : 1;
   for (DevBuf* b : {&dnum, &dden}) MPVSS_CUDA(ctx, b->ensure(parts * k * EB));
@@ -1129,8 +1174,8 @@ int reconstruct(mpvss_ctx* ctx, size_t k, const int64_t* positions, const uint8_
     for (DevBuf* b : {&dnum, &dden})
       MPVSS_TRY(dev_mul(ctx, Kg, b->as<uint32_t>(), EW, b->as<uint32_t>() + half * k * EW, EW, 0, half * k,
                         b->as<uint32_t>()));
-  MPVSS_TRY(dev_exp2(ctx, Kg, dden.as<uint32_t>(), EW, de.as<uint32_t>(), 0, windows_for(gm2.data(), EB, 1), nullptr, 0,
-                     nullptr, 0, 0, k, dinv.as<uint32_t>()));
+  // den^-1 mod g: the denominators are products of non-zero integers below 2^31 < g, so none is 0 mod g
+  MPVSS_TRY(dev_batch_inverse_g(ctx, dden.as<uint32_t>(), k, dinv.as<uint32_t>()));
   MPVSS_TRY(dev_mul(ctx, Kg, dnum.as<uint32_t>(), EW, dinv.as<uint32_t>(), EW, 0, k, dlam.as<uint32_t>()));
   MPVSS_TRY(timing_end(ctx));
   const float ms_lambda = ctx->last_ms;

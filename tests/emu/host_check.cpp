@@ -23,6 +23,12 @@ int hc_modinv(const uint8_t* a, size_t alen, const uint8_t* m, size_t mlen, uint
   big::to_le(r, out, outlen);
   return 0;
 }
+int hc_modinv_odd(const uint8_t* a, size_t alen, const uint8_t* m, size_t mlen, uint8_t* out, size_t outlen) {
+  big::Int r;
+  if (!big::modinv_odd(big::from_le(a, alen), big::from_le(m, mlen), &r)) return 1;
+  big::to_le(r, out, outlen);
+  return 0;
+}
 void hc_sha256(const uint8_t* d, size_t n, size_t chunk, uint8_t* out) {
   sha2::Sha256 h;
   for (size_t i = 0; i < n; i += chunk) h.update(d + i, i + chunk <= n ? chunk : n - i);

@@ -19,6 +19,7 @@ def build():
     L.hc_divmod.argtypes = [_p, _s, _p, _s, _p, _p, _s]
     L.hc_mulmod.argtypes = [_p, _s, _p, _s, _p, _s, _p, _s]
     L.hc_modinv.argtypes = [_p, _s, _p, _s, _p, _s]
+    L.hc_modinv_odd.argtypes = [_p, _s, _p, _s, _p, _s]
     L.hc_sha256.argtypes = [_p, _s, _s, _p]
     L.hc_sha512.argtypes = [_p, _s, _s, _p]
     L.hc_chain_ops.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint16),

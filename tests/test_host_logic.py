@@ -33,6 +33,10 @@ def test_bigint_divmod_modinv_mulmod():
             assert rc == 0 and int.from_bytes(bytes(out), "little") == pow(a, -1, m)
         else:
             assert rc == 1
+        # binary extended Euclid for odd moduli (the root of the device-side batch inversion): same answers
+        out2 = (ctypes.c_uint8 * N)()
+        rc2 = L.hc_modinv_odd(host_util.le(a, N), N, host_util.le(m, N), N, out2, N)
+        assert rc2 == rc and (rc or bytes(out2) == bytes(out))
         c = rng.getrandbits(2048)
         L.hc_mulmod(host_util.le(a, N), N, host_util.le(c, N), N, host_util.le(m, N), N, out, N)
         assert int.from_bytes(bytes(out), "little") == a * c % m
@@ -41,6 +45,17 @@ def test_bigint_divmod_modinv_mulmod():
     assert L.hc_modinv(host_util.le(7, N), N, host_util.le(30, N), N, out, N) == 0
     assert int.from_bytes(bytes(out), "little") == 13
     assert L.hc_modinv(host_util.le(6, N), N, host_util.le(30, N), N, out, N) == 1
+    assert L.hc_modinv_odd(host_util.le(7, N), N, host_util.le(30, N), N, out, N) == 1      # even modulus: refused
+    g = (int("ffffffffffffffffc90fdaa22168c234c4c6628b80dc1cd129024e088a67cc74020bbea63b139b22514a08798e3404dd"
+             "ef9519b3cd3a431b302b0a6df25f14374fe1356d6d51c245e485b576625e7ec6f44c42e9a637ed6b0bff5cb6f406b7ed"
+             "ee386bfb5a899fa5ae9f24117c4b1fe649286651ece45b3dc2007cb8a163bf0598da48361c55d39a69163fa8fd24cf5f"
+             "83655d23dca3ad961c62f356208552bb9ed529077096966d670c354e4abc9804f1746c08ca18217c32905e462e36ce3b"
+             "e39e772c180e86039b2783a2ec07a28fb5c55df06f4c52c9de2bcbf6955817183995497cea956ae515d2261898fa0510"
+             "15728e5a8aacaa68ffffffffffffffff", 16) - 1) // 2
+    for a in (1, 2, g - 1, g - 2, rng.randrange(g), g + 5, 3 * g + 1):
+        assert L.hc_modinv_odd(host_util.le(a, N), N, host_util.le(g, N), N, out, N) == 0
+        assert int.from_bytes(bytes(out), "little") == pow(a, -1, g)
+    assert L.hc_modinv_odd(host_util.le(2 * g, N), N, host_util.le(g, N), N, out, N) == 1   # a = 0 mod m
 
 
 def test_sha2_matches_hashlib():
