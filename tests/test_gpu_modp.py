@@ -162,6 +162,17 @@ def test_tampering_is_rejected(modp_group):
     evbox = dealer.distribute_secret(SECRET, [modp_group.generate_public_key(even_sk)] + pks[1:], t,
                                      coeffs=co, witnesses=ws)
     assert dealer.extract_secret_share(evbox, even_sk, ws[0]) is None
+    # ... and inside a batch it only spoils its own instance: the inverses of the batch come from ONE inversion
+    # (product tree on the device), so the non-invertible key must not leak into its neighbours
+    n = len(sks)
+    got = dealer.extract_secret_shares(evbox, [even_sk] + sks[1:], ws)
+    assert got[0] is None and all(g is not None for g in got[1:])
+    want = dealer.extract_secret_shares(box, sks, ws)
+    for i in range(1, n):            # same keys, witnesses and encrypted shares as in the untouched box
+        assert evbox.shares[modp_group.codec.key(pks[i])] == box.shares[modp_group.codec.key(pks[i])]
+        assert (got[i].publickey, got[i].share, got[i].challenge, got[i].response) == \
+               (want[i].publickey, want[i].share, want[i].challenge, want[i].response)
+    assert all(dealer.verify_shares(got[1:], evbox, pks[1:]))
 
 
 def test_medium_box_against_oracle(modp_group):
