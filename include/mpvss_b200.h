@@ -72,7 +72,8 @@ const char* mpvss_last_error(const mpvss_ctx* ctx);
 /* tunables: "modp_tpi" (lanes per 2048-bit value: 4, 8, 16); "modp_comb" (0/1: fixed-base tables for
  * the two generators); "modp_overlap" (where the X-independent a2 = y^r Y^c runs during
  * verify_distribution: 0 before the X_i launch, 2 beside it on a side stream, 3 (default) beside it as
- * one persistent one-warp CTA per SM, which takes the warp slot the X_i launch leaves idle);
+ * one persistent one-warp CTA per SM, which takes the warp slot the X_i launch leaves idle; the default falls
+ * back to 0 when that slot does not exist, or to 2 for small boxes whose two launches fit the chip together);
  * "modp_chunks" (contiguous chunks per position of the X_i launch, 0 = automatic: more than one only when the
  * launch would leave most of the chip idle); "modp_wpc" (warps per CTA of that launch); "modp_msm" /
  * "msm_threshold" (bucket method for multi_exp / reconstruct); "ec_threads" (thread target of the chunked
