@@ -491,6 +491,7 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c5", action="store_true", help="also time BASELINE config 5 (n=65536 t=43691) [default at 8 GPUs]")
+    ap.add_argument("--no-c5", action="store_true", help="skip config 5 at 8 GPUs (short re-runs)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     n = args.n
@@ -599,7 +600,7 @@ def main():
                           "e2e": {"value": n / (sm["e2e_ms"] * 1e-3), "unit": "shares/s"},
                           "note": "one box of n participants in total, sharded over all ranks"}
         sg.ctx.close()
-    if (args.c5 or world == 8) and args.group == "modp" and not args.no_also:
+    if (args.c5 or world == 8) and not args.no_c5 and args.group == "modp" and not args.no_also:
         # BASELINE config 5: ModpGroup n = 65536, t = 43691, distribute + verify sharded over the ranks
         cg = make_group("modp", True)
         t0 = time.perf_counter()
