@@ -992,6 +992,8 @@ static int dev_batch_inverse_g(mpvss_ctx* ctx, const uint32_t* v, size_t n, uint
   uint32_t *cur = ia.as<uint32_t>(), *nxt = ib.as<uint32_t>();
   MPVSS_CUDA(ctx, cudaMemcpyAsync(cur, root, EB, cudaMemcpyHostToDevice, ctx->stream));
   MPVSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memset(root, 0, EB);  // a function of secret values when the batch holds private keys
+  std::fill(inv.begin(), inv.end(), 0u);
   for (size_t l = L; l >= 1; --l) {  // inverse of a child = inverse of the parent * the sibling
     const size_t h = N >> l;
     MPVSS_TRY(dev_mul(ctx, Kg, cur, EW, T + (off[l - 1] + h) * EW, EW, 0, h, nxt));
