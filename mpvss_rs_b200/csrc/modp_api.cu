@@ -752,7 +752,7 @@ static int verify_kernels(mpvss_ctx* ctx) {
     const size_t holes = (slots - hw % slots) % slots;
     if (holes < (size_t)ctx->sm_count) overlap = 0;
     // Small boxes: when both launches together stay below three warps per scheduler the chip has room for a2
-    // as a regular launch beside the X_i launch (measured, tools/gpu_s2_h.sh: n = 1024, t = 683 36.5 -> 28.5 ms;
+    // as a regular launch beside the X_i launch (measured, tools/small_box_overlap_sweep.sh: n = 1024, t = 683 36.5 -> 28.5 ms;
     // n = 2048, t = 1366 72.9 -> 71.0 ms; at n = 4096 the same mode slows the X_i warps: 265.6 against 256.5 ms)
     if (overlap == 0 && hw + nwarps <= (size_t)12 * (size_t)ctx->sm_count) overlap = 2;
   }
