@@ -430,7 +430,8 @@ class Runner:
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch at n = 4096, t = 2731 on one GPU, from the
 # ncu --set full captures summarised under profiles/ (horner_r02_ncu.txt, ec_horner_*_r02_ncu.txt)
-NCU_TRAFFIC = {"modp": 1277952, "secp256k1": 307200 + 780032, "ristretto255": 275456 + 21468160}
+# (values of the final round-2 captures; DRAM traffic of these launches moves by a few hundred KB from run to run)
+NCU_TRAFFIC = {"modp": 1161472 + 0, "secp256k1": 307712 + 2316544, "ristretto255": 259584 + 26141696}
 
 
 def modp_roofline(m, n_local, imad_lo, imad_wide, peak_src, traffic=None):
